@@ -1,0 +1,41 @@
+"""Build of the in-tree CUDA library (sm_100a only, no multi-arch fallbacks)."""
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libknowhere_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC,-fopenmp,-O3,-mavx2,-mfma", "-shared",
+]
+
+
+def sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    hdr = os.path.join(os.path.dirname(HERE), "include", "knowhere_b200.h")
+    return any(os.path.getmtime(s) > t for s in sources() + [hdr])
+
+
+def build(force=False, verbose=False):
+    """nvcc -> knowhere_b200/libknowhere_b200.so (in-tree, so it travels to the GPU box)."""
+    if not force and not needs_build():
+        return LIB
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB, os.path.join(CSRC, "kb2_capi.cu"), "-lgomp"]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stderr)
+    return LIB

@@ -1,0 +1,346 @@
+// kb2_build.cuh — device-side index construction: k-means, PQ training/encoding, list layout.
+// (SURVEY §8f rank 3 — the step before the search path; kept on the GPU so that a 10M-row
+//  Build() finishes in seconds.)  Hyper-parameters follow the reference:
+//   Clustering: niter=25, max_points_per_centroid=256, seed=1234   F/Clustering.h:22-80
+//   PQ        : M independent k-means, ksub=256, <=256*ksub points  F/impl/ProductQuantizer.cpp:130-200
+//   encoding  : residual to the assigned centroid, nearest sub-centroid per m (first minimum wins)
+//                                                                  F/IndexIVFPQ.cpp:178-200, ProductQuantizer.cpp:220-260
+#pragma once
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <random>
+#include <vector>
+
+#include "kb2_flat.cuh"
+
+namespace kb2 {
+
+// ---------------------------------------------------------------- small kernels
+__global__ void
+iota_kernel(int32_t* out, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int32_t)i;
+}
+__global__ void
+fill_i32_kernel(int32_t* out, int64_t n, int32_t v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = v;
+}
+// out[i][:] = x[idx[i]][:]   (warp per row)
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float* __restrict__ x, const int32_t* __restrict__ idx, int64_t n, int d, int d_out,
+                   float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const int32_t r = idx[i];
+    for (int j = lane; j < d_out; j += kWarp) out[i * d_out + j] = (r >= 0 && j < d) ? x[(int64_t)r * d + j] : 0.f;
+}
+// sub-vector slice: out[i][0..dsub) = x[i][m*dsub .. ) - (cent ? cent[assign[i]][m*dsub..] : 0)
+__global__ void
+slice_residual_kernel(const float* __restrict__ x, const float* __restrict__ cent, const int32_t* __restrict__ assign,
+                      int64_t n, int d, int m, int dsub, float* __restrict__ out) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * dsub) return;
+    const int64_t i = t / dsub;
+    const int j = (int)(t % dsub);
+    float v = x[i * d + m * dsub + j];
+    if (cent) v -= cent[(int64_t)assign[i] * d + m * dsub + j];
+    out[t] = v;
+}
+// argmin over a row of keys (warp per row); first minimum wins like the reference's strict '<'
+__global__ void __launch_bounds__(256)
+argmin_rows_kernel(const float* __restrict__ keys, int64_t ldk, int64_t n, int k, int32_t* __restrict__ out,
+                   float* __restrict__ out_val) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const float* row = keys + i * ldk;
+    float best = INFINITY;
+    int bj = 0x7fffffff;
+    for (int j = lane; j < k; j += kWarp) {
+        const float v = row[j];
+        if (v < best) { best = v; bj = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+        if (ov < best || (ov == best && oj < bj)) { best = ov; bj = oj; }
+    }
+    if (lane == 0) {
+        out[i] = (bj == 0x7fffffff) ? 0 : bj;
+        if (out_val) out_val[i] = best;
+    }
+}
+__global__ void __launch_bounds__(256)
+kmeans_accumulate_kernel(const float* __restrict__ x, const int32_t* __restrict__ assign, int64_t n, int d,
+                         float* __restrict__ sums, int32_t* __restrict__ counts) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const int c = assign[i];
+    for (int j = lane; j < d; j += kWarp) atomicAdd(&sums[(int64_t)c * d + j], x[i * d + j]);
+    if (lane == 0) atomicAdd(&counts[c], 1);
+}
+__global__ void
+kmeans_divide_kernel(float* __restrict__ cent, const float* __restrict__ sums, const int32_t* __restrict__ counts,
+                     int k, int d) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)k * d) return;
+    const int c = (int)(t / d);
+    if (counts[c] > 0) cent[t] = sums[t] / (float)counts[c];
+}
+// sequentially applied (ci <- perturbed copy of cj) pairs; faiss split_clusters semantics
+__global__ void
+kmeans_split_kernel(float* cent, const int32_t* pairs, int npairs, int d) {
+    const float eps = 1.f / 1024.f;
+    for (int p = 0; p < npairs; p++) {
+        const int ci = pairs[2 * p], cj = pairs[2 * p + 1];
+        for (int j = threadIdx.x; j < d; j += blockDim.x) {
+            const float v = cent[(int64_t)cj * d + j];
+            if (j % 2 == 0) {
+                cent[(int64_t)ci * d + j] = v * (1 + eps);
+                cent[(int64_t)cj * d + j] = v * (1 - eps);
+            } else {
+                cent[(int64_t)ci * d + j] = v * (1 - eps);
+                cent[(int64_t)cj * d + j] = v * (1 + eps);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// PQ encode: warp per vector.  codes_flat[i*M + m], residual against cent[assign[i]] when cent != NULL.
+__global__ void __launch_bounds__(256)
+pq_encode_kernel(const float* __restrict__ x, const float* __restrict__ cent, const int32_t* __restrict__ assign,
+                 const float* __restrict__ pqc, int64_t n, int d, int M, int dsub, uint8_t* __restrict__ codes) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const float* xi = x + i * d;
+    const float* ci = cent ? cent + (int64_t)assign[i] * d : nullptr;
+    for (int m = 0; m < M; m++) {
+        float best = INFINITY;
+        int bj = 0;
+        for (int j = lane; j < 256; j += kWarp) {  // ascending j per lane => first minimum kept
+            const float* c = pqc + ((int64_t)m * 256 + j) * dsub;
+            float acc = 0.f;
+            for (int t = 0; t < dsub; t++) {
+                float r = xi[m * dsub + t];
+                if (ci) r -= ci[m * dsub + t];
+                const float df = r - c[t];
+                acc = fmaf(df, df, acc);
+            }
+            if (acc < best) { best = acc; bj = j; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+            if (ov < best || (ov == best && oj < bj)) { best = ov; bj = oj; }
+        }
+        if (lane == 0) codes[i * M + m] = (uint8_t)bj;
+    }
+}
+
+// t1[i] = sum_m ( |c_pq[m][code]|^2 + 2 <cent[assign[i]][m], c_pq[m][code]> )    (warp per vector)
+// == sum over m of the reference's precomputed_table[list][m][code] (F/IndexIVFPQ.cpp:462-513)
+__global__ void __launch_bounds__(256)
+pq_t1_kernel(const uint8_t* __restrict__ codes, const float* __restrict__ cent, const int32_t* __restrict__ assign,
+             const float* __restrict__ pqc, int64_t n, int d, int M, int dsub, float* __restrict__ t1) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const float* ci = cent + (int64_t)assign[i] * d;
+    float acc = 0.f;
+    for (int m = lane; m < M; m += kWarp) {
+        const float* c = pqc + ((int64_t)m * 256 + codes[i * M + m]) * dsub;
+        float nn = 0.f, ip = 0.f;
+        for (int t = 0; t < dsub; t++) {
+            nn = fmaf(c[t], c[t], nn);
+            ip = fmaf(ci[m * dsub + t], c[t], ip);
+        }
+        acc += nn + 2.f * ip;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) t1[i] = acc;
+}
+
+__global__ void
+histogram_kernel(const int32_t* __restrict__ assign, int64_t n, int32_t* __restrict__ counts) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&counts[assign[i]], 1);
+}
+// r = rank in the (list, insertion)-sorted order; write rows[pos] for owned lists
+__global__ void
+place_rows_kernel(const int32_t* __restrict__ sorted_list, const int32_t* __restrict__ sorted_idx, int64_t n,
+                  const int64_t* __restrict__ first_rank, const int64_t* __restrict__ list_off,
+                  const int32_t* __restrict__ list_len, int32_t* __restrict__ rows, int32_t* __restrict__ pos_of_row) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int l = sorted_list[r];
+    if (list_len[l] == 0) {
+        if (pos_of_row) pos_of_row[sorted_idx[r]] = -1;
+        return;
+    }
+    const int64_t pos = list_off[l] + (r - first_rank[l]);
+    rows[pos] = sorted_idx[r];
+    if (pos_of_row) pos_of_row[sorted_idx[r]] = (int32_t)pos;
+}
+// group-major rotated code layout (see kb2_ivf.cuh header)
+__global__ void
+layout_codes_kernel(const uint8_t* __restrict__ codes_flat, const int32_t* __restrict__ rows, int64_t npad, int M,
+                    int G, uint8_t* __restrict__ out /* [G][npad][16] */) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= npad * G * 16) return;
+    const int s = (int)(t & 15);
+    const int64_t pos = (t >> 4) % npad;
+    const int g = (int)((t >> 4) / npad);
+    const int32_t r = rows[pos];
+    uint8_t v = 0;
+    if (r >= 0) v = codes_flat[(int64_t)r * M + g * 16 + ((s + (int)(pos & 15)) & 15)];
+    out[t] = v;
+}
+__global__ void
+layout_codes_plain_kernel(const uint8_t* __restrict__ codes_flat, const int32_t* __restrict__ rows, int64_t npad,
+                          int M, uint8_t* __restrict__ out /* [npad][M] */) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= npad * M) return;
+    const int64_t pos = t / M;
+    const int m = (int)(t % M);
+    const int32_t r = rows[pos];
+    out[t] = (r >= 0) ? codes_flat[(int64_t)r * M + m] : 0;
+}
+__global__ void
+gather_f32_kernel(const float* __restrict__ src, const int32_t* __restrict__ rows, int64_t npad, float* __restrict__ out,
+                  float fill) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= npad) return;
+    const int32_t r = rows[t];
+    out[t] = (r >= 0) ? src[r] : fill;
+}
+
+static inline dim3
+grid1d(int64_t n, int block) {
+    return dim3((unsigned)((n + block - 1) / block));
+}
+
+// ---------------------------------------------------------------- nearest-centroid assignment
+// assign[i] = argmin_j key(x_i, c_j)   chunked so that the key matrix stays under ~256 MB
+struct AssignScratch {
+    DevBuf<float> keys, xn, cn;
+};
+inline void
+assign_nearest(const float* x, int64_t n, int d, const float* cent, int k, int metric, int32_t* assign,
+               float* out_val, AssignScratch& sc, cudaStream_t st) {
+    if (n == 0) return;
+    sc.cn.ensure(k);
+    row_norms_kernel<<<grid1d((int64_t)k * 32, 256), 256, 0, st>>>(cent, k, d, sc.cn.p);
+    int64_t chunk = std::max<int64_t>(128, std::min<int64_t>(n, (int64_t)(64ll << 20) / std::max(k, 1)));
+    chunk = std::min<int64_t>(chunk, 1 << 20);
+    sc.keys.ensure((size_t)chunk * k);
+    sc.xn.ensure((size_t)chunk);
+    for (int64_t i0 = 0; i0 < n; i0 += chunk) {
+        const int64_t m = std::min(chunk, n - i0);
+        const float* xc = x + i0 * d;
+        row_norms_kernel<<<grid1d(m * 32, 256), 256, 0, st>>>(xc, m, d, sc.xn.p);
+        dim3 g((k + GK_BN - 1) / GK_BN, (unsigned)((m + GK_BM - 1) / GK_BM));
+        if (metric == KB2_METRIC_L2)
+            gemm_keys_kernel<KB2_METRIC_L2><<<g, 256, 0, st>>>(xc, cent, sc.xn.p, sc.cn.p, (int)m, k, d, sc.keys.p, k,
+                                                               nullptr, nullptr, 0);
+        else
+            gemm_keys_kernel<KB2_METRIC_IP><<<g, 256, 0, st>>>(xc, cent, sc.xn.p, sc.cn.p, (int)m, k, d, sc.keys.p, k,
+                                                               nullptr, nullptr, 0);
+        argmin_rows_kernel<<<grid1d(m * 32, 256), 256, 0, st>>>(sc.keys.p, k, m, k, assign + i0,
+                                                               out_val ? out_val + i0 : nullptr);
+    }
+    KB2_CUDA_CHECK(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------- k-means (device data)
+// x: [n][d] device.  centroids: [k][d] device (output).
+inline void
+kmeans_train(const float* x, int64_t n, int d, int k, int metric, int niter, uint64_t seed, float* centroids,
+             cudaStream_t st) {
+    KB2_REQUIRE(n >= k, KB2_INVALID_ARGS, "k-means: fewer training points than centroids");
+    // subsample to <= 256 points per centroid (F/Clustering.cpp subsample_training_set)
+    const int64_t max_pts = (int64_t)256 * k;
+    DevBuf<float> sample;
+    const float* xt = x;
+    int64_t nt = n;
+    std::mt19937_64 rng(seed);
+    if (n > max_pts) {
+        std::vector<int32_t> perm(n);
+        for (int64_t i = 0; i < n; i++) perm[i] = (int32_t)i;
+        for (int64_t i = 0; i < max_pts; i++) {
+            int64_t j = i + (int64_t)(rng() % (uint64_t)(n - i));
+            std::swap(perm[i], perm[j]);
+        }
+        perm.resize(max_pts);
+        DevBuf<int32_t> didx;
+        didx.ensure(max_pts);
+        KB2_CUDA_CHECK(cudaMemcpyAsync(didx.p, perm.data(), max_pts * 4, cudaMemcpyHostToDevice, st));
+        sample.ensure((size_t)max_pts * d);
+        gather_rows_kernel<<<grid1d(max_pts * 32, 256), 256, 0, st>>>(x, didx.p, max_pts, d, d, sample.p);
+        KB2_CUDA_CHECK(cudaStreamSynchronize(st));
+        xt = sample.p;
+        nt = max_pts;
+    }
+    // init: k distinct random training points
+    {
+        std::vector<int32_t> perm(nt);
+        for (int64_t i = 0; i < nt; i++) perm[i] = (int32_t)i;
+        for (int64_t i = 0; i < k; i++) {
+            int64_t j = i + (int64_t)(rng() % (uint64_t)(nt - i));
+            std::swap(perm[i], perm[j]);
+        }
+        DevBuf<int32_t> didx;
+        didx.ensure(k);
+        KB2_CUDA_CHECK(cudaMemcpyAsync(didx.p, perm.data(), (size_t)k * 4, cudaMemcpyHostToDevice, st));
+        gather_rows_kernel<<<grid1d((int64_t)k * 32, 256), 256, 0, st>>>(xt, didx.p, k, d, d, centroids);
+        KB2_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    DevBuf<int32_t> assign, counts, pairs;
+    DevBuf<float> sums;
+    assign.ensure(nt);
+    counts.ensure(k);
+    sums.ensure((size_t)k * d);
+    AssignScratch sc;
+    std::vector<int32_t> hcounts(k);
+    for (int it = 0; it < niter; it++) {
+        assign_nearest(xt, nt, d, centroids, k, metric, assign.p, nullptr, sc, st);
+        KB2_CUDA_CHECK(cudaMemsetAsync(counts.p, 0, (size_t)k * 4, st));
+        KB2_CUDA_CHECK(cudaMemsetAsync(sums.p, 0, (size_t)k * d * 4, st));
+        kmeans_accumulate_kernel<<<grid1d(nt * 32, 256), 256, 0, st>>>(xt, assign.p, nt, d, sums.p, counts.p);
+        kmeans_divide_kernel<<<grid1d((int64_t)k * d, 256), 256, 0, st>>>(centroids, sums.p, counts.p, k, d);
+        KB2_CUDA_CHECK(cudaMemcpyAsync(hcounts.data(), counts.p, (size_t)k * 4, cudaMemcpyDeviceToHost, st));
+        KB2_CUDA_CHECK(cudaStreamSynchronize(st));
+        // empty clusters: split a populated one (probability ~ size), like faiss split_clusters
+        std::vector<int32_t> hp;
+        for (int ci = 0; ci < k; ci++) {
+            if (hcounts[ci] != 0) continue;
+            if (nt <= k) break;
+            int cj = 0;
+            for (cj = 0;; cj = (cj + 1) % k) {
+                const double pr = (hcounts[cj] - 1.0) / (double)(nt - k);
+                const double r = (double)(rng() >> 11) * (1.0 / 9007199254740992.0);
+                if (r < pr) break;
+            }
+            hp.push_back(ci);
+            hp.push_back(cj);
+            hcounts[ci] = hcounts[cj] / 2;
+            hcounts[cj] -= hcounts[ci];
+        }
+        if (!hp.empty()) {
+            pairs.ensure(hp.size());
+            KB2_CUDA_CHECK(cudaMemcpyAsync(pairs.p, hp.data(), hp.size() * 4, cudaMemcpyHostToDevice, st));
+            kmeans_split_kernel<<<1, 256, 0, st>>>(centroids, pairs.p, (int)(hp.size() / 2), d);
+            KB2_CUDA_CHECK(cudaStreamSynchronize(st));
+        }
+    }
+    KB2_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace kb2

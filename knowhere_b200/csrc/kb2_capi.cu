@@ -1,0 +1,508 @@
+// kb2_capi.cu — the extern "C" boundary declared in include/knowhere_b200.h.
+// Everything behind it is CUDA; there is no CPU fallback: without a usable sm_100 device every
+// entry point fails with KB2_CUDA_RUNTIME_ERROR.
+#include <cstring>
+#include <memory>
+
+#include "kb2_hnsw.cuh"
+#include "kb2_index.cuh"
+#include "kb2_range.cuh"
+
+using namespace kb2;
+
+namespace {
+thread_local std::string g_last_error;
+
+template <typename F>
+int
+guarded(F&& f) {
+    try {
+        f();
+        return KB2_SUCCESS;
+    } catch (const Error& e) {
+        g_last_error = e.what();
+        cudaGetLastError();
+        return e.status;
+    } catch (const std::bad_alloc&) {
+        g_last_error = "host allocation failed";
+        return KB2_MALLOC_ERROR;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return KB2_INTERNAL_ERROR;
+    } catch (...) {
+        g_last_error = "unknown error";
+        return KB2_INTERNAL_ERROR;
+    }
+}
+
+int
+usable_devices() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int ok = 0;
+    for (int i = 0; i < n; i++) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ok++;
+    }
+    return ok;
+}
+
+void
+require_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        throw Error(KB2_CUDA_RUNTIME_ERROR, "no CUDA device available (this library has no CPU fallback)");
+    }
+    KB2_REQUIRE(device >= 0 && device < n, KB2_INVALID_ARGS, "bad device ordinal");
+    cudaDeviceProp p;
+    KB2_CUDA_CHECK(cudaGetDeviceProperties(&p, device));
+    KB2_REQUIRE(p.major == 10, KB2_CUDA_RUNTIME_ERROR,
+                "device is not sm_100 (this library ships sm_100a SASS only)");
+    KB2_CUDA_CHECK(cudaSetDevice(device));
+}
+
+struct Handle {
+    std::unique_ptr<IndexBase> ix;
+};
+inline IndexBase*
+ix_of(kb2_index_t h) {
+    KB2_REQUIRE(h != nullptr, KB2_INVALID_ARGS, "null index handle");
+    return reinterpret_cast<Handle*>(h)->ix.get();
+}
+template <typename T>
+inline T*
+ix_as(kb2_index_t h, const char* what) {
+    T* p = dynamic_cast<T*>(ix_of(h));
+    KB2_REQUIRE(p != nullptr, KB2_INVALID_ARGS, std::string("handle is not an ") + what + " index");
+    return p;
+}
+
+int
+parse_metric(int metric, const JsonObj& cfg) {
+    if (cfg.has("metric_type")) {
+        const std::string m = cfg.get_str("metric_type", "L2");
+        if (m == "L2") return KB2_METRIC_L2;
+        if (m == "IP") return KB2_METRIC_IP;
+        if (m == "COSINE") return KB2_METRIC_COSINE;
+        throw Error(KB2_INVALID_METRIC_TYPE, "unsupported metric_type " + m);
+    }
+    return metric;
+}
+}  // namespace
+
+extern "C" {
+
+const char*
+kb2_version(void) {
+    return "knowhere_b200 0.1 (sm_100a)";
+}
+const char*
+kb2_last_error(void) {
+    return g_last_error.c_str();
+}
+int
+kb2_device_count(void) {
+    return usable_devices();
+}
+
+int
+kb2_index_create(const char* index_type, int metric, int dim, const char* json_cfg, int device, kb2_index_t* out) {
+    return guarded([&] {
+        KB2_REQUIRE(out != nullptr && index_type != nullptr, KB2_INVALID_ARGS, "null argument");
+        *out = nullptr;
+        JsonObj cfg = JsonObj::parse(json_cfg);
+        KB2_REQUIRE(cfg.ok, KB2_INVALID_PARAM_IN_JSON, "malformed json");
+        metric = parse_metric(metric, cfg);
+        KB2_REQUIRE(metric == KB2_METRIC_L2 || metric == KB2_METRIC_IP, KB2_INVALID_METRIC_TYPE,
+                    "metric must be L2 or IP (COSINE: normalise and use IP)");
+        if (dim <= 0) dim = (int)cfg.get_int("dim", 0);
+        KB2_REQUIRE(dim > 0, KB2_INVALID_ARGS, "dim must be positive");
+        require_device(device);
+        const std::string t = index_type;
+        std::unique_ptr<IndexBase> ix;
+        if (t == "FLAT") {
+            ix.reset(new FlatIndex());
+        } else if (t == "IVF_FLAT" || t == "IVF_PQ") {
+            auto* iv = new IvfIndex();
+            ix.reset(iv);
+            iv->is_pq = (t == "IVF_PQ");
+            iv->nlist = cfg.get_int("nlist", 128);
+            KB2_REQUIRE(iv->nlist >= 1 && iv->nlist <= 65536 * 16, KB2_OUT_OF_RANGE_IN_JSON, "nlist out of range");
+            if (iv->is_pq) {
+                KB2_REQUIRE(cfg.has("m"), KB2_INVALID_PARAM_IN_JSON, "IVF_PQ requires m");
+                iv->M = (int)cfg.get_int("m", 0);
+                iv->nbits = (int)cfg.get_int("nbits", 8);
+                KB2_REQUIRE(iv->M >= 1 && dim % iv->M == 0, KB2_INVALID_ARGS, "dim must be a multiple of m");
+                KB2_REQUIRE(iv->nbits >= 1 && iv->nbits <= 24, KB2_OUT_OF_RANGE_IN_JSON, "nbits out of range");
+                iv->refine = cfg.get_bool("refine", false);
+                if (iv->refine) {
+                    const std::string rt = cfg.get_str("refine_type", "flat");
+                    KB2_REQUIRE(rt == "flat" || rt == "FLAT" || rt == "fp32" || rt == "FP32" || rt == "float32",
+                                KB2_NOT_IMPLEMENTED, "only refine_type=flat (fp32) is implemented");
+                }
+            }
+        } else if (t == "HNSW") {
+            auto* hn = new HnswIndex();
+            ix.reset(hn);
+            hn->M = (int)cfg.get_int("M", 30);
+            hn->efConstruction = (int)cfg.get_int("efConstruction", 360);
+            KB2_REQUIRE(hn->M >= 2 && hn->M <= 2048, KB2_OUT_OF_RANGE_IN_JSON, "M out of range");
+        } else {
+            throw Error(KB2_INVALID_ARGS, "unknown index type " + t);
+        }
+        ix->type = t;
+        ix->metric = metric;
+        ix->dim = dim;
+        ix->device = device;
+        ix->init_common();
+        auto* h = new Handle();
+        h->ix = std::move(ix);
+        *out = reinterpret_cast<kb2_index_t>(h);
+    });
+}
+
+void
+kb2_index_destroy(kb2_index_t h) {
+    if (!h) return;
+    Handle* hh = reinterpret_cast<Handle*>(h);
+    if (hh->ix) cudaSetDevice(hh->ix->device);
+    delete hh;
+}
+
+int
+kb2_index_set_stream(kb2_index_t h, void* cuda_stream) {
+    return guarded([&] {
+        IndexBase* ix = ix_of(h);
+        std::lock_guard<std::mutex> lk(ix->mu);
+        ix->set_stream((cudaStream_t)cuda_stream);
+    });
+}
+
+int
+kb2_index_set_shard(kb2_index_t h, int rank, int world) {
+    return guarded([&] {
+        IndexBase* ix = ix_of(h);
+        KB2_REQUIRE(world >= 1 && rank >= 0 && rank < world, KB2_INVALID_ARGS, "bad shard rank/world");
+        KB2_REQUIRE(ix->count() == 0, KB2_INVALID_ARGS, "set_shard must precede add/import");
+        ix->shard_rank = rank;
+        ix->shard_world = world;
+    });
+}
+
+int
+kb2_index_train(kb2_index_t h, const float* x, int64_t n) {
+    return guarded([&] {
+        IndexBase* ix = ix_of(h);
+        std::lock_guard<std::mutex> lk(ix->mu);
+        KB2_CUDA_CHECK(cudaSetDevice(ix->device));
+        KB2_REQUIRE(x != nullptr || n == 0, KB2_INVALID_ARGS, "null training data");
+        ix->train(x, n);
+    });
+}
+
+int
+kb2_index_add(kb2_index_t h, const float* x, int64_t n, const int64_t* ids) {
+    return guarded([&] {
+        IndexBase* ix = ix_of(h);
+        std::lock_guard<std::mutex> lk(ix->mu);
+        KB2_CUDA_CHECK(cudaSetDevice(ix->device));
+        KB2_REQUIRE(x != nullptr || n == 0, KB2_INVALID_ARGS, "null data");
+        ix->add(x, n, ids);
+    });
+}
+
+int
+kb2_index_search(kb2_index_t h, const float* queries, int64_t nq, int k, const char* json, const uint8_t* bitset,
+                 int64_t bitset_nbits, int64_t* out_ids, float* out_dist) {
+    return guarded([&] {
+        IndexBase* ix = ix_of(h);
+        std::lock_guard<std::mutex> lk(ix->mu);
+        KB2_CUDA_CHECK(cudaSetDevice(ix->device));
+        KB2_REQUIRE(nq >= 0 && k > 0, KB2_INVALID_ARGS, "bad nq / k");
+        if (nq == 0) return;
+        KB2_REQUIRE(queries && out_ids && out_dist, KB2_INVALID_ARGS, "null buffer");
+        KB2_REQUIRE(is_device_ptr(out_ids) == is_device_ptr(out_dist), KB2_INVALID_ARGS,
+                    "out_ids and out_dist must both be host or both be device buffers");
+        JsonObj cfg = JsonObj::parse(json);
+        KB2_REQUIRE(cfg.ok, KB2_INVALID_PARAM_IN_JSON, "malformed json");
+        ix->last = Counters{};
+        ix->search(queries, nq, k, cfg, bitset, bitset_nbits, out_ids, out_dist);
+    });
+}
+
+int
+kb2_index_range_search(kb2_index_t h, const float* queries, int64_t nq, float radius, float range_filter,
+                       int has_range_filter, const char* json, const uint8_t* bitset, int64_t bitset_nbits,
+                       int64_t** out_lims, int64_t** out_ids, float** out_dist) {
+    return guarded([&] {
+        IndexBase* ix = ix_of(h);
+        std::lock_guard<std::mutex> lk(ix->mu);
+        KB2_CUDA_CHECK(cudaSetDevice(ix->device));
+        KB2_REQUIRE(out_lims && out_ids && out_dist, KB2_INVALID_ARGS, "null output");
+        JsonObj cfg = JsonObj::parse(json);
+        KB2_REQUIRE(cfg.ok, KB2_INVALID_PARAM_IN_JSON, "malformed json");
+        ix->last = Counters{};
+        range_search_index(*ix, queries, nq, radius, range_filter, has_range_filter != 0, cfg, bitset, bitset_nbits,
+                           out_lims, out_ids, out_dist);
+    });
+}
+
+void
+kb2_free(void* p) {
+    free(p);
+}
+
+int64_t
+kb2_index_count(kb2_index_t h) {
+    return h ? reinterpret_cast<Handle*>(h)->ix->count() : 0;
+}
+int
+kb2_index_dim(kb2_index_t h) {
+    return h ? reinterpret_cast<Handle*>(h)->ix->dim : 0;
+}
+int64_t
+kb2_index_size_bytes(kb2_index_t h) {
+    return h ? reinterpret_cast<Handle*>(h)->ix->size_bytes() : 0;
+}
+int
+kb2_index_is_trained(kb2_index_t h) {
+    return h ? (int)reinterpret_cast<Handle*>(h)->ix->is_trained() : 0;
+}
+int
+kb2_index_has_raw_data(kb2_index_t h) {
+    return h ? (int)reinterpret_cast<Handle*>(h)->ix->has_raw() : 0;
+}
+int
+kb2_index_get_vector_by_ids(kb2_index_t h, const int64_t* ids, int64_t n, float* out) {
+    return guarded([&] {
+        IndexBase* ix = ix_of(h);
+        std::lock_guard<std::mutex> lk(ix->mu);
+        KB2_CUDA_CHECK(cudaSetDevice(ix->device));
+        ix->get_vectors(ids, n, out);
+    });
+}
+
+// ---------------------------------------------------------------- IVF import / export
+int
+kb2_ivf_import_begin(kb2_index_t h, int64_t nlist, const float* centroids, const float* pq_centroids) {
+    return guarded([&] {
+        auto* iv = ix_as<IvfIndex>(h, "IVF");
+        std::lock_guard<std::mutex> lk(iv->mu);
+        KB2_CUDA_CHECK(cudaSetDevice(iv->device));
+        iv->import_begin(nlist, centroids, pq_centroids);
+    });
+}
+int
+kb2_ivf_import_list(kb2_index_t h, int64_t list_no, int64_t list_size, const int64_t* ids, const uint8_t* codes) {
+    return guarded([&] {
+        auto* iv = ix_as<IvfIndex>(h, "IVF");
+        std::lock_guard<std::mutex> lk(iv->mu);
+        if (list_size > 0) iv->import_list(list_no, list_size, ids, codes);
+    });
+}
+int
+kb2_ivf_import_finish(kb2_index_t h, const float* raw, int64_t n_raw) {
+    return guarded([&] {
+        auto* iv = ix_as<IvfIndex>(h, "IVF");
+        std::lock_guard<std::mutex> lk(iv->mu);
+        KB2_CUDA_CHECK(cudaSetDevice(iv->device));
+        iv->import_finish(raw, n_raw);
+    });
+}
+int64_t
+kb2_ivf_nlist(kb2_index_t h) {
+    auto* iv = dynamic_cast<IvfIndex*>(reinterpret_cast<Handle*>(h)->ix.get());
+    return iv ? iv->nlist : -1;
+}
+int64_t
+kb2_ivf_list_size(kb2_index_t h, int64_t list_no) {
+    int64_t r = -1;
+    guarded([&] {
+        auto* iv = ix_as<IvfIndex>(h, "IVF");
+        std::lock_guard<std::mutex> lk(iv->mu);
+        KB2_CUDA_CHECK(cudaSetDevice(iv->device));
+        iv->seal();
+        KB2_REQUIRE(list_no >= 0 && list_no < iv->nlist, KB2_INVALID_ARGS, "list number out of range");
+        r = iv->h_list_len[list_no];
+    });
+    return r;
+}
+int
+kb2_ivf_export_centroids(kb2_index_t h, float* centroids, float* pq_centroids) {
+    return guarded([&] {
+        auto* iv = ix_as<IvfIndex>(h, "IVF");
+        std::lock_guard<std::mutex> lk(iv->mu);
+        KB2_CUDA_CHECK(cudaSetDevice(iv->device));
+        KB2_REQUIRE(iv->trained, KB2_INDEX_NOT_TRAINED, "index not trained");
+        if (centroids)
+            KB2_CUDA_CHECK(cudaMemcpy(centroids, iv->centroids.p, (size_t)iv->nlist * iv->dim * 4, cudaMemcpyDefault));
+        if (pq_centroids && iv->is_pq)
+            KB2_CUDA_CHECK(cudaMemcpy(pq_centroids, iv->pqc.p, (size_t)iv->M * 256 * iv->dsub * 4, cudaMemcpyDefault));
+    });
+}
+int
+kb2_ivf_export_list(kb2_index_t h, int64_t list_no, int64_t* ids, uint8_t* codes) {
+    return guarded([&] {
+        auto* iv = ix_as<IvfIndex>(h, "IVF");
+        std::lock_guard<std::mutex> lk(iv->mu);
+        KB2_CUDA_CHECK(cudaSetDevice(iv->device));
+        iv->export_list(list_no, ids, codes);
+    });
+}
+
+// ---------------------------------------------------------------- HNSW import / export
+int
+kb2_hnsw_import(kb2_index_t h, int64_t n, const float* vectors, const int32_t* levels, const int64_t* offsets,
+                const int32_t* neighbors, const int32_t* cum_nneighbor, int n_cum, int32_t entry_point,
+                int32_t max_level) {
+    return guarded([&] {
+        auto* hn = ix_as<HnswIndex>(h, "HNSW");
+        std::lock_guard<std::mutex> lk(hn->mu);
+        KB2_CUDA_CHECK(cudaSetDevice(hn->device));
+        hn->import_graph(n, vectors, levels, offsets, neighbors, cum_nneighbor, n_cum, entry_point, max_level);
+    });
+}
+int
+kb2_hnsw_export_meta(kb2_index_t h, int64_t* out5) {
+    return guarded([&] {
+        auto* hn = ix_as<HnswIndex>(h, "HNSW");
+        out5[0] = hn->n;
+        out5[1] = hn->entry_point;
+        out5[2] = hn->max_level;
+        out5[3] = (int64_t)hn->h_neighbors.size();
+        out5[4] = (int64_t)hn->h_cum.size();
+    });
+}
+int
+kb2_hnsw_export(kb2_index_t h, int32_t* levels, int64_t* offsets, int32_t* neighbors, int32_t* cum) {
+    return guarded([&] {
+        auto* hn = ix_as<HnswIndex>(h, "HNSW");
+        memcpy(levels, hn->h_levels.data(), hn->h_levels.size() * 4);
+        memcpy(offsets, hn->h_offsets.data(), hn->h_offsets.size() * 8);
+        memcpy(neighbors, hn->h_neighbors.data(), hn->h_neighbors.size() * 4);
+        memcpy(cum, hn->h_cum.data(), hn->h_cum.size() * 4);
+    });
+}
+int
+kb2_hnsw_last_stats(kb2_index_t h, int64_t* out2) {
+    return guarded([&] {
+        auto* hn = ix_as<HnswIndex>(h, "HNSW");
+        out2[0] = hn->last_ndis;
+        out2[1] = hn->last_nhops;
+    });
+}
+
+// ---------------------------------------------------------------- serialisation ("KB2I" container)
+int
+kb2_index_serialize(kb2_index_t h, uint8_t** out, size_t* out_size) {
+    return guarded([&] {
+        IndexBase* ix = ix_of(h);
+        std::lock_guard<std::mutex> lk(ix->mu);
+        KB2_CUDA_CHECK(cudaSetDevice(ix->device));
+        std::vector<uint8_t> blob;
+        serialize_index(*ix, blob);
+        *out = (uint8_t*)malloc(blob.size() ? blob.size() : 1);
+        KB2_REQUIRE(*out != nullptr, KB2_MALLOC_ERROR, "malloc failed");
+        memcpy(*out, blob.data(), blob.size());
+        *out_size = blob.size();
+    });
+}
+int
+kb2_index_deserialize(const uint8_t* blob, size_t size, int device, kb2_index_t* out) {
+    return guarded([&] {
+        KB2_REQUIRE(blob && out, KB2_INVALID_ARGS, "null argument");
+        require_device(device);
+        std::unique_ptr<IndexBase> ix = deserialize_index(blob, size, device);
+        auto* hh = new Handle();
+        hh->ix = std::move(ix);
+        *out = reinterpret_cast<kb2_index_t>(hh);
+    });
+}
+
+// ---------------------------------------------------------------- BruteForce
+int
+kb2_bruteforce_search(const float* base, int64_t nb, int dim, int metric, const float* queries, int64_t nq, int k,
+                      const uint8_t* bitset, int64_t bitset_nbits, int64_t* out_ids, float* out_dist, int device,
+                      void* cuda_stream) {
+    return guarded([&] {
+        KB2_REQUIRE(base && queries && out_ids && out_dist, KB2_INVALID_ARGS, "null buffer");
+        KB2_REQUIRE(metric == KB2_METRIC_L2 || metric == KB2_METRIC_IP, KB2_INVALID_METRIC_TYPE, "metric must be L2 or IP");
+        require_device(device);
+        FlatIndex fi;
+        fi.type = "FLAT";
+        fi.metric = metric;
+        fi.dim = dim;
+        fi.device = device;
+        fi.init_common();
+        if (cuda_stream) fi.set_stream((cudaStream_t)cuda_stream);
+        fi.add(base, nb, nullptr);
+        JsonObj cfg;
+        fi.search(queries, nq, k, cfg, bitset, bitset_nbits, out_ids, out_dist);
+    });
+}
+int
+kb2_bruteforce_range_search(const float* base, int64_t nb, int dim, int metric, const float* queries, int64_t nq,
+                            float radius, float range_filter, int has_range_filter, const uint8_t* bitset,
+                            int64_t bitset_nbits, int64_t** out_lims, int64_t** out_ids, float** out_dist, int device,
+                            void* cuda_stream) {
+    return guarded([&] {
+        KB2_REQUIRE(base && queries, KB2_INVALID_ARGS, "null buffer");
+        KB2_REQUIRE(metric == KB2_METRIC_L2 || metric == KB2_METRIC_IP, KB2_INVALID_METRIC_TYPE, "metric must be L2 or IP");
+        require_device(device);
+        FlatIndex fi;
+        fi.type = "FLAT";
+        fi.metric = metric;
+        fi.dim = dim;
+        fi.device = device;
+        fi.init_common();
+        if (cuda_stream) fi.set_stream((cudaStream_t)cuda_stream);
+        fi.add(base, nb, nullptr);
+        JsonObj cfg;
+        range_search_index(fi, queries, nq, radius, range_filter, has_range_filter != 0, cfg, bitset, bitset_nbits,
+                           out_lims, out_ids, out_dist);
+    });
+}
+
+// ---------------------------------------------------------------- multi-GPU merge
+int
+kb2_merge_topk(int metric, int world, int64_t nq, int k, const int64_t* in_ids, const float* in_dist, int64_t* out_ids,
+               float* out_dist, int device, void* cuda_stream) {
+    return guarded([&] {
+        KB2_REQUIRE(in_ids && in_dist && out_ids && out_dist, KB2_INVALID_ARGS, "null buffer");
+        KB2_REQUIRE(world >= 1 && k >= 1 && (int64_t)world * k <= kMaxSortEntries, KB2_INVALID_ARGS, "world*k too large");
+        require_device(device);
+        merge_topk_device(metric, world, nq, k, in_ids, in_dist, out_ids, out_dist, (cudaStream_t)cuda_stream);
+    });
+}
+
+// ---------------------------------------------------------------- introspection
+int
+kb2_index_last_search_counters(kb2_index_t h, int64_t* out8) {
+    return guarded([&] {
+        IndexBase* ix = ix_of(h);
+        const Counters& c = ix->last;
+        out8[0] = c.launches;
+        out8[1] = c.codes;
+        out8[2] = c.code_bytes;
+        out8[3] = c.pairs;
+        out8[4] = c.h2d;
+        out8[5] = c.d2h;
+        out8[6] = 0;
+        out8[7] = 0;
+    });
+}
+int
+kb2_index_enable_kernel_timing(kb2_index_t h, int on) {
+    return guarded([&] { ix_of(h)->timing = (on != 0); });
+}
+int
+kb2_index_last_kernel_ms(kb2_index_t h, float* out_ms) {
+    return guarded([&] { *out_ms = ix_of(h)->last_kernel_ms; });
+}
+
+}  // extern "C"

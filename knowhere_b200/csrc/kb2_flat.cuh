@@ -1,0 +1,174 @@
+// kb2_flat.cuh — dense query x base contraction with fused key epilogue, and key selection.
+//
+// Replaces the reference's per-query sequential scans (one thread-pool task per query):
+//   BruteForce  K/utils/distances.cpp:994 knn_L2sqr -> exhaustive_L2sqr_seq -> fvec_L2sqr_ny_if (:249-322)
+//   FLAT index  F/IndexFlat.cpp:29-60 -> F/utils/distances.cpp:834-875, 326-363
+//   IVF coarse  F/IndexIVF.cpp:336-342 (quantizer->search)
+// with one batched contraction  keys[q][j] = |q|^2 + |x_j|^2 - 2 q.x_j  (L2) / -q.x_j (IP),
+// a per-(query,slice) k-selection, and an exact fp32 re-rank of k' > k candidates in
+// finalize_kernel so that returned distances are the directly accumulated sum((q-x)^2)
+// (self-distance is exactly 0 like fvec_L2sqr, src/simd/distances_ref.cc:31-38).
+//
+// This file holds the fp32 CUDA-core contraction (bit-for-bit deterministic); the tcgen05
+// tensor-core contraction lives in kb2_gemm_tc.cuh and produces the same key matrix.
+#pragma once
+#include "kb2_topk.cuh"
+
+namespace kb2 {
+
+// ---------------------------------------------------------------- row squared norms (warp per row)
+__global__ void __launch_bounds__(256)
+row_norms_kernel(const float* __restrict__ x, int64_t n, int d, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const float* r = x + row * d;
+    float acc = 0.f;
+    for (int j = lane; j < d; j += kWarp) acc = fmaf(r[j], r[j], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) out[row] = acc;
+}
+
+// ---------------------------------------------------------------- fp32 SGEMM-style key kernel
+// keys[q][j] for q in [0,nq), j in [0,nb): 128x128 CTA tile, 8x8 register micro-tile, BK=8.
+// Q [nq][d], X [nb][d] row-major (both K-contiguous => "NT" GEMM).
+constexpr int GK_BM = 128, GK_BN = 128, GK_BK = 8;
+
+template <int METRIC>
+__global__ void __launch_bounds__(256)
+gemm_keys_kernel(const float* __restrict__ Q, const float* __restrict__ X, const float* __restrict__ qn,
+                 const float* __restrict__ xn, int nq, int nb, int d, float* __restrict__ keys, int64_t ldk,
+                 const uint8_t* __restrict__ bitset, const int32_t* __restrict__ rows, int64_t row_base) {
+    __shared__ float As[2][GK_BK][GK_BM + 4];
+    __shared__ float Bs[2][GK_BK][GK_BN + 4];
+
+    const int tid = threadIdx.x;
+    const int q0 = blockIdx.y * GK_BM;
+    const int j0 = blockIdx.x * GK_BN;
+    // loader mapping: 128 rows x 8 k-values = 256 float4 -> one float4 per thread per matrix
+    const int lrow = tid >> 1;        // 0..127
+    const int lk = (tid & 1) * 4;     // 0 or 4
+    const int ty = tid >> 4;          // 0..15 -> 8 query rows each
+    const int tx = tid & 15;          // 0..15 -> 8 base rows each
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
+
+    const bool a_ok = (q0 + lrow) < nq;
+    const bool b_ok = (j0 + lrow) < nb;
+    const float* ap = Q + (int64_t)(q0 + lrow) * d + lk;
+    const float* bp = X + (int64_t)(j0 + lrow) * d + lk;
+
+    const bool vec4 = ((d & 3) == 0);
+    auto load_tile = [&](int kt, float4& a, float4& b) {
+        const int kk = kt * GK_BK + lk;
+        a = make_float4(0.f, 0.f, 0.f, 0.f);
+        b = a;
+        if (vec4 && kk + 3 < d) {
+            if (a_ok) a = *reinterpret_cast<const float4*>(ap + kt * GK_BK);
+            if (b_ok) b = *reinterpret_cast<const float4*>(bp + kt * GK_BK);
+        } else {
+            float ta[4] = {0, 0, 0, 0}, tb[4] = {0, 0, 0, 0};
+            for (int t = 0; t < 4; t++)
+                if (kk + t < d) {
+                    if (a_ok) ta[t] = ap[kt * GK_BK + t];
+                    if (b_ok) tb[t] = bp[kt * GK_BK + t];
+                }
+            a = make_float4(ta[0], ta[1], ta[2], ta[3]);
+            b = make_float4(tb[0], tb[1], tb[2], tb[3]);
+        }
+    };
+    auto store_tile = [&](int buf, const float4& a, const float4& b) {
+        As[buf][lk + 0][lrow] = a.x; As[buf][lk + 1][lrow] = a.y;
+        As[buf][lk + 2][lrow] = a.z; As[buf][lk + 3][lrow] = a.w;
+        Bs[buf][lk + 0][lrow] = b.x; Bs[buf][lk + 1][lrow] = b.y;
+        Bs[buf][lk + 2][lrow] = b.z; Bs[buf][lk + 3][lrow] = b.w;
+    };
+
+    const int nkt = (d + GK_BK - 1) / GK_BK;
+    float4 ra, rb;
+    load_tile(0, ra, rb);
+    store_tile(0, ra, rb);
+    __syncthreads();
+    for (int kt = 0; kt < nkt; kt++) {
+        const int buf = kt & 1;
+        if (kt + 1 < nkt) load_tile(kt + 1, ra, rb);
+#pragma unroll
+        for (int kk = 0; kk < GK_BK; kk++) {
+            float a[8], b[8];
+            // rows {ty*4..+3} U {64+ty*4..+3}: a half-warp reads 16 consecutive float4 (no bank conflict)
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+            b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (kt + 1 < nkt) {
+            store_tile(buf ^ 1, ra, rb);
+            __syncthreads();
+        }
+    }
+
+    // epilogue
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int q = q0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        if (q >= nq) continue;
+        const float qq = (METRIC == KB2_METRIC_L2) ? qn[q] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int col = j0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+            if (col >= nb) continue;
+            float key;
+            if (METRIC == KB2_METRIC_L2) {
+                key = qq + xn[col] - 2.f * acc[i][j];
+            } else {
+                key = -acc[i][j];
+            }
+            if (bitset) {
+                const int64_t row = rows ? (int64_t)rows[row_base + col] : (row_base + col);
+                if (bit_is_set(bitset, row)) key = INFINITY;
+            }
+            keys[(int64_t)q * ldk + col] = key;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- key selection
+// grid (nq, nsplit): CTA (q, s) selects the K smallest keys of keys[q][c0..c1) and writes them
+// sorted to partial[q][slot_base + s][0..kout).  Position written = pos_base + column.
+__global__ void __launch_bounds__(kScanThreads)
+select_keys_kernel(const float* __restrict__ keys, int64_t ldk, int ncols, int K, int kout,
+                   uint64_t* __restrict__ partial, int slots_per_query, int slot_base, uint32_t pos_base) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* lists = (uint64_t*)smem_raw;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t q = blockIdx.x;
+    const int nsplit = gridDim.y, s = blockIdx.y;
+    const int per = (((ncols + nsplit - 1) / nsplit) + 31) / 32 * 32;
+    const int c0 = s * per;
+    const int c1 = min(ncols, c0 + per);
+
+    WarpTopK tk;
+    tk.init(lists + warp * K, K, lane);
+    const float* row = keys + q * ldk;
+    for (int base = c0 + warp * kWarp; base < c1; base += kScanWarps * kWarp) {
+        const int c = base + lane;
+        const bool valid = c < c1;
+        const float key = valid ? row[c] : INFINITY;
+        // +inf keys are filtered rows: never candidates
+        tk.push(pack_kp(key, pos_base + (uint32_t)c), valid && key < INFINITY, lane);
+    }
+    uint64_t* out = partial + (q * slots_per_query + slot_base + s) * (int64_t)kout;
+    block_emit_topk(lists, K, out, kout);
+}
+
+}  // namespace kb2

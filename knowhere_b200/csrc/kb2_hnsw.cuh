@@ -1,0 +1,736 @@
+// kb2_hnsw.cuh — HNSW: graph container in the reference's layout, host-side construction, and the
+// device search kernel (greedy descent on the upper levels + best-first beam on level 0).
+//
+// Reference path being replaced:
+//   v2_hnsw_searcher::{search, greedy_search_top_levels, greedy_update_nearest,
+//                      search_on_a_level, evaluate_single_node}   K/impl/HnswSearcher.h:116-432
+//   NeighborSetPopList (sorted array, upper_bound insert, cursor)  K/impl/Neighbor.h:46-150
+//   IndexHNSWWrapper::search (visited bitset per query, IP negation) src/index/hnsw/impl/IndexHNSWWrapper.cc:67-205
+//   graph layout: neighbors/offsets/levels/cum_nneighbor_per_level   K/impl/HNSW.h, HNSW.cpp:53-89,202-225
+//
+// Device mapping: ONE WARP PER QUERY.  All <=32 link slots of the expanded node are examined
+// at once (lane = slot), the visited test-and-set is one atomicOr per lane on a per-warp bitmap in
+// HBM, distances are computed with the lanes striding the dimension (coalesced 128-bit row reads,
+// two rows in flight), and the candidate pool is a sorted array in shared memory updated by
+// warp-cooperative shifts.  The algorithm state after each expansion equals the reference's
+// (same pool capacity max(ef,k), same strict/upper_bound tie rules), so with identical graph and
+// distances the result is identical; distances differ by fp32 summation order only.
+#pragma once
+#include <omp.h>
+
+#include <cmath>
+#include <queue>
+
+#include "kb2_blob.h"
+#include "kb2_index.cuh"
+
+namespace kb2 {
+
+struct HnswSearchParams {
+    const float* vecs;        // [n][d]
+    int d;
+    int64_t n;
+    const int32_t* neighbors;
+    const int64_t* offsets;   // [n+1]
+    const int32_t* cum;       // cum_nneighbor_per_level
+    int32_t entry_point, max_level;
+    int metric;
+    const float* queries;
+    int nq, ef_cap, k;
+    uint32_t* visited;        // [total_warps][nwords]
+    int64_t nwords;
+    int32_t* vis_log;         // [total_warps][log_cap]
+    int log_cap;
+    int* next_query;          // work counter
+    const int64_t* labels;
+    int64_t* out_ids;
+    float* out_dist;
+    unsigned long long* stats;  // [0] ndis, [1] nhops
+};
+
+constexpr int kHnswWarps = 4;  // warps (queries in flight) per CTA
+
+// distance key of node v to the query held in shared memory (lanes stride the dimension)
+template <int METRIC>
+__device__ __forceinline__ float
+hnsw_key(const float* __restrict__ vecs, int d, const float* s_q, int32_t v, int lane) {
+    const float* x = vecs + (int64_t)v * d;
+    float acc = 0.f;
+    if ((d & 3) == 0) {
+        const float4* x4 = reinterpret_cast<const float4*>(x);
+        const float4* q4 = reinterpret_cast<const float4*>(s_q);
+        for (int j = lane; j < (d >> 2); j += kWarp) {
+            const float4 a = ldg_stream_f4(x4 + j);
+            const float4 b = q4[j];
+            if (METRIC == KB2_METRIC_L2) {
+                float t;
+                t = b.x - a.x; acc = fmaf(t, t, acc);
+                t = b.y - a.y; acc = fmaf(t, t, acc);
+                t = b.z - a.z; acc = fmaf(t, t, acc);
+                t = b.w - a.w; acc = fmaf(t, t, acc);
+            } else {
+                acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc);
+                acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+            }
+        }
+    } else {
+        for (int j = lane; j < d; j += kWarp) {
+            if (METRIC == KB2_METRIC_L2) {
+                const float t = s_q[j] - x[j];
+                acc = fmaf(t, t, acc);
+            } else {
+                acc = fmaf(s_q[j], x[j], acc);
+            }
+        }
+    }
+    acc = warp_sum(acc);
+    return (METRIC == KB2_METRIC_L2) ? acc : -acc;  // NegativeDistanceComputer for IP
+}
+
+// two rows at once (independent loads in flight)
+template <int METRIC>
+__device__ __forceinline__ void
+hnsw_key2(const float* __restrict__ vecs, int d, const float* s_q, int32_t v0, int32_t v1, int lane, float& k0,
+          float& k1) {
+    if ((d & 3) != 0) {
+        k0 = hnsw_key<METRIC>(vecs, d, s_q, v0, lane);
+        k1 = hnsw_key<METRIC>(vecs, d, s_q, v1, lane);
+        return;
+    }
+    const float4* x0 = reinterpret_cast<const float4*>(vecs + (int64_t)v0 * d);
+    const float4* x1 = reinterpret_cast<const float4*>(vecs + (int64_t)v1 * d);
+    const float4* q4 = reinterpret_cast<const float4*>(s_q);
+    float a0 = 0.f, a1 = 0.f;
+    for (int j = lane; j < (d >> 2); j += kWarp) {
+        const float4 a = ldg_stream_f4(x0 + j);
+        const float4 c = ldg_stream_f4(x1 + j);
+        const float4 b = q4[j];
+        if (METRIC == KB2_METRIC_L2) {
+            float t;
+            t = b.x - a.x; a0 = fmaf(t, t, a0); t = b.y - a.y; a0 = fmaf(t, t, a0);
+            t = b.z - a.z; a0 = fmaf(t, t, a0); t = b.w - a.w; a0 = fmaf(t, t, a0);
+            t = b.x - c.x; a1 = fmaf(t, t, a1); t = b.y - c.y; a1 = fmaf(t, t, a1);
+            t = b.z - c.z; a1 = fmaf(t, t, a1); t = b.w - c.w; a1 = fmaf(t, t, a1);
+        } else {
+            a0 = fmaf(a.x, b.x, a0); a0 = fmaf(a.y, b.y, a0); a0 = fmaf(a.z, b.z, a0); a0 = fmaf(a.w, b.w, a0);
+            a1 = fmaf(c.x, b.x, a1); a1 = fmaf(c.y, b.y, a1); a1 = fmaf(c.z, b.z, a1); a1 = fmaf(c.w, b.w, a1);
+        }
+    }
+    a0 = warp_sum(a0);
+    a1 = warp_sum(a1);
+    k0 = (METRIC == KB2_METRIC_L2) ? a0 : -a0;
+    k1 = (METRIC == KB2_METRIC_L2) ? a1 : -a1;
+}
+
+// dynamic smem per warp: d floats (query, 16B aligned) + ef_cap * (4 + 4)
+template <int METRIC>
+__global__ void __launch_bounds__(kHnswWarps * 32)
+hnsw_search_kernel(HnswSearchParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int dpad = (p.d + 3) & ~3;
+    const size_t per_warp = (size_t)dpad * 4 + (size_t)p.ef_cap * 8;
+    unsigned char* mine = smem_raw + (size_t)warp * per_warp;
+    float* s_q = (float*)mine;
+    float* s_dist = (float*)(mine + (size_t)dpad * 4);
+    uint32_t* s_id = (uint32_t*)(s_dist + p.ef_cap);  // bit31 = checked flag
+
+    const int64_t gw = (int64_t)blockIdx.x * kHnswWarps + warp;
+    uint32_t* vis = p.visited + gw * p.nwords;
+    int32_t* vlog = p.vis_log + gw * p.log_cap;
+    unsigned long long ndis_tot = 0, nhops_tot = 0;
+
+    for (;;) {
+        int q = 0;
+        if (lane == 0) q = atomicAdd(p.next_query, 1);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if (q >= p.nq) break;
+        for (int j = lane; j < p.d; j += kWarp) s_q[j] = p.queries[(int64_t)q * p.d + j];
+        __syncwarp();
+
+        // ---- greedy descent on the upper levels (HnswSearcher.h:116-170,334-356)
+        int32_t nearest = p.entry_point;
+        float d_nearest = hnsw_key<METRIC>(p.vecs, p.d, s_q, nearest, lane);
+        for (int level = p.max_level; level >= 1; level--) {
+            for (;;) {
+                const int32_t prev = nearest;
+                const int64_t begin = p.offsets[prev] + p.cum[level];
+                const int64_t end = p.offsets[prev] + p.cum[level + 1];
+                bool done = false;
+                for (int64_t b = begin; b < end && !done; b += kWarp) {
+                    const int32_t v = (b + lane < end) ? p.neighbors[b + lane] : -1;
+                    const unsigned neg = __ballot_sync(0xffffffffu, v < 0);
+                    const int cnt = neg ? (__ffs(neg) - 1) : kWarp;
+                    float myk = INFINITY;
+                    for (int j = 0; j < cnt; j += 2) {
+                        const int32_t va = __shfl_sync(0xffffffffu, v, j);
+                        float ka, kb = INFINITY;
+                        if (j + 1 < cnt) {
+                            const int32_t vb = __shfl_sync(0xffffffffu, v, j + 1);
+                            hnsw_key2<METRIC>(p.vecs, p.d, s_q, va, vb, lane, ka, kb);
+                        } else {
+                            ka = hnsw_key<METRIC>(p.vecs, p.d, s_q, va, lane);
+                        }
+                        if (lane == j) myk = ka;
+                        if (lane == j + 1) myk = kb;
+                    }
+                    ndis_tot += cnt;
+                    // sequential "if (dis < d_nearest)" over the slots == first strict minimum
+                    float bk = myk;
+                    int bl = lane;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const float ok = __shfl_xor_sync(0xffffffffu, bk, o);
+                        const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+                        if (ok < bk || (ok == bk && ol < bl)) { bk = ok; bl = ol; }
+                    }
+                    if (bk < d_nearest) {
+                        d_nearest = bk;
+                        nearest = __shfl_sync(0xffffffffu, v, bl);
+                    }
+                    if (cnt < kWarp) done = true;
+                }
+                nhops_tot++;
+                if (nearest == prev) break;
+            }
+        }
+
+        // ---- level 0 beam (HnswSearcher.h:296-332,390-432; Neighbor.h:46-150)
+        const int cap = p.ef_cap;
+        int size = 0, cursor = 0, logn = 0;
+        bool log_overflow = false;
+        if (lane == 0) {
+            s_dist[0] = d_nearest;
+            s_id[0] = (uint32_t)nearest;
+            atomicOr(&vis[nearest >> 5], 1u << (nearest & 31));
+            vlog[0] = nearest;
+        }
+        size = 1;
+        logn = 1;
+        __syncwarp();
+
+        while (cursor < size) {
+            // pop: closest unchecked entry
+            const uint32_t cur_id = s_id[cursor] & 0x7fffffffu;
+            __syncwarp();
+            if (lane == 0) s_id[cursor] |= 0x80000000u;
+            __syncwarp();
+            cursor++;
+            while (cursor < size && (s_id[cursor] & 0x80000000u)) cursor++;
+            nhops_tot++;
+
+            const int64_t begin = p.offsets[cur_id] + p.cum[0];
+            const int64_t end = p.offsets[cur_id] + p.cum[1];
+            bool done = false;
+            for (int64_t b = begin; b < end && !done; b += kWarp) {
+                const int32_t v = (b + lane < end) ? p.neighbors[b + lane] : -1;
+                const unsigned neg = __ballot_sync(0xffffffffu, v < 0);
+                const int cnt = neg ? (__ffs(neg) - 1) : kWarp;
+                if (cnt < kWarp) done = true;
+                bool fresh = false;
+                if (lane < cnt) {
+                    const uint32_t bit = 1u << (v & 31);
+                    const uint32_t old = atomicOr(&vis[v >> 5], bit);
+                    fresh = !(old & bit);
+                }
+                unsigned fm = __ballot_sync(0xffffffffu, fresh);
+                const int nf = __popc(fm);
+                if (nf == 0) continue;
+                // remember touched ids so the bitmap can be cleared cheaply afterwards
+                if (logn + nf <= p.log_cap) {
+                    if (fresh) vlog[logn + __popc(fm & ((1u << lane) - 1))] = v;
+                } else {
+                    log_overflow = true;
+                }
+                logn += nf;
+                ndis_tot += nf;
+                // distances of the fresh neighbours, two at a time, in slot order
+                float myk = INFINITY;
+                unsigned rem = fm;
+                while (rem) {
+                    const int ja = __ffs(rem) - 1;
+                    rem &= rem - 1;
+                    const int32_t va = __shfl_sync(0xffffffffu, v, ja);
+                    float ka, kb = INFINITY;
+                    int jb = -1;
+                    if (rem) {
+                        jb = __ffs(rem) - 1;
+                        rem &= rem - 1;
+                        const int32_t vb = __shfl_sync(0xffffffffu, v, jb);
+                        hnsw_key2<METRIC>(p.vecs, p.d, s_q, va, vb, lane, ka, kb);
+                    } else {
+                        ka = hnsw_key<METRIC>(p.vecs, p.d, s_q, va, lane);
+                    }
+                    if (lane == ja) myk = ka;
+                    if (lane == jb) myk = kb;
+                }
+                // insert in slot order (the reference inserts batch-4 results in the same order)
+                unsigned ins = fm;
+                while (ins) {
+                    const int j = __ffs(ins) - 1;
+                    ins &= ins - 1;
+                    const float key = __shfl_sync(0xffffffffu, myk, j);
+                    const uint32_t id = (uint32_t)__shfl_sync(0xffffffffu, v, j);
+                    // pos = upper_bound(key)
+                    int pos = 0;
+                    for (int base = 0; base < size; base += kWarp) {
+                        const int i = base + lane;
+                        const bool le = (i < size) && (s_dist[i] <= key);
+                        pos += __popc(__ballot_sync(0xffffffffu, le));
+                    }
+                    if (pos >= cap) continue;
+                    const int newsize = min(size + 1, cap);
+                    for (int hi = newsize - 1; hi > pos; hi -= kWarp) {
+                        const int i = hi - lane;
+                        float td = 0.f;
+                        uint32_t ti = 0;
+                        if (i > pos) { td = s_dist[i - 1]; ti = s_id[i - 1]; }
+                        __syncwarp();
+                        if (i > pos) { s_dist[i] = td; s_id[i] = ti; }
+                        __syncwarp();
+                    }
+                    if (lane == 0) { s_dist[pos] = key; s_id[pos] = id; }
+                    __syncwarp();
+                    size = newsize;
+                    if (pos < cursor) cursor = pos;
+                }
+            }
+        }
+
+        // ---- results (HnswSearcher.h:414-428; IP sign restored as IndexHNSWWrapper.cc:198-204)
+        const int len = min(size, p.k);
+        for (int i = lane; i < p.k; i += kWarp) {
+            const int64_t o = (int64_t)q * p.k + i;
+            if (i < len) {
+                const int64_t id = (int64_t)(s_id[i] & 0x7fffffffu);
+                p.out_ids[o] = p.labels ? p.labels[id] : id;
+                p.out_dist[o] = (METRIC == KB2_METRIC_L2) ? s_dist[i] : -s_dist[i];
+            } else {
+                p.out_ids[o] = -1;
+                p.out_dist[o] = (METRIC == KB2_METRIC_L2) ? FLT_MAX : -FLT_MAX;
+            }
+        }
+        // ---- clear the visited bits this query set
+        __syncwarp();
+        if (!log_overflow) {
+            for (int i = lane; i < logn; i += kWarp) vis[vlog[i] >> 5] = 0u;
+        } else {
+            for (int64_t i = lane; i < p.nwords; i += kWarp) vis[i] = 0u;
+        }
+        __syncwarp();
+    }
+    if (p.stats) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            // every lane carries the same totals; nothing to reduce, but keep lanes converged
+        }
+        if (lane == 0) {
+            atomicAdd(&p.stats[0], ndis_tot);
+            atomicAdd(&p.stats[1], nhops_tot);
+        }
+    }
+}
+
+// ============================================================================================
+struct HnswIndex : IndexBase {
+    int M = 30, efConstruction = 360;
+    int64_t n = 0;
+    int32_t entry_point = -1, max_level = -1;
+    // host copies (reference layout)
+    std::vector<float> h_vecs;
+    std::vector<int32_t> h_levels, h_neighbors, h_cum;
+    std::vector<int64_t> h_offsets;
+    std::vector<int64_t> h_labels;
+    bool custom_labels = false;
+    // device
+    DevBuf<float> d_vecs;
+    DevBuf<int32_t> d_neighbors, d_cum, d_vlog;
+    DevBuf<int64_t> d_offsets, d_labels;
+    DevBuf<uint32_t> d_visited;
+    DevBuf<int> d_next;
+    bool uploaded = false;
+    int64_t last_ndis = 0, last_nhops = 0;
+
+    void train(const float*, int64_t) override {}
+    bool is_trained() const override { return true; }
+    bool has_raw() const override { return true; }
+    int64_t count() const override { return n; }
+    int64_t size_bytes() const override {
+        return (int64_t)(h_vecs.size() * 4 + h_neighbors.size() * 4 + h_offsets.size() * 8 + h_levels.size() * 4);
+    }
+
+    void
+    set_default_cum(int nlevels) {
+        // K/impl/HNSW.cpp:78-89 set_default_probas: level 0 has 2*M links, upper levels M
+        h_cum.assign(1, 0);
+        for (int l = 0; l < nlevels; l++) h_cum.push_back(h_cum.back() + (l == 0 ? 2 * M : M));
+    }
+
+    // ------------------------------------------------------------ host-side construction
+    inline float
+    host_key(const float* a, const float* b) const {
+        float acc = 0.f;
+        if (metric == KB2_METRIC_L2) {
+            for (int j = 0; j < dim; j++) { const float t = a[j] - b[j]; acc += t * t; }
+            return acc;
+        }
+        for (int j = 0; j < dim; j++) acc += a[j] * b[j];
+        return -acc;
+    }
+    struct Cand { float key; int32_t id; };
+    struct CandLess { bool operator()(const Cand& a, const Cand& b) const { return a.key < b.key; } };
+    struct CandGreater { bool operator()(const Cand& a, const Cand& b) const { return a.key > b.key; } };
+
+    int32_t* links(int32_t i, int level) { return h_neighbors.data() + h_offsets[i] + h_cum[level]; }
+    int nlinks(int level) const { return h_cum[level + 1] - h_cum[level]; }
+
+    // heuristic neighbour selection (HNSW paper alg. 4; reference shrink_neighbor_list, K/impl/HNSW.cpp:231-300)
+    void
+    select_neighbors(std::vector<Cand>& cands /* ascending */, int maxn, std::vector<Cand>& out) const {
+        out.clear();
+        for (const Cand& c : cands) {
+            bool good = true;
+            for (const Cand& s : out) {
+                if (host_key(&h_vecs[(size_t)c.id * dim], &h_vecs[(size_t)s.id * dim]) < c.key) { good = false; break; }
+            }
+            if (good) {
+                out.push_back(c);
+                if ((int)out.size() >= maxn) return;
+            }
+        }
+    }
+    void
+    search_layer(const float* qv, int32_t ep, float ep_key, int ef, int level, std::vector<omp_lock_t>& locks,
+                 std::vector<uint32_t>& vis_tag, uint32_t tag, std::vector<Cand>& result) {
+        std::priority_queue<Cand, std::vector<Cand>, CandGreater> cand;   // min-heap
+        std::priority_queue<Cand, std::vector<Cand>, CandLess> best;      // max-heap
+        cand.push({ep_key, ep});
+        best.push({ep_key, ep});
+        vis_tag[ep] = tag;
+        std::vector<int32_t> nb;
+        while (!cand.empty()) {
+            Cand c = cand.top();
+            if (c.key > best.top().key && (int)best.size() >= ef) break;
+            cand.pop();
+            nb.clear();
+            omp_set_lock(&locks[c.id]);
+            {
+                const int32_t* l = links(c.id, level);
+                for (int j = 0; j < nlinks(level); j++) { if (l[j] < 0) break; nb.push_back(l[j]); }
+            }
+            omp_unset_lock(&locks[c.id]);
+            for (int32_t v : nb) {
+                if (vis_tag[v] == tag) continue;
+                vis_tag[v] = tag;
+                const float kv = host_key(qv, &h_vecs[(size_t)v * dim]);
+                if ((int)best.size() < ef || kv < best.top().key) {
+                    cand.push({kv, v});
+                    best.push({kv, v});
+                    if ((int)best.size() > ef) best.pop();
+                }
+            }
+        }
+        result.clear();
+        while (!best.empty()) { result.push_back(best.top()); best.pop(); }
+        std::reverse(result.begin(), result.end());
+    }
+    void
+    add_link(int32_t src, int32_t dst, float key, int level) {
+        int32_t* l = links(src, level);
+        const int cap = nlinks(level);
+        if (l[cap - 1] < 0) {
+            int j = 0;
+            while (l[j] >= 0) j++;
+            l[j] = dst;
+            return;
+        }
+        std::vector<Cand> cands;
+        cands.push_back({key, dst});
+        for (int j = 0; j < cap; j++)
+            cands.push_back({host_key(&h_vecs[(size_t)src * dim], &h_vecs[(size_t)l[j] * dim]), l[j]});
+        std::sort(cands.begin(), cands.end(), [](const Cand& a, const Cand& b) { return a.key < b.key; });
+        std::vector<Cand> sel;
+        select_neighbors(cands, cap, sel);
+        for (int j = 0; j < cap; j++) l[j] = j < (int)sel.size() ? sel[j].id : -1;
+    }
+
+    // IndexNode::Add for HNSW == build (faiss_hnsw.cc:2073-2178 -> K/IndexHNSW.cpp:83-215)
+    void
+    add(const float* x, int64_t nadd, const int64_t* ids) override {
+        KB2_REQUIRE(n == 0, KB2_NOT_IMPLEMENTED, "HNSW: incremental add after the first build is not implemented");
+        KB2_REQUIRE(nadd > 0 && nadd < (1ll << 31), KB2_INVALID_ARGS, "bad row count");
+        h_vecs.resize((size_t)nadd * dim);
+        KB2_CUDA_CHECK(cudaMemcpy(h_vecs.data(), x, h_vecs.size() * 4, cudaMemcpyDefault));
+        if (ids) {
+            h_labels.resize(nadd);
+            KB2_CUDA_CHECK(cudaMemcpy(h_labels.data(), ids, nadd * 8, cudaMemcpyDefault));
+            custom_labels = true;
+        }
+        n = nadd;
+        // levels: floor(-ln(U) / ln(M)), RNG seed 12345 (K/impl/HNSW.cpp:60-63,92-105)
+        std::mt19937 rng(12345);
+        std::uniform_real_distribution<double> uni(0.0, 1.0);
+        const double mult = 1.0 / std::log((double)M);
+        h_levels.resize(n);
+        int top = 0;
+        for (int64_t i = 0; i < n; i++) {
+            double u = uni(rng);
+            if (u <= 0) u = 1e-12;
+            const int lv = (int)(-std::log(u) * mult);
+            h_levels[i] = lv + 1;
+            top = std::max(top, lv);
+        }
+        set_default_cum(top + 1);
+        h_offsets.assign(n + 1, 0);
+        for (int64_t i = 0; i < n; i++) h_offsets[i + 1] = h_offsets[i] + h_cum[h_levels[i]];
+        h_neighbors.assign(h_offsets[n], -1);
+        // insertion order: highest level first (K/IndexHNSW.cpp:112-166)
+        std::vector<int32_t> order(n);
+        for (int64_t i = 0; i < n; i++) order[i] = (int32_t)i;
+        std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return h_levels[a] > h_levels[b]; });
+        std::vector<omp_lock_t> locks(n);
+        for (auto& l : locks) omp_init_lock(&l);
+        entry_point = order[0];
+        max_level = h_levels[order[0]] - 1;
+        const int nthreads = omp_get_max_threads();
+        std::vector<std::vector<uint32_t>> tags(nthreads, std::vector<uint32_t>(n, 0));
+        std::vector<uint32_t> tagc(nthreads, 0);
+        omp_lock_t global;
+        omp_init_lock(&global);
+        int64_t start = 1;
+        while (start < n) {
+            int64_t stop = start;
+            const int lv = h_levels[order[start]];
+            while (stop < n && h_levels[order[stop]] == lv) stop++;
+#pragma omp parallel for schedule(dynamic, 16)
+            for (int64_t t = start; t < stop; t++) {
+                const int tid = omp_get_thread_num();
+                const int32_t pt = order[t];
+                const int pt_level = h_levels[pt] - 1;
+                const float* qv = &h_vecs[(size_t)pt * dim];
+                int32_t nearest;
+                int cur_max;
+                omp_set_lock(&global);
+                nearest = entry_point;
+                cur_max = max_level;
+                omp_unset_lock(&global);
+                float d_nearest = host_key(qv, &h_vecs[(size_t)nearest * dim]);
+                for (int level = cur_max; level > pt_level; level--) {
+                    bool changed = true;
+                    while (changed) {
+                        changed = false;
+                        std::vector<int32_t> nb;
+                        omp_set_lock(&locks[nearest]);
+                        const int32_t* l = links(nearest, level);
+                        for (int j = 0; j < nlinks(level); j++) { if (l[j] < 0) break; nb.push_back(l[j]); }
+                        omp_unset_lock(&locks[nearest]);
+                        for (int32_t v : nb) {
+                            const float kv = host_key(qv, &h_vecs[(size_t)v * dim]);
+                            if (kv < d_nearest) { d_nearest = kv; nearest = v; changed = true; }
+                        }
+                    }
+                }
+                std::vector<Cand> res, sel;
+                for (int level = std::min(pt_level, cur_max); level >= 0; level--) {
+                    search_layer(qv, nearest, d_nearest, efConstruction, level, locks, tags[tid], ++tagc[tid], res);
+                    // drop self if present
+                    res.erase(std::remove_if(res.begin(), res.end(), [&](const Cand& c) { return c.id == pt; }), res.end());
+                    select_neighbors(res, nlinks(level), sel);  // K/impl/HNSW.cpp add_links_starting_from: M = nb_neighbors(level)
+                    omp_set_lock(&locks[pt]);
+                    {
+                        int32_t* l = links(pt, level);
+                        for (int j = 0; j < (int)sel.size() && j < nlinks(level); j++) l[j] = sel[j].id;
+                    }
+                    omp_unset_lock(&locks[pt]);
+                    for (const Cand& s : sel) {
+                        omp_set_lock(&locks[s.id]);
+                        add_link(s.id, pt, s.key, level);
+                        omp_unset_lock(&locks[s.id]);
+                    }
+                    if (!res.empty()) { nearest = res[0].id; d_nearest = res[0].key; }
+                }
+            }
+            if (lv - 1 > max_level) { max_level = lv - 1; entry_point = order[start]; }
+            start = stop;
+        }
+        for (auto& l : locks) omp_destroy_lock(&l);
+        omp_destroy_lock(&global);
+        uploaded = false;
+    }
+
+    void
+    import_graph(int64_t nn, const float* vectors, const int32_t* levels, const int64_t* offsets, const int32_t* neighbors,
+                 const int32_t* cum, int n_cum, int32_t ep, int32_t ml) {
+        KB2_REQUIRE(nn > 0 && n_cum >= 2, KB2_INVALID_ARGS, "bad graph");
+        n = nn;
+        h_vecs.assign(vectors, vectors + (size_t)nn * dim);
+        h_levels.assign(levels, levels + nn);
+        h_offsets.assign(offsets, offsets + nn + 1);
+        h_neighbors.assign(neighbors, neighbors + offsets[nn]);
+        h_cum.assign(cum, cum + n_cum);
+        entry_point = ep;
+        max_level = ml;
+        KB2_REQUIRE(max_level + 1 < n_cum, KB2_INVALID_ARGS, "cum_nneighbor_per_level shorter than max_level");
+        uploaded = false;
+    }
+
+    void
+    upload() {
+        if (uploaded) return;
+        d_vecs.alloc_exact(h_vecs.size());
+        d_neighbors.alloc_exact(h_neighbors.size());
+        d_offsets.alloc_exact(h_offsets.size());
+        d_cum.alloc_exact(h_cum.size() + 1);
+        KB2_CUDA_CHECK(cudaMemcpyAsync(d_vecs.p, h_vecs.data(), h_vecs.size() * 4, cudaMemcpyHostToDevice, stream));
+        KB2_CUDA_CHECK(cudaMemcpyAsync(d_neighbors.p, h_neighbors.data(), h_neighbors.size() * 4, cudaMemcpyHostToDevice, stream));
+        KB2_CUDA_CHECK(cudaMemcpyAsync(d_offsets.p, h_offsets.data(), h_offsets.size() * 8, cudaMemcpyHostToDevice, stream));
+        KB2_CUDA_CHECK(cudaMemcpyAsync(d_cum.p, h_cum.data(), h_cum.size() * 4, cudaMemcpyHostToDevice, stream));
+        if (custom_labels) {
+            d_labels.alloc_exact(h_labels.size());
+            KB2_CUDA_CHECK(cudaMemcpyAsync(d_labels.p, h_labels.data(), h_labels.size() * 8, cudaMemcpyHostToDevice, stream));
+        }
+        d_next.ensure(1);
+        KB2_CUDA_CHECK(cudaStreamSynchronize(stream));
+        uploaded = true;
+    }
+
+    void
+    search(const float* q, int64_t nq, int k, const JsonObj& cfg, const uint8_t* bitset, int64_t, int64_t* out_ids,
+           float* out_dist) override {
+        KB2_REQUIRE(n > 0 && entry_point >= 0, KB2_EMPTY_INDEX, "index is empty");
+        KB2_REQUIRE(bitset == nullptr, KB2_NOT_IMPLEMENTED, "HNSW: bitset-filtered search is not implemented yet");
+        upload();
+        static std::once_flag once;
+        std::call_once(once, [] {
+            cudaFuncSetAttribute((const void*)hnsw_search_kernel<KB2_METRIC_L2>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+            cudaFuncSetAttribute((const void*)hnsw_search_kernel<KB2_METRIC_IP>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+        });
+        // base_hnsw_config.h:40-71: search key is "ef", default max(k,16), must be >= k
+        int ef = (int)cfg.get_int("ef", std::max(k, 16));
+        KB2_REQUIRE(ef >= k, KB2_OUT_OF_RANGE_IN_JSON, "ef must be >= k");
+        const int ef_cap = std::max(ef, k);
+        cudaStream_t st = stream;
+        const float* dq = to_device(q, (size_t)nq * dim, s_q);
+        const bool dev_out = is_device_ptr(out_ids);
+        int64_t* d_ids = out_ids;
+        float* d_dist = out_dist;
+        if (!dev_out) {
+            s_out_ids.ensure((size_t)nq * k);
+            s_out_dist.ensure((size_t)nq * k);
+            d_ids = s_out_ids.p;
+            d_dist = s_out_dist.p;
+        }
+        const int dpad = (dim + 3) & ~3;
+        const size_t smem = kHnswWarps * ((size_t)dpad * 4 + (size_t)ef_cap * 8);
+        KB2_REQUIRE(smem <= (size_t)kMaxDynSmem, KB2_OUT_OF_RANGE_IN_JSON, "ef / dim too large for shared memory");
+        const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)kMaxDynSmem / std::max<size_t>(smem, 1)));
+        const int grid = (int)std::min<int64_t>((nq + kHnswWarps - 1) / kHnswWarps, (int64_t)kNumSMs * ctas_per_sm);
+        const int64_t total_warps = (int64_t)grid * kHnswWarps;
+        const int64_t nwords = (n + 31) / 32;
+        const int log_cap = (int)std::min<int64_t>(n, (int64_t)ef_cap * h_cum[1] * 4 + 256);
+        if (d_visited.n < (size_t)(total_warps * nwords)) {
+            d_visited.ensure((size_t)(total_warps * nwords));
+            KB2_CUDA_CHECK(cudaMemsetAsync(d_visited.p, 0, (size_t)(total_warps * nwords) * 4, st));
+        }
+        d_vlog.ensure((size_t)(total_warps * log_cap));
+        KB2_CUDA_CHECK(cudaMemsetAsync(d_next.p, 0, 4, st));
+        KB2_CUDA_CHECK(cudaMemsetAsync(d_counter.p, 0, 16, st));
+        HnswSearchParams p{};
+        p.vecs = d_vecs.p;
+        p.d = dim;
+        p.n = n;
+        p.neighbors = d_neighbors.p;
+        p.offsets = d_offsets.p;
+        p.cum = d_cum.p;
+        p.entry_point = entry_point;
+        p.max_level = max_level;
+        p.metric = metric;
+        p.queries = dq;
+        p.nq = (int)nq;
+        p.ef_cap = ef_cap;
+        p.k = k;
+        p.visited = d_visited.p;
+        p.nwords = nwords;
+        p.vis_log = d_vlog.p;
+        p.log_cap = log_cap;
+        p.next_query = d_next.p;
+        p.labels = custom_labels ? d_labels.p : nullptr;
+        p.out_ids = d_ids;
+        p.out_dist = d_dist;
+        p.stats = d_counter.p;
+        if (timing) KB2_CUDA_CHECK(cudaEventRecord(ev0, st));
+        if (metric == KB2_METRIC_L2)
+            hnsw_search_kernel<KB2_METRIC_L2><<<grid, kHnswWarps * 32, smem, st>>>(p);
+        else
+            hnsw_search_kernel<KB2_METRIC_IP><<<grid, kHnswWarps * 32, smem, st>>>(p);
+        if (timing) KB2_CUDA_CHECK(cudaEventRecord(ev1, st));
+        last.launches++;
+        KB2_CUDA_CHECK(cudaGetLastError());
+        unsigned long long hs[2] = {0, 0};
+        KB2_CUDA_CHECK(cudaMemcpyAsync(hs, d_counter.p, 16, cudaMemcpyDeviceToHost, st));
+        results_out(nq, k, out_ids, out_dist, d_ids, d_dist);
+        last_ndis = (int64_t)hs[0];
+        last_nhops = (int64_t)hs[1];
+        last.codes = last_ndis;
+        last.code_bytes = last_ndis * (int64_t)dim * 4 + last_nhops * (int64_t)h_cum[1] * 4;
+        last.pairs = last_nhops;
+        if (timing) KB2_CUDA_CHECK(cudaEventElapsedTime(&last_kernel_ms, ev0, ev1));
+    }
+
+    void
+    get_vectors(const int64_t* ids, int64_t cnt, float* out) override {
+        KB2_REQUIRE(!custom_labels, KB2_NOT_IMPLEMENTED, "GetVectorByIds with custom ids");
+        std::vector<int64_t> h(cnt);
+        KB2_CUDA_CHECK(cudaMemcpy(h.data(), ids, cnt * 8, cudaMemcpyDefault));
+        for (int64_t i = 0; i < cnt; i++) {
+            KB2_REQUIRE(h[i] >= 0 && h[i] < n, KB2_INVALID_ARGS, "id out of range");
+            KB2_CUDA_CHECK(cudaMemcpy(out + i * dim, &h_vecs[(size_t)h[i] * dim], (size_t)dim * 4, cudaMemcpyDefault));
+        }
+    }
+
+    void
+    serialize(BlobWriter& w) {
+        w.put<int32_t>(M);
+        w.put<int32_t>(efConstruction);
+        w.put<int64_t>(n);
+        w.put<int32_t>(entry_point);
+        w.put<int32_t>(max_level);
+        w.put<int32_t>((int32_t)h_cum.size());
+        w.put<int32_t>(custom_labels ? 1 : 0);
+        w.put_bytes(h_cum.data(), h_cum.size() * 4);
+        w.put_bytes(h_levels.data(), h_levels.size() * 4);
+        w.put_bytes(h_offsets.data(), h_offsets.size() * 8);
+        w.put_bytes(h_neighbors.data(), h_neighbors.size() * 4);
+        w.put_bytes(h_vecs.data(), h_vecs.size() * 4);
+        if (custom_labels) w.put_bytes(h_labels.data(), h_labels.size() * 8);
+    }
+    void
+    deserialize(BlobReader& r) {
+        M = r.get<int32_t>();
+        efConstruction = r.get<int32_t>();
+        n = r.get<int64_t>();
+        entry_point = r.get<int32_t>();
+        max_level = r.get<int32_t>();
+        const int ncum = r.get<int32_t>();
+        custom_labels = r.get<int32_t>() != 0;
+        h_cum.resize(ncum);
+        memcpy(h_cum.data(), r.get_bytes((size_t)ncum * 4), (size_t)ncum * 4);
+        h_levels.resize(n);
+        memcpy(h_levels.data(), r.get_bytes((size_t)n * 4), (size_t)n * 4);
+        h_offsets.resize(n + 1);
+        memcpy(h_offsets.data(), r.get_bytes((size_t)(n + 1) * 8), (size_t)(n + 1) * 8);
+        h_neighbors.resize(h_offsets[n]);
+        memcpy(h_neighbors.data(), r.get_bytes(h_neighbors.size() * 4), h_neighbors.size() * 4);
+        h_vecs.resize((size_t)n * dim);
+        memcpy(h_vecs.data(), r.get_bytes(h_vecs.size() * 4), h_vecs.size() * 4);
+        if (custom_labels) {
+            h_labels.resize(n);
+            memcpy(h_labels.data(), r.get_bytes((size_t)n * 8), (size_t)n * 8);
+        }
+        uploaded = false;
+    }
+};
+
+}  // namespace kb2

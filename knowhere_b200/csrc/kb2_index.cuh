@@ -1,0 +1,880 @@
+// kb2_index.cuh — host-side index objects behind the C ABI (FLAT, IVF_FLAT, IVF_PQ).
+// They play the role of the reference's IndexNode implementations
+//   FlatIndexNode  src/index/flat/flat.cc:33-427
+//   IvfIndexNode   src/index/ivf/ivf.cc:68-1972   (IVF_FLAT + IVF_PQ branches)
+// but hand the WHOLE query batch to the device in one call (like the in-tree GPU precedent,
+// src/common/cuvs/integration/cuvs_knowhere_index.cuh:508-632) instead of nq thread-pool tasks.
+#pragma once
+#include <mutex>
+#include <vector>
+
+#include "kb2_build.cuh"
+#include "kb2_ivf.cuh"
+#include "kb2_json.h"
+
+namespace kb2 {
+
+constexpr int kMaxK = 1024;            // largest k' any selection kernel keeps
+constexpr int kMaxSortEntries = 8192;  // finalize sorts at most this many candidates per query
+constexpr int kMaxDynSmem = 227 * 1024;
+
+inline void
+init_kernel_attributes() {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        auto set = [](const void* f) {
+            cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+        };
+        set((const void*)finalize_kernel);
+        set((const void*)reduce_partials_kernel);
+        set((const void*)select_keys_kernel);
+        set((const void*)ivfpq_scan_kernel<1, KB2_METRIC_L2>);
+        set((const void*)ivfpq_scan_kernel<1, KB2_METRIC_IP>);
+        set((const void*)ivfpq_scan_kernel<2, KB2_METRIC_L2>);
+        set((const void*)ivfpq_scan_kernel<2, KB2_METRIC_IP>);
+        set((const void*)ivfpq_scan_kernel<3, KB2_METRIC_L2>);
+        set((const void*)ivfpq_scan_kernel<3, KB2_METRIC_IP>);
+        set((const void*)ivfpq_scan_generic_kernel<KB2_METRIC_L2>);
+        set((const void*)ivfpq_scan_generic_kernel<KB2_METRIC_IP>);
+        set((const void*)ivfflat_scan_kernel<KB2_METRIC_L2>);
+        set((const void*)ivfflat_scan_kernel<KB2_METRIC_IP>);
+        cudaGetLastError();
+    });
+}
+
+struct Counters {
+    int64_t launches = 0, codes = 0, code_bytes = 0, pairs = 0, h2d = 0, d2h = 0;
+};
+
+// grow-by-doubling append of `count` elements (device->device or host->device)
+template <typename T>
+inline void
+dev_append(DevBuf<T>& buf, size_t& used, const T* src, size_t count, cudaStream_t st) {
+    if (used + count > buf.n) {
+        size_t cap = std::max(used + count, buf.n * 2);
+        DevBuf<T> nb;
+        nb.ensure(cap);
+        if (used) KB2_CUDA_CHECK(cudaMemcpyAsync(nb.p, buf.p, used * sizeof(T), cudaMemcpyDeviceToDevice, st));
+        KB2_CUDA_CHECK(cudaStreamSynchronize(st));
+        buf = std::move(nb);
+    }
+    if (count) KB2_CUDA_CHECK(cudaMemcpyAsync(buf.p + used, src, count * sizeof(T), cudaMemcpyDefault, st));
+    used += count;
+}
+
+// ============================================================================================
+struct IndexBase {
+    std::string type;
+    int metric = KB2_METRIC_L2, dim = 0, device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int shard_rank = 0, shard_world = 1;
+    std::mutex mu;
+    Counters last;
+    bool timing = false;
+    float last_kernel_ms = 0.f;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DevBuf<unsigned long long> d_counter;
+
+    // per-search scratch (grow-only, reused across calls)
+    DevBuf<float> s_q, s_keys, s_qn, s_out_dist, s_probe_dis;
+    DevBuf<uint64_t> s_partial, s_partial2;
+    DevBuf<int64_t> s_out_ids, s_probe_ids;
+    DevBuf<uint8_t> s_bitset;
+
+    virtual ~IndexBase() {
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (own_stream && stream) cudaStreamDestroy(stream);
+    }
+    void
+    init_common() {
+        KB2_CUDA_CHECK(cudaSetDevice(device));
+        init_kernel_attributes();
+        KB2_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        own_stream = true;
+        KB2_CUDA_CHECK(cudaEventCreate(&ev0));
+        KB2_CUDA_CHECK(cudaEventCreate(&ev1));
+        d_counter.ensure(4);
+    }
+    void
+    set_stream(cudaStream_t s) {
+        if (own_stream && stream) cudaStreamDestroy(stream);
+        stream = s;
+        own_stream = false;
+    }
+
+    // returns a device pointer to `count` floats of `src` (copying H2D on the stream if needed)
+    const float*
+    to_device(const float* src, size_t count, DevBuf<float>& buf, bool count_io = true) {
+        if (is_device_ptr(src)) return src;
+        buf.ensure(count);
+        KB2_CUDA_CHECK(cudaMemcpyAsync(buf.p, src, count * sizeof(float), cudaMemcpyHostToDevice, stream));
+        if (count_io) last.h2d += (int64_t)(count * sizeof(float));
+        return buf.p;
+    }
+    const uint8_t*
+    bitset_to_device(const uint8_t* bits, int64_t nbits) {
+        if (!bits || nbits <= 0) return nullptr;
+        if (is_device_ptr(bits)) return bits;
+        const size_t nbytes = (size_t)((nbits + 7) / 8);
+        s_bitset.ensure(nbytes);
+        KB2_CUDA_CHECK(cudaMemcpyAsync(s_bitset.p, bits, nbytes, cudaMemcpyHostToDevice, stream));
+        last.h2d += (int64_t)nbytes;
+        return s_bitset.p;
+    }
+    // write [nq*k] results to the caller (device: results were produced in place)
+    void
+    results_out(int64_t nq, int k, int64_t* out_ids, float* out_dist, const int64_t* d_ids, const float* d_dist) {
+        if (d_ids != out_ids) {
+            KB2_CUDA_CHECK(cudaMemcpyAsync(out_ids, d_ids, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, stream));
+            KB2_CUDA_CHECK(cudaMemcpyAsync(out_dist, d_dist, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, stream));
+            last.d2h += nq * k * 12;
+        }
+        KB2_CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+
+    virtual void train(const float* x, int64_t n) = 0;
+    virtual void add(const float* x, int64_t n, const int64_t* ids) = 0;
+    virtual void search(const float* q, int64_t nq, int k, const JsonObj& cfg, const uint8_t* bitset, int64_t nbits,
+                        int64_t* out_ids, float* out_dist) = 0;
+    virtual int64_t count() const = 0;
+    virtual int64_t size_bytes() const = 0;
+    virtual bool is_trained() const = 0;
+    virtual bool has_raw() const = 0;
+    virtual void get_vectors(const int64_t* ids, int64_t n, float* out) {
+        throw Error(KB2_NOT_IMPLEMENTED, "GetVectorByIds not supported by this index");
+    }
+};
+
+// ============================================================================================
+// Dense candidate generation shared by FLAT and the IVF coarse quantizer:
+//   partial[nq][S][Kout] <- per (query, base-slice) best Ksel approximate keys
+// ============================================================================================
+struct DensePlan {
+    int Ksel = 32;
+    int S = 1;        // slot capacity per query
+    int used = 0;     // slots filled
+    int64_t stride() const { return (int64_t)S * Ksel; }
+};
+
+inline DensePlan
+dense_candidates(IndexBase& ix, const float* Q, int64_t nq, const float* X, const float* xn, int64_t n, int d,
+                 int metric, int k_need, const uint8_t* bitset, const int32_t* rows) {
+    cudaStream_t st = ix.stream;
+    DensePlan pl;
+    pl.Ksel = next_pow2(std::max(32, k_need));
+    KB2_REQUIRE(pl.Ksel <= kMaxK, KB2_INVALID_ARGS, "k too large for the GPU selection kernels (max 1008)");
+    pl.S = std::max(2, kMaxSortEntries / pl.Ksel);
+    ix.s_partial.ensure((size_t)nq * pl.stride());
+    KB2_CUDA_CHECK(cudaMemsetAsync(ix.s_partial.p, 0xFF, (size_t)nq * pl.stride() * 8, st));
+    ix.s_qn.ensure(nq);
+    if (metric == KB2_METRIC_L2) {
+        row_norms_kernel<<<grid1d(nq * 32, 256), 256, 0, st>>>(Q, nq, d, ix.s_qn.p);
+        ix.last.launches++;
+    }
+    const int64_t max_key_elems = 64ll << 20;  // 256 MB of keys
+    int64_t chunk = std::min<int64_t>(n, std::max<int64_t>(1024, max_key_elems / std::max<int64_t>(nq, 1)));
+    if (chunk < n) chunk = std::max<int64_t>(128, chunk / 128 * 128);
+    ix.s_keys.ensure((size_t)nq * chunk);
+    int nsplit = (int)std::min<int64_t>(std::max<int64_t>(1, (2 * kNumSMs + nq - 1) / nq),
+                                        std::max<int64_t>(1, chunk / 512));
+    nsplit = std::min(nsplit, pl.S - 1);
+    const size_t sel_smem = (size_t)kScanWarps * pl.Ksel * 8;
+    for (int64_t c0 = 0; c0 < n; c0 += chunk) {
+        const int64_t cols = std::min(chunk, n - c0);
+        if (pl.used + nsplit > pl.S) {
+            const int n_in = pl.used * pl.Ksel;
+            const int n_sort = next_pow2(n_in);
+            reduce_partials_kernel<<<(unsigned)nq, 256, (size_t)n_sort * 8, st>>>(ix.s_partial.p, (int)pl.stride(), n_in,
+                                                                                 n_sort, pl.Ksel);
+            ix.last.launches++;
+            pl.used = 1;
+        }
+        dim3 g((unsigned)((cols + GK_BN - 1) / GK_BN), (unsigned)((nq + GK_BM - 1) / GK_BM));
+        if (metric == KB2_METRIC_L2)
+            gemm_keys_kernel<KB2_METRIC_L2><<<g, 256, 0, st>>>(Q, X + c0 * d, ix.s_qn.p, xn + c0, (int)nq, (int)cols, d,
+                                                               ix.s_keys.p, chunk, bitset, rows, c0);
+        else
+            gemm_keys_kernel<KB2_METRIC_IP><<<g, 256, 0, st>>>(Q, X + c0 * d, ix.s_qn.p, xn, (int)nq, (int)cols, d,
+                                                               ix.s_keys.p, chunk, bitset, rows, c0);
+        select_keys_kernel<<<dim3((unsigned)nq, nsplit), kScanThreads, sel_smem, st>>>(
+            ix.s_keys.p, chunk, (int)cols, pl.Ksel, pl.Ksel, ix.s_partial.p, pl.S, pl.used, (uint32_t)c0);
+        ix.last.launches += 2;
+        pl.used += nsplit;
+    }
+    KB2_CUDA_CHECK(cudaGetLastError());
+    return pl;
+}
+
+inline void
+launch_finalize(IndexBase& ix, FinalizeParams fp, int64_t nq) {
+    fp.n_sort = next_pow2(std::max(fp.n_partial, 2));
+    KB2_REQUIRE(fp.n_sort <= kMaxSortEntries, KB2_INTERNAL_ERROR, "finalize: too many partial candidates");
+    KB2_REQUIRE(fp.k_sel <= kMaxK && fp.k_out <= fp.k_sel, KB2_INVALID_ARGS, "k too large");
+    const size_t smem = (size_t)fp.n_sort * 8 + (size_t)fp.k_sel * 16 + (size_t)fp.d * 4 + 16;
+    finalize_kernel<<<(unsigned)nq, 256, smem, ix.stream>>>(fp);
+    ix.last.launches++;
+    KB2_CUDA_CHECK(cudaGetLastError());
+}
+
+// ============================================================================================
+// FLAT
+// ============================================================================================
+struct FlatIndex : IndexBase {
+    DevBuf<float> base, norms;
+    DevBuf<int64_t> labels;   // only when custom ids were given or the shard is offset
+    size_t n_used = 0, norms_used = 0, labels_used = 0;
+    bool custom_labels = false;
+    int64_t n_global_added = 0;  // rows offered to add() over all calls (for sharding)
+
+    void train(const float*, int64_t) override {}
+    bool is_trained() const override { return true; }
+    bool has_raw() const override { return true; }
+    int64_t count() const override { return (int64_t)(n_used / std::max(dim, 1)); }
+    int64_t size_bytes() const override { return (int64_t)(n_used * 4 + norms_used * 4 + labels_used * 8); }
+
+    void
+    add(const float* x, int64_t n, const int64_t* ids) override {
+        if (n <= 0) return;
+        // sharding: this rank keeps the contiguous slice [lo, hi) of each add() call
+        int64_t lo = 0, hi = n;
+        if (shard_world > 1) {
+            lo = n * shard_rank / shard_world;
+            hi = n * (shard_rank + 1) / shard_world;
+        }
+        const int64_t m = hi - lo;
+        const int64_t first_label = n_global_added + lo;
+        const bool need_labels = custom_labels || ids != nullptr || shard_world > 1;
+        if (need_labels && !custom_labels) {
+            // materialise identity labels for what is already stored
+            const int64_t have = count();
+            std::vector<int64_t> h(have);
+            for (int64_t i = 0; i < have; i++) h[i] = i;
+            labels_used = 0;
+            if (have) dev_append(labels, labels_used, h.data(), (size_t)have, stream);
+            KB2_CUDA_CHECK(cudaStreamSynchronize(stream));
+            custom_labels = true;
+        }
+        if (m > 0) {
+            dev_append(base, n_used, x + lo * dim, (size_t)m * dim, stream);
+            DevBuf<float> tmp;
+            tmp.ensure(m);
+            row_norms_kernel<<<grid1d(m * 32, 256), 256, 0, stream>>>(base.p + n_used - (size_t)m * dim, m, dim, tmp.p);
+            dev_append(norms, norms_used, tmp.p, (size_t)m, stream);
+            if (custom_labels) {
+                std::vector<int64_t> h(m);
+                if (ids) {
+                    if (is_device_ptr(ids)) {
+                        KB2_CUDA_CHECK(cudaMemcpyAsync(h.data(), ids + lo, m * 8, cudaMemcpyDeviceToHost, stream));
+                        KB2_CUDA_CHECK(cudaStreamSynchronize(stream));
+                    } else {
+                        memcpy(h.data(), ids + lo, m * 8);
+                    }
+                } else {
+                    for (int64_t i = 0; i < m; i++) h[i] = first_label + i;
+                }
+                dev_append(labels, labels_used, h.data(), (size_t)m, stream);
+            }
+            KB2_CUDA_CHECK(cudaStreamSynchronize(stream));
+        }
+        n_global_added += n;
+    }
+
+    void
+    search(const float* q, int64_t nq, int k, const JsonObj&, const uint8_t* bitset, int64_t nbits, int64_t* out_ids,
+           float* out_dist) override {
+        const int64_t n = count();
+        KB2_REQUIRE(n > 0, KB2_EMPTY_INDEX, "index is empty");
+        KB2_REQUIRE(k > 0 && k <= kMaxK - 16, KB2_INVALID_ARGS, "k out of range (1..1008)");
+        const float* dq = to_device(q, (size_t)nq * dim, s_q);
+        const uint8_t* dbits = bitset_to_device(bitset, nbits);
+        const bool dev_out = is_device_ptr(out_ids);
+        int64_t* d_ids = out_ids;
+        float* d_dist = out_dist;
+        if (!dev_out) {
+            s_out_ids.ensure((size_t)nq * k);
+            s_out_dist.ensure((size_t)nq * k);
+            d_ids = s_out_ids.p;
+            d_dist = s_out_dist.p;
+        }
+        if (timing) KB2_CUDA_CHECK(cudaEventRecord(ev0, stream));
+        // bitset indexes internal rows == labels when labels are the identity (like BitsetView over segment offsets)
+        DensePlan pl = dense_candidates(*this, dq, nq, base.p, norms.p, n, dim, metric, k + 16, dbits, nullptr);
+        if (timing) KB2_CUDA_CHECK(cudaEventRecord(ev1, stream));
+        FinalizeParams fp{};
+        fp.partial = s_partial.p;
+        fp.partial_stride = pl.stride();
+        fp.n_partial = pl.used * pl.Ksel;
+        fp.k_sel = std::min(pl.Ksel, k + 16);
+        fp.k_out = k;
+        fp.rows = nullptr;
+        fp.labels = custom_labels ? labels.p : nullptr;
+        fp.rerank = 1;
+        fp.raw = base.p;
+        fp.raw_by_pos = 1;
+        fp.queries = dq;
+        fp.d = dim;
+        fp.metric = metric;
+        fp.out_ids = d_ids;
+        fp.out_dist = d_dist;
+        fp.out_pos = nullptr;
+        launch_finalize(*this, fp, nq);
+        last.codes = nq * n;
+        last.code_bytes = n * (int64_t)dim * 4;  // list-major contraction reads the base once per batch
+        last.pairs = nq;
+        results_out(nq, k, out_ids, out_dist, d_ids, d_dist);
+        if (timing) KB2_CUDA_CHECK(cudaEventElapsedTime(&last_kernel_ms, ev0, ev1));
+    }
+
+    void
+    get_vectors(const int64_t* ids, int64_t n, float* out) override {
+        KB2_REQUIRE(!custom_labels, KB2_NOT_IMPLEMENTED, "GetVectorByIds with custom ids");
+        std::vector<int64_t> h(n);
+        if (is_device_ptr(ids)) {
+            KB2_CUDA_CHECK(cudaMemcpy(h.data(), ids, n * 8, cudaMemcpyDeviceToHost));
+        } else {
+            memcpy(h.data(), ids, n * 8);
+        }
+        for (int64_t i = 0; i < n; i++) {
+            KB2_REQUIRE(h[i] >= 0 && h[i] < count(), KB2_INVALID_ARGS, "id out of range");
+            KB2_CUDA_CHECK(cudaMemcpyAsync(out + i * dim, base.p + h[i] * dim, (size_t)dim * 4, cudaMemcpyDefault, stream));
+        }
+        KB2_CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+};
+
+// ============================================================================================
+// IVF_FLAT / IVF_PQ
+// ============================================================================================
+struct IvfIndex : IndexBase {
+    bool is_pq = false;
+    int64_t nlist = 128;
+    int M = 0, nbits = 8, dsub = 0;
+    bool refine = false;
+    bool trained = false;
+    // trained state
+    DevBuf<float> centroids, cnorms, pqc;
+    // flat (insertion-order) staging, valid while !sealed
+    DevBuf<int32_t> f_assign;
+    DevBuf<uint8_t> f_codes;
+    DevBuf<float> f_vecs;
+    DevBuf<int64_t> f_labels;
+    size_t f_assign_used = 0, f_codes_used = 0, f_vecs_used = 0, f_labels_used = 0;
+    bool custom_labels = false;
+    int64_t n_total = 0;
+    // sealed (list-order) layout
+    bool sealed = false;
+    int64_t npad = 0;
+    int G = 0;                 // 16-sub-quantizer groups when the skewed kernel applies, else 0
+    std::vector<int64_t> h_list_off;
+    std::vector<int32_t> h_list_len, h_list_cnt_all;
+    DevBuf<int64_t> list_off;
+    DevBuf<int32_t> list_len, rows, pos_of_row;
+    DevBuf<uint8_t> codes;     // [G][npad][16] or [npad][M]
+    DevBuf<float> t1, vecs;
+    DevBuf<int64_t> labels;    // row -> label (sealed copy of f_labels)
+
+    bool keeps_vecs() const { return !is_pq || refine; }
+    bool is_trained() const override { return trained; }
+    bool has_raw() const override { return keeps_vecs(); }
+    int64_t count() const override { return n_total; }
+    int64_t
+    size_bytes() const override {
+        return (int64_t)(centroids.bytes() + pqc.bytes() + codes.bytes() + t1.bytes() + vecs.bytes() + rows.bytes() +
+                         pos_of_row.bytes() + f_codes.bytes() + f_vecs.bytes() + f_assign.bytes());
+    }
+
+    void
+    set_centroids_common() {
+        cnorms.ensure(nlist);
+        row_norms_kernel<<<grid1d(nlist * 32, 256), 256, 0, stream>>>(centroids.p, nlist, dim, cnorms.p);
+        KB2_CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+
+    // ---------------------------------------------------------------- Train (ivf.cc:545-807)
+    void
+    train(const float* x, int64_t n) override {
+        KB2_REQUIRE(!trained, KB2_INDEX_ALREADY_TRAINED, "index already trained");
+        KB2_REQUIRE(n > 0, KB2_INVALID_ARGS, "empty training set");
+        // MatchNlist (ivf.cc:479-489)
+        if (nlist * 39 > n) nlist = std::max<int64_t>(1, n / 39);
+        DevBuf<float> xbuf;
+        const float* dx = to_device(x, (size_t)n * dim, xbuf, false);
+        centroids.alloc_exact((size_t)nlist * dim);
+        kmeans_train(dx, n, dim, (int)nlist, metric, 25, 1234, centroids.p, stream);
+        set_centroids_common();
+        if (is_pq) {
+            KB2_REQUIRE(nbits == 8, KB2_NOT_IMPLEMENTED, "IVF_PQ: only nbits=8 is implemented on the GPU path");
+            KB2_REQUIRE(M > 0 && dim % M == 0, KB2_INVALID_ARGS, "IVF_PQ: dim must be a multiple of m");
+            KB2_REQUIRE(n >= 256, KB2_INVALID_ARGS, "IVF_PQ: need at least 256 training rows for nbits=8");
+            dsub = dim / M;
+            // residuals of (a subsample of) the training set: F/IndexIVF.cpp:1307-1329, IndexIVFPQ.cpp:76-95
+            const int64_t nt = std::min<int64_t>(n, 256 * 256);
+            DevBuf<float> sample;
+            const float* xt = dx;
+            if (nt < n) {
+                std::mt19937_64 rng(1234 + 7);
+                std::vector<int32_t> perm(n);
+                for (int64_t i = 0; i < n; i++) perm[i] = (int32_t)i;
+                for (int64_t i = 0; i < nt; i++) std::swap(perm[i], perm[i + (int64_t)(rng() % (uint64_t)(n - i))]);
+                DevBuf<int32_t> didx;
+                didx.ensure(nt);
+                KB2_CUDA_CHECK(cudaMemcpyAsync(didx.p, perm.data(), nt * 4, cudaMemcpyHostToDevice, stream));
+                sample.ensure((size_t)nt * dim);
+                gather_rows_kernel<<<grid1d(nt * 32, 256), 256, 0, stream>>>(dx, didx.p, nt, dim, dim, sample.p);
+                KB2_CUDA_CHECK(cudaStreamSynchronize(stream));
+                xt = sample.p;
+            }
+            DevBuf<int32_t> asg;
+            asg.ensure(nt);
+            AssignScratch sc;
+            assign_nearest(xt, nt, dim, centroids.p, (int)nlist, metric, asg.p, nullptr, sc, stream);
+            pqc.alloc_exact((size_t)M * 256 * dsub);
+            DevBuf<float> sub;
+            sub.ensure((size_t)nt * dsub);
+            for (int m = 0; m < M; m++) {
+                slice_residual_kernel<<<grid1d(nt * dsub, 256), 256, 0, stream>>>(xt, centroids.p, asg.p, nt, dim, m, dsub,
+                                                                                sub.p);
+                kmeans_train(sub.p, nt, dsub, 256, KB2_METRIC_L2, 25, 1234 + m, pqc.p + (size_t)m * 256 * dsub, stream);
+            }
+        }
+        KB2_CUDA_CHECK(cudaStreamSynchronize(stream));
+        trained = true;
+    }
+
+    // ---------------------------------------------------------------- Add (ivf.cc:809-844; F/IndexIVF.cpp:212-287)
+    void
+    add(const float* x, int64_t n, const int64_t* ids) override {
+        KB2_REQUIRE(trained, KB2_INDEX_NOT_TRAINED, "index not trained");
+        if (n <= 0) return;
+        if (sealed) unseal();
+        DevBuf<float> xbuf;
+        const float* dx = to_device(x, (size_t)n * dim, xbuf, false);
+        DevBuf<int32_t> asg;
+        asg.ensure(n);
+        AssignScratch sc;
+        assign_nearest(dx, n, dim, centroids.p, (int)nlist, metric, asg.p, nullptr, sc, stream);
+        dev_append(f_assign, f_assign_used, asg.p, (size_t)n, stream);
+        if (is_pq) {
+            DevBuf<uint8_t> cb;
+            cb.ensure((size_t)n * M);
+            pq_encode_kernel<<<grid1d(n * 32, 256), 256, 0, stream>>>(dx, centroids.p, asg.p, pqc.p, n, dim, M, dsub, cb.p);
+            dev_append(f_codes, f_codes_used, cb.p, (size_t)n * M, stream);
+        }
+        if (keeps_vecs()) dev_append(f_vecs, f_vecs_used, dx, (size_t)n * dim, stream);
+        append_labels(ids, n);
+        KB2_CUDA_CHECK(cudaStreamSynchronize(stream));
+        KB2_CUDA_CHECK(cudaGetLastError());
+        n_total += n;
+    }
+
+    void
+    append_labels(const int64_t* ids, int64_t n) {
+        if (ids && !custom_labels) {
+            std::vector<int64_t> h(n_total);
+            for (int64_t i = 0; i < n_total; i++) h[i] = i;
+            f_labels_used = 0;
+            if (n_total) dev_append(f_labels, f_labels_used, h.data(), (size_t)n_total, stream);
+            KB2_CUDA_CHECK(cudaStreamSynchronize(stream));
+            custom_labels = true;
+        }
+        if (custom_labels) {
+            if (ids) {
+                dev_append(f_labels, f_labels_used, ids, (size_t)n, stream);
+            } else {
+                std::vector<int64_t> h(n);
+                for (int64_t i = 0; i < n; i++) h[i] = n_total + i;
+                dev_append(f_labels, f_labels_used, h.data(), (size_t)n, stream);
+            }
+            KB2_CUDA_CHECK(cudaStreamSynchronize(stream));
+        }
+    }
+
+    // ---------------------------------------------------------------- list-order layout
+    void
+    seal() {
+        if (sealed) return;
+        const int64_t n = n_total;
+        cudaStream_t st = stream;
+        // list sizes
+        DevBuf<int32_t> dcnt;
+        dcnt.ensure(nlist);
+        KB2_CUDA_CHECK(cudaMemsetAsync(dcnt.p, 0, nlist * 4, st));
+        if (n) histogram_kernel<<<grid1d(n, 256), 256, 0, st>>>(f_assign.p, n, dcnt.p);
+        h_list_cnt_all.assign(nlist, 0);
+        KB2_CUDA_CHECK(cudaMemcpyAsync(h_list_cnt_all.data(), dcnt.p, nlist * 4, cudaMemcpyDeviceToHost, st));
+        KB2_CUDA_CHECK(cudaStreamSynchronize(st));
+        h_list_off.assign(nlist, 0);
+        h_list_len.assign(nlist, 0);
+        std::vector<int64_t> first_rank(nlist, 0);
+        int64_t cur = 0, rank = 0;
+        for (int64_t l = 0; l < nlist; l++) {
+            first_rank[l] = rank;
+            rank += h_list_cnt_all[l];
+            const bool owned = (l % shard_world) == shard_rank;
+            h_list_len[l] = owned ? h_list_cnt_all[l] : 0;
+            h_list_off[l] = cur;
+            cur += round_up(h_list_len[l], 32);
+        }
+        npad = cur + 32;
+        KB2_REQUIRE(npad < (int64_t)0xfffffff0ll, KB2_INVALID_ARGS, "index too large for 32-bit positions");
+        list_off.alloc_exact(nlist);
+        list_len.alloc_exact(nlist);
+        DevBuf<int64_t> d_first;
+        d_first.ensure(nlist);
+        KB2_CUDA_CHECK(cudaMemcpyAsync(list_off.p, h_list_off.data(), nlist * 8, cudaMemcpyHostToDevice, st));
+        KB2_CUDA_CHECK(cudaMemcpyAsync(list_len.p, h_list_len.data(), nlist * 4, cudaMemcpyHostToDevice, st));
+        KB2_CUDA_CHECK(cudaMemcpyAsync(d_first.p, first_rank.data(), nlist * 8, cudaMemcpyHostToDevice, st));
+        // stable sort rows by list id
+        rows.alloc_exact(npad);
+        pos_of_row.alloc_exact(std::max<int64_t>(n, 1));
+        fill_i32_kernel<<<grid1d(npad, 256), 256, 0, st>>>(rows.p, npad, -1);
+        if (n) {
+            DevBuf<int32_t> idx_in, idx_out, key_out;
+            idx_in.ensure(n);
+            idx_out.ensure(n);
+            key_out.ensure(n);
+            iota_kernel<<<grid1d(n, 256), 256, 0, st>>>(idx_in.p, n);
+            size_t tmp_bytes = 0;
+            int end_bit = 1;
+            while ((1ll << end_bit) < nlist) end_bit++;
+            cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, f_assign.p, key_out.p, idx_in.p, idx_out.p, (int)n, 0,
+                                            end_bit, st);
+            DevBuf<uint8_t> tmp;
+            tmp.ensure(tmp_bytes);
+            cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, f_assign.p, key_out.p, idx_in.p, idx_out.p, (int)n, 0,
+                                            end_bit, st);
+            place_rows_kernel<<<grid1d(n, 256), 256, 0, st>>>(key_out.p, idx_out.p, n, d_first.p, list_off.p, list_len.p,
+                                                            rows.p, pos_of_row.p);
+            KB2_CUDA_CHECK(cudaStreamSynchronize(st));
+        }
+        // payload in list order
+        if (is_pq) {
+            G = (M % 16 == 0 && M / 16 <= 3) ? M / 16 : 0;
+            DevBuf<float> t1_flat;
+            if (metric == KB2_METRIC_L2) {
+                t1_flat.ensure(std::max<int64_t>(n, 1));
+                if (n) pq_t1_kernel<<<grid1d(n * 32, 256), 256, 0, st>>>(f_codes.p, centroids.p, f_assign.p, pqc.p, n, dim, M,
+                                                                         dsub, t1_flat.p);
+                t1.alloc_exact(npad);
+                gather_f32_kernel<<<grid1d(npad, 256), 256, 0, st>>>(t1_flat.p, rows.p, npad, t1.p, 0.f);
+            }
+            if (G > 0) {
+                codes.alloc_exact((size_t)G * npad * 16);
+                layout_codes_kernel<<<grid1d((int64_t)G * npad * 16, 256), 256, 0, st>>>(f_codes.p, rows.p, npad, M, G, codes.p);
+            } else {
+                codes.alloc_exact((size_t)npad * M);
+                layout_codes_plain_kernel<<<grid1d(npad * M, 256), 256, 0, st>>>(f_codes.p, rows.p, npad, M, codes.p);
+            }
+        }
+        if (keeps_vecs()) {
+            vecs.alloc_exact((size_t)npad * dim);
+            gather_rows_kernel<<<grid1d(npad * 32, 256), 256, 0, st>>>(f_vecs.p, rows.p, npad, dim, dim, vecs.p);
+        }
+        if (custom_labels) {
+            labels.alloc_exact(std::max<int64_t>(n, 1));
+            KB2_CUDA_CHECK(cudaMemcpyAsync(labels.p, f_labels.p, n * 8, cudaMemcpyDeviceToDevice, st));
+        }
+        KB2_CUDA_CHECK(cudaStreamSynchronize(st));
+        KB2_CUDA_CHECK(cudaGetLastError());
+        // the insertion-order payload is no longer needed (assign/labels stay: small)
+        f_codes.release();
+        f_vecs.release();
+        sealed = true;
+    }
+
+    // rebuild the insertion-order payload from the list-order one so that add() can append
+    void
+    unseal() {
+        KB2_REQUIRE(shard_world == 1, KB2_NOT_IMPLEMENTED, "add() after search on a sharded index");
+        const int64_t n = n_total;
+        cudaStream_t st = stream;
+        if (is_pq) {
+            // gather codes back: launch one thread per (row, m)
+            KB2_REQUIRE(false, KB2_NOT_IMPLEMENTED, "IVF_PQ add() after the first search is not supported yet");
+        }
+        if (keeps_vecs()) {
+            f_vecs.alloc_exact((size_t)std::max<int64_t>(n, 1) * dim);
+            gather_rows_kernel<<<grid1d(n * 32, 256), 256, 0, st>>>(vecs.p, pos_of_row.p, n, dim, dim, f_vecs.p);
+            f_vecs_used = (size_t)n * dim;
+        }
+        KB2_CUDA_CHECK(cudaStreamSynchronize(st));
+        sealed = false;
+    }
+
+    // ---------------------------------------------------------------- Search (ivf.cc:887-1168)
+    void
+    search(const float* q, int64_t nq, int k, const JsonObj& cfg, const uint8_t* bitset, int64_t nbits, int64_t* out_ids,
+           float* out_dist) override {
+        KB2_REQUIRE(trained, KB2_INDEX_NOT_TRAINED, "index not trained");
+        KB2_REQUIRE(n_total > 0, KB2_EMPTY_INDEX, "index is empty");
+        seal();
+        int nprobe = (int)cfg.get_int("nprobe", 8);
+        nprobe = (int)std::min<int64_t>(std::max(nprobe, 1), nlist);
+        KB2_REQUIRE(nprobe <= kMaxK - 16, KB2_OUT_OF_RANGE_IN_JSON, "nprobe too large for the GPU path (max 1008)");
+        const bool use_refine = is_pq && refine;
+        const double refine_k = cfg.get_num("refine_k", 1.0);
+        KB2_REQUIRE(refine_k >= 1.0, KB2_OUT_OF_RANGE_IN_JSON, "refine_k must be >= 1");
+        const int k_base = use_refine ? (int)((double)k * refine_k) : k;  // K/IndexRefine.cpp:80-83
+        KB2_REQUIRE(k > 0 && k_base <= kMaxK, KB2_INVALID_ARGS, "k (x refine_k) out of range (max 1024)");
+
+        cudaStream_t st = stream;
+        const float* dq = to_device(q, (size_t)nq * dim, s_q);
+        const uint8_t* dbits = bitset_to_device(bitset, nbits);
+        const bool dev_out = is_device_ptr(out_ids);
+        int64_t* d_ids = out_ids;
+        float* d_dist = out_dist;
+        if (!dev_out) {
+            s_out_ids.ensure((size_t)nq * k);
+            s_out_dist.ensure((size_t)nq * k);
+            d_ids = s_out_ids.p;
+            d_dist = s_out_dist.p;
+        }
+
+        // ---- coarse quantizer: top-nprobe centroids, exact dis0 (F/IndexIVF.cpp:336-342)
+        s_probe_ids.ensure((size_t)nq * nprobe);
+        s_probe_dis.ensure((size_t)nq * nprobe);
+        {
+            DensePlan pl = dense_candidates(*this, dq, nq, centroids.p, cnorms.p, nlist, dim, metric, nprobe + 16, nullptr,
+                                            nullptr);
+            FinalizeParams fp{};
+            fp.partial = s_partial.p;
+            fp.partial_stride = pl.stride();
+            fp.n_partial = pl.used * pl.Ksel;
+            fp.k_sel = (int)std::min<int64_t>(std::min(pl.Ksel, nprobe + 16), nlist);
+            fp.k_out = nprobe;
+            fp.rerank = 1;
+            fp.raw = centroids.p;
+            fp.raw_by_pos = 1;
+            fp.queries = dq;
+            fp.d = dim;
+            fp.metric = metric;
+            fp.out_ids = s_probe_ids.p;
+            fp.out_dist = s_probe_dis.p;
+            launch_finalize(*this, fp, nq);
+        }
+
+        // ---- list scan
+        int nsplit = 1;
+        if (nq < 2 * kNumSMs) nsplit = (int)std::min<int64_t>(nprobe, (2 * kNumSMs + nq - 1) / nq);
+        const int Ksel = next_pow2(std::max(32, k_base));
+        while ((int64_t)nsplit * Ksel > kMaxSortEntries) nsplit--;
+        const int np_max = (nprobe + nsplit - 1) / nsplit;
+        s_partial2.ensure((size_t)nq * nsplit * Ksel);
+        KB2_CUDA_CHECK(cudaMemsetAsync(d_counter.p, 0, 16, st));
+        IvfScanParams sp{};
+        sp.queries = dq;
+        sp.nq = (int)nq;
+        sp.d = dim;
+        sp.metric = metric;
+        sp.probe_ids = s_probe_ids.p;
+        sp.probe_dis = s_probe_dis.p;
+        sp.nprobe = nprobe;
+        sp.list_off = list_off.p;
+        sp.list_len = list_len.p;
+        sp.nsplit = nsplit;
+        sp.K = Ksel;
+        sp.kout = Ksel;
+        sp.partial = s_partial2.p;
+        sp.bitset = dbits;
+        sp.rows = rows.p;
+        sp.vecs = vecs.p;
+        sp.pq_centroids = pqc.p;
+        sp.M = M;
+        sp.dsub = dsub;
+        sp.codes = (const uint4*)codes.p;
+        sp.npad = npad;
+        sp.t1 = t1.p;
+        sp.counters = d_counter.p;
+        const size_t common_smem = (size_t)kScanWarps * Ksel * 8 + (size_t)(np_max + 1) * 4 + (size_t)np_max * 12 +
+                                   (size_t)dim * 4 + 64;
+        const unsigned grid = (unsigned)(nq * nsplit);
+        if (timing) KB2_CUDA_CHECK(cudaEventRecord(ev0, st));
+        if (is_pq) {
+            if (G > 0) {
+                const size_t smem = (size_t)G * 65536 + common_smem;
+                KB2_REQUIRE(smem <= (size_t)kMaxDynSmem, KB2_INVALID_ARGS, "IVF_PQ: k too large for shared memory");
+#define KB2_LAUNCH_PQ(GG)                                                                             \
+    if (metric == KB2_METRIC_L2)                                                                      \
+        ivfpq_scan_kernel<GG, KB2_METRIC_L2><<<grid, kScanThreads, smem, st>>>(sp);                   \
+    else                                                                                              \
+        ivfpq_scan_kernel<GG, KB2_METRIC_IP><<<grid, kScanThreads, smem, st>>>(sp);
+                if (G == 1) { KB2_LAUNCH_PQ(1) } else if (G == 2) { KB2_LAUNCH_PQ(2) } else { KB2_LAUNCH_PQ(3) }
+#undef KB2_LAUNCH_PQ
+            } else {
+                const size_t smem = (size_t)M * 1024 + common_smem;
+                KB2_REQUIRE(smem <= (size_t)kMaxDynSmem, KB2_NOT_IMPLEMENTED, "IVF_PQ: m too large for the generic kernel");
+                if (metric == KB2_METRIC_L2)
+                    ivfpq_scan_generic_kernel<KB2_METRIC_L2><<<grid, kScanThreads, smem, st>>>(sp, codes.p);
+                else
+                    ivfpq_scan_generic_kernel<KB2_METRIC_IP><<<grid, kScanThreads, smem, st>>>(sp, codes.p);
+            }
+        } else {
+            KB2_REQUIRE(dim % 4 == 0, KB2_NOT_IMPLEMENTED, "IVF_FLAT: dim must be a multiple of 4 on the GPU path");
+            if (metric == KB2_METRIC_L2)
+                ivfflat_scan_kernel<KB2_METRIC_L2><<<grid, kScanThreads, common_smem, st>>>(sp);
+            else
+                ivfflat_scan_kernel<KB2_METRIC_IP><<<grid, kScanThreads, common_smem, st>>>(sp);
+        }
+        if (timing) KB2_CUDA_CHECK(cudaEventRecord(ev1, st));
+        last.launches++;
+        KB2_CUDA_CHECK(cudaGetLastError());
+
+        // ---- finalize: merge CTA lists, optional exact refine, labels
+        {
+            FinalizeParams fp{};
+            fp.partial = s_partial2.p;
+            fp.partial_stride = (int64_t)nsplit * Ksel;
+            fp.n_partial = nsplit * Ksel;
+            fp.k_sel = k_base;
+            fp.k_out = k;
+            fp.rows = rows.p;
+            fp.labels = custom_labels ? labels.p : nullptr;
+            fp.rerank = use_refine ? 1 : 0;
+            fp.raw = vecs.p;
+            fp.raw_by_pos = 1;
+            fp.queries = dq;
+            fp.d = dim;
+            fp.metric = metric;
+            fp.out_ids = d_ids;
+            fp.out_dist = d_dist;
+            launch_finalize(*this, fp, nq);
+        }
+        unsigned long long hc[2] = {0, 0};
+        KB2_CUDA_CHECK(cudaMemcpyAsync(hc, d_counter.p, 16, cudaMemcpyDeviceToHost, st));
+        results_out(nq, k, out_ids, out_dist, d_ids, d_dist);
+        KB2_REQUIRE(hc[1] == 0, KB2_INTERNAL_ERROR, "ivfpq_scan_kernel: unexpected shared-memory window base");
+        const unsigned long long scanned = hc[0];
+        last.codes = (int64_t)scanned;
+        last.code_bytes = (int64_t)scanned * (is_pq ? (int64_t)M : (int64_t)dim * 4);
+        last.pairs = nq * nprobe;
+        if (timing) KB2_CUDA_CHECK(cudaEventElapsedTime(&last_kernel_ms, ev0, ev1));
+    }
+
+    void
+    get_vectors(const int64_t* ids, int64_t n, float* out) override {
+        KB2_REQUIRE(keeps_vecs(), KB2_NOT_IMPLEMENTED, "index holds no raw data");
+        KB2_REQUIRE(!custom_labels && shard_world == 1, KB2_NOT_IMPLEMENTED, "GetVectorByIds with custom ids / shards");
+        seal();
+        std::vector<int64_t> h(n);
+        if (is_device_ptr(ids)) {
+            KB2_CUDA_CHECK(cudaMemcpy(h.data(), ids, n * 8, cudaMemcpyDeviceToHost));
+        } else {
+            memcpy(h.data(), ids, n * 8);
+        }
+        std::vector<int32_t> hpos(n_total);
+        KB2_CUDA_CHECK(cudaMemcpy(hpos.data(), pos_of_row.p, n_total * 4, cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < n; i++) {
+            KB2_REQUIRE(h[i] >= 0 && h[i] < n_total, KB2_INVALID_ARGS, "id out of range");
+            KB2_CUDA_CHECK(cudaMemcpyAsync(out + i * dim, vecs.p + (int64_t)hpos[h[i]] * dim, (size_t)dim * 4,
+                                           cudaMemcpyDefault, stream));
+        }
+        KB2_CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+
+    // ---------------------------------------------------------------- import of an externally built index
+    std::vector<int32_t> imp_assign;
+    std::vector<int64_t> imp_labels;
+    std::vector<uint8_t> imp_codes;
+    void
+    import_begin(int64_t nl, const float* cent, const float* pq_cent) {
+        KB2_REQUIRE(n_total == 0, KB2_INVALID_ARGS, "import into a non-empty index");
+        nlist = nl;
+        centroids.alloc_exact((size_t)nlist * dim);
+        KB2_CUDA_CHECK(cudaMemcpyAsync(centroids.p, cent, (size_t)nlist * dim * 4, cudaMemcpyDefault, stream));
+        set_centroids_common();
+        if (is_pq) {
+            KB2_REQUIRE(pq_cent != nullptr, KB2_INVALID_ARGS, "IVF_PQ import needs pq centroids");
+            KB2_REQUIRE(M > 0 && dim % M == 0 && nbits == 8, KB2_INVALID_ARGS, "IVF_PQ import: bad m / nbits");
+            dsub = dim / M;
+            pqc.alloc_exact((size_t)M * 256 * dsub);
+            KB2_CUDA_CHECK(cudaMemcpyAsync(pqc.p, pq_cent, (size_t)M * 256 * dsub * 4, cudaMemcpyDefault, stream));
+        }
+        KB2_CUDA_CHECK(cudaStreamSynchronize(stream));
+        trained = true;
+        imp_assign.clear();
+        imp_labels.clear();
+        imp_codes.clear();
+    }
+    void
+    import_list(int64_t l, int64_t sz, const int64_t* ids, const uint8_t* cds) {
+        KB2_REQUIRE(l >= 0 && l < nlist, KB2_INVALID_ARGS, "list number out of range");
+        const size_t cs = is_pq ? (size_t)M : (size_t)dim * 4;
+        imp_assign.insert(imp_assign.end(), (size_t)sz, (int32_t)l);
+        imp_labels.insert(imp_labels.end(), ids, ids + sz);
+        imp_codes.insert(imp_codes.end(), cds, cds + (size_t)sz * cs);
+    }
+    void
+    import_finish(const float* raw, int64_t n_raw) {
+        const int64_t n = (int64_t)imp_assign.size();
+        f_assign_used = 0;
+        dev_append(f_assign, f_assign_used, imp_assign.data(), (size_t)n, stream);
+        custom_labels = true;
+        f_labels_used = 0;
+        dev_append(f_labels, f_labels_used, imp_labels.data(), (size_t)n, stream);
+        if (is_pq) {
+            f_codes_used = 0;
+            dev_append(f_codes, f_codes_used, imp_codes.data(), imp_codes.size(), stream);
+            if (refine) {
+                KB2_REQUIRE(raw != nullptr, KB2_INVALID_ARGS, "refine=true import needs the raw vectors");
+                // raw is in label order; our rows are import-order: gather raw[label[row]]
+                std::vector<int32_t> lab32(n);
+                for (int64_t i = 0; i < n; i++) {
+                    KB2_REQUIRE(imp_labels[i] >= 0 && imp_labels[i] < n_raw, KB2_INVALID_ARGS, "label outside raw data");
+                    lab32[i] = (int32_t)imp_labels[i];
+                }
+                DevBuf<float> rbuf;
+                const float* draw = to_device(raw, (size_t)n_raw * dim, rbuf, false);
+                DevBuf<int32_t> dl;
+                dl.ensure(n);
+                KB2_CUDA_CHECK(cudaMemcpyAsync(dl.p, lab32.data(), n * 4, cudaMemcpyHostToDevice, stream));
+                f_vecs.alloc_exact((size_t)n * dim);
+                gather_rows_kernel<<<grid1d(n * 32, 256), 256, 0, stream>>>(draw, dl.p, n, dim, dim, f_vecs.p);
+                f_vecs_used = (size_t)n * dim;
+                KB2_CUDA_CHECK(cudaStreamSynchronize(stream));
+            }
+        } else {
+            f_vecs_used = 0;
+            dev_append(f_vecs, f_vecs_used, (const float*)imp_codes.data(), (size_t)n * dim, stream);
+        }
+        KB2_CUDA_CHECK(cudaStreamSynchronize(stream));
+        n_total = n;
+        imp_assign.clear(); imp_assign.shrink_to_fit();
+        imp_labels.clear(); imp_labels.shrink_to_fit();
+        imp_codes.clear(); imp_codes.shrink_to_fit();
+        sealed = false;
+    }
+    // export one list in scan order (host buffers)
+    void
+    export_list(int64_t l, int64_t* ids, uint8_t* cds) {
+        seal();
+        KB2_REQUIRE(l >= 0 && l < nlist, KB2_INVALID_ARGS, "list number out of range");
+        const int64_t off = h_list_off[l], len = h_list_len[l];
+        if (len == 0) return;
+        std::vector<int32_t> hrows(len);
+        KB2_CUDA_CHECK(cudaMemcpy(hrows.data(), rows.p + off, len * 4, cudaMemcpyDeviceToHost));
+        std::vector<int64_t> hl;
+        if (custom_labels) {
+            hl.resize(n_total);
+            KB2_CUDA_CHECK(cudaMemcpy(hl.data(), labels.p, n_total * 8, cudaMemcpyDeviceToHost));
+        }
+        for (int64_t i = 0; i < len; i++) ids[i] = custom_labels ? hl[hrows[i]] : hrows[i];
+        if (!is_pq) {
+            KB2_CUDA_CHECK(cudaMemcpy(cds, vecs.p + off * dim, (size_t)len * dim * 4, cudaMemcpyDeviceToHost));
+        } else if (G > 0) {
+            std::vector<uint8_t> tmp((size_t)len * 16);
+            for (int g = 0; g < G; g++) {
+                KB2_CUDA_CHECK(cudaMemcpy(tmp.data(), codes.p + ((size_t)g * npad + off) * 16, (size_t)len * 16,
+                                          cudaMemcpyDeviceToHost));
+                for (int64_t i = 0; i < len; i++)
+                    for (int s = 0; s < 16; s++)
+                        cds[i * M + g * 16 + ((s + (off + i)) & 15)] = tmp[i * 16 + s];
+            }
+        } else {
+            KB2_CUDA_CHECK(cudaMemcpy(cds, codes.p + (size_t)off * M, (size_t)len * M, cudaMemcpyDeviceToHost));
+        }
+    }
+};
+
+}  // namespace kb2

@@ -1,0 +1,224 @@
+// kb2_topk.cuh — k-selection primitives shared by every scan kernel.
+//
+// Semantics we implement (documented deviation, see DESIGN.md "ties"): results are the k smallest
+// under the TOTAL order (key, id).  The reference's binary heap admits a candidate only on strict
+// improvement and evicts the (value,id)-largest root (K/impl/ResultHandler.h:238-245,
+// F/utils/Heap.h:113-160), which yields the same set unless several candidates tie *exactly*
+// with the k-th distance; the final ordering (distance, then id) is identical
+// (heap_reorder, F/utils/Heap.h; F/IndexIVF.cpp:484-494).
+#pragma once
+#include <float.h>
+
+#include "kb2_common.cuh"
+
+namespace kb2 {
+
+// --------------------------------------------------------------------------------------------
+// Per-warp top-K: unsorted list of K packed (key,pos) entries in shared memory, replace-the-max
+// admission with a warp-uniform threshold.  After the first few hundred candidates the common
+// path is ONE ballot per 32 candidates.
+// --------------------------------------------------------------------------------------------
+struct WarpTopK {
+    uint64_t* list;  // shared memory, K entries
+    int K;           // multiple of 32
+    uint64_t thr;    // current maximum of the list (kEmpty until full); warp-uniform
+    int maxpos;
+
+    __device__ __forceinline__ void
+    init(uint64_t* l, int k, int lane) {
+        list = l;
+        K = k;
+        for (int i = lane; i < K; i += kWarp) list[i] = kEmpty;
+        thr = kEmpty;
+        maxpos = 0;
+        __syncwarp();
+    }
+
+    __device__ __forceinline__ void
+    recompute_max(int lane) {
+        uint64_t lm = list[lane];  // K >= 32
+        int lp = lane;
+        for (int i = lane + kWarp; i < K; i += kWarp) {
+            uint64_t v = list[i];
+            if (v > lm) { lm = v; lp = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            uint64_t ov = __shfl_xor_sync(0xffffffffu, lm, o);
+            int op = __shfl_xor_sync(0xffffffffu, lp, o);
+            if (ov > lm || (ov == lm && op < lp)) { lm = ov; lp = op; }
+        }
+        thr = lm;
+        maxpos = lp;
+    }
+
+    // all 32 lanes must call; `valid` lanes offer `cand`
+    __device__ __forceinline__ void
+    push(uint64_t cand, bool valid, int lane) {
+        unsigned m = __ballot_sync(0xffffffffu, valid && cand < thr);
+        while (m) {
+            int src = __ffs(m) - 1;
+            m &= m - 1;
+            uint64_t c = __shfl_sync(0xffffffffu, cand, src);
+            if (c < thr) {  // thr shrinks while we drain the ballot
+                if (lane == 0) list[maxpos] = c;
+                __syncwarp();
+                recompute_max(lane);
+            }
+        }
+    }
+};
+
+// --------------------------------------------------------------------------------------------
+// CTA-wide bitonic sort of n (power of two) u64 keys in shared memory, ascending.
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ void
+block_bitonic_sort(uint64_t* s, int n) {
+    for (int k2 = 2; k2 <= n; k2 <<= 1) {
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    uint64_t a = s[i], b = s[ixj];
+                    bool asc = ((i & k2) == 0);
+                    if ((a > b) == asc) { s[i] = b; s[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// After the per-warp lists (kScanWarps * K contiguous u64 in `lists`) are complete: sort them
+// CTA-wide and write the best `kout` to out[0..kout).  Requires kScanWarps*K to be a power of two.
+__device__ __forceinline__ void
+block_emit_topk(uint64_t* lists, int K, uint64_t* __restrict__ out, int kout) {
+    __syncthreads();
+    block_bitonic_sort(lists, kScanWarps * K);
+    for (int i = threadIdx.x; i < kout; i += blockDim.x) out[i] = lists[i];
+}
+
+// --------------------------------------------------------------------------------------------
+// Finalize: one CTA per query.
+//   1. gather this query's partial candidate lists, CTA bitonic sort, keep the best k_sel
+//   2. optional exact re-rank of those candidates from raw fp32 vectors (FLAT exactness,
+//      IVF coarse dis0, IVF_PQ refine: K/IndexRefine.cpp:66-160)
+//   3. order by (key, label) and emit k_out (ids int64, dist fp32); pad with -1 / +-FLT_MAX
+// --------------------------------------------------------------------------------------------
+struct FinalizeParams {
+    const uint64_t* partial;   // [nq][partial_stride], first n_partial entries of each row are used
+    int64_t partial_stride;
+    int n_partial;             // entries per query
+    int n_sort;                // next_pow2(n_partial) (<= 8192)
+    int k_sel;                 // candidates kept after the sort (<= 1024)
+    int k_out;                 // results written per query
+    const int32_t* rows;       // pos -> internal row id (NULL: identity)
+    const int64_t* labels;     // row -> label (NULL: identity)
+    int rerank;                // 1: recompute keys exactly from `raw`
+    const float* raw;          // [*][d] fp32
+    int raw_by_pos;            // 1: raw indexed by pos, 0: by row
+    const float* queries;      // [nq][d]
+    int d;
+    int metric;                // KB2_METRIC_L2 / KB2_METRIC_IP
+    int64_t* out_ids;          // [nq][k_out]
+    float* out_dist;           // [nq][k_out]
+    int32_t* out_pos;          // optional [nq][k_out] positions (NULL: skip)
+};
+
+// dynamic smem: n_sort*8 + k_sel*(4+8+4) + d*4
+__global__ void __launch_bounds__(256)
+finalize_kernel(FinalizeParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* s_sort = (uint64_t*)smem_raw;
+    int64_t* s_label = (int64_t*)(s_sort + p.n_sort);
+    float* s_key = (float*)(s_label + p.k_sel);
+    uint32_t* s_pos = (uint32_t*)(s_key + p.k_sel);
+    float* s_q = (float*)(s_pos + p.k_sel);
+
+    const int64_t q = blockIdx.x;
+    const uint64_t* src = p.partial + q * p.partial_stride;
+    for (int i = threadIdx.x; i < p.n_sort; i += blockDim.x) s_sort[i] = (i < p.n_partial) ? src[i] : kEmpty;
+    if (p.rerank)
+        for (int i = threadIdx.x; i < p.d; i += blockDim.x) s_q[i] = p.queries[q * p.d + i];
+    __syncthreads();
+    block_bitonic_sort(s_sort, p.n_sort);
+
+    const int ksel = p.k_sel;
+    for (int i = threadIdx.x; i < ksel; i += blockDim.x) {
+        uint64_t e = (i < p.n_sort) ? s_sort[i] : kEmpty;
+        if (e == kEmpty) {
+            s_label[i] = INT64_MAX;
+            s_key[i] = INFINITY;
+            s_pos[i] = kNoPos;
+        } else {
+            uint32_t pos = unpack_pos(e);
+            int64_t row = p.rows ? (int64_t)p.rows[pos] : (int64_t)pos;
+            s_label[i] = p.labels ? p.labels[row] : row;
+            s_key[i] = unpack_key(e);
+            s_pos[i] = pos;
+        }
+    }
+    __syncthreads();
+
+    if (p.rerank) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int i = warp; i < ksel; i += (blockDim.x >> 5)) {
+            uint32_t pos = s_pos[i];
+            if (pos == kNoPos) continue;
+            int64_t r = p.raw_by_pos ? (int64_t)pos : (p.rows ? (int64_t)p.rows[pos] : (int64_t)pos);
+            const float* x = p.raw + r * (int64_t)p.d;
+            float acc = 0.f;
+            if (p.metric == KB2_METRIC_L2) {
+                for (int j = lane; j < p.d; j += kWarp) {
+                    float t = s_q[j] - x[j];
+                    acc = fmaf(t, t, acc);
+                }
+            } else {
+                for (int j = lane; j < p.d; j += kWarp) acc = fmaf(s_q[j], x[j], acc);
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) s_key[i] = (p.metric == KB2_METRIC_L2) ? acc : -acc;
+        }
+        __syncthreads();
+    }
+
+    // rank by (key, label, slot)
+    for (int i = threadIdx.x; i < ksel; i += blockDim.x) {
+        const float ki = s_key[i];
+        const int64_t li = s_label[i];
+        int rank = 0;
+        for (int j = 0; j < ksel; j++) {
+            const float kj = s_key[j];
+            const int64_t lj = s_label[j];
+            rank += (kj < ki) || (kj == ki && (lj < li || (lj == li && j < i)));
+        }
+        if (rank < p.k_out) {
+            const int64_t o = q * p.k_out + rank;
+            if (s_pos[i] == kNoPos) {
+                p.out_ids[o] = -1;
+                p.out_dist[o] = (p.metric == KB2_METRIC_L2) ? FLT_MAX : -FLT_MAX;
+                if (p.out_pos) p.out_pos[o] = -1;
+            } else {
+                p.out_ids[o] = li;
+                p.out_dist[o] = (p.metric == KB2_METRIC_L2) ? ki : -ki;
+                if (p.out_pos) p.out_pos[o] = (int32_t)s_pos[i];
+            }
+        }
+    }
+    // k_out > k_sel cannot happen (host guarantees k_sel >= k_out)
+}
+
+// reduce [nq][n_in] partial entries to the best n_keep per query, in place at the front of each
+// query's slot range (used when many base chunks accumulate more than 8192 candidates)
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(uint64_t* partial, int stride, int n_in, int n_sort, int n_keep) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* s = (uint64_t*)smem_raw;
+    uint64_t* base = partial + (int64_t)blockIdx.x * stride;
+    for (int i = threadIdx.x; i < n_sort; i += blockDim.x) s[i] = (i < n_in) ? base[i] : kEmpty;
+    __syncthreads();
+    block_bitonic_sort(s, n_sort);
+    for (int i = threadIdx.x; i < n_keep; i += blockDim.x) base[i] = s[i];
+}
+
+}  // namespace kb2

@@ -1,0 +1,156 @@
+"""IVF_FLAT / IVF_PQ parity against the compiled reference (GPU).
+
+Parity protocol: the index is trained and populated by the reference
+(faiss IndexIVFFlat / IndexIVFPQ == what Knowhere's IvfIndexNode wraps), exported, and imported
+into the GPU index, so both sides search the SAME centroids / codebooks / codes.  Then
+ids must match (up to boundary ties) and distances agree to 1e-4 relative."""
+import numpy as np
+import pytest
+
+from knowhere_b200 import datagen
+from tests.util import assert_topk_parity, recall_at_k
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk_ref(ref, kind, xb, metric, nlist, m=0, refine=False):
+    r = ref.RefIvf(kind, xb.shape[1], metric, nlist, m, 8, refine=refine)
+    r.train(xb)
+    r.add(xb)
+    return r
+
+
+def _import(kb, r, kind, metric, xb, refine=False):
+    cfg = {"nlist": r.nlist}
+    if kind == "IVF_PQ":
+        cfg.update(m=r.m, nbits=8, refine=refine, refine_type="flat")
+    ix = kb.Index(kind, "L2" if metric == 0 else "IP", xb.shape[1], cfg)
+    ix.ivf_import(r.centroids(), r.pq_centroids() if kind == "IVF_PQ" else None, list(r.lists()),
+                  raw=xb if refine else None)
+    assert ix.count() == xb.shape[0]
+    return ix
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+@pytest.mark.parametrize("nb,d,nlist,nprobe,nq,k", [(20000, 128, 64, 8, 100, 10), (5000, 32, 16, 16, 33, 5)])
+def test_ivfflat_imported_index_parity(kb, ref, metric, nb, d, nlist, nprobe, nq, k):
+    xb = datagen.clustered(nb, d, 42)
+    xq = datagen.clustered(nq, d, 43)
+    r = _mk_ref(ref, "IVF_FLAT", xb, metric, nlist)
+    ix = _import(kb, r, "IVF_FLAT", metric, xb)
+    I0, D0 = r.search(xq, k, nprobe)
+    ids, dist = ix.search(xq, k, {"nprobe": nprobe})
+    assert_topk_parity(ids, dist, I0, D0, what="IVF_FLAT")
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+@pytest.mark.parametrize("m,d", [(16, 128), (8, 64), (32, 128), (48, 96)])
+def test_ivfpq_imported_index_parity(kb, ref, metric, m, d):
+    nb, nlist, nprobe, nq, k = 30000, 64, 8, 100, 10
+    xb = datagen.clustered(nb, d, 42)
+    xq = datagen.clustered(nq, d, 43)
+    r = _mk_ref(ref, "IVF_PQ", xb, metric, nlist, m)
+    ix = _import(kb, r, "IVF_PQ", metric, xb)
+    I0, D0 = r.search(xq, k, nprobe)
+    ids, dist = ix.search(xq, k, {"nprobe": nprobe})
+    # PQ codes collide (identical codes => identical ADC distance): allow tie rows, compare sets
+    assert_topk_parity(ids, dist, I0, D0, rtol=1e-4, atol=1e-3, what=f"IVF_PQ m={m}")
+    # coarse stage must agree exactly with the reference quantizer
+    CI, CD = r.coarse(xq, nprobe)
+    # (indirectly checked by the result parity above; direct check through nprobe=1 results)
+    ids1, _ = ix.search(xq, 1, {"nprobe": 1})
+    I1, _ = r.search(xq, 1, 1)
+    assert (ids1 == I1).mean() > 0.97
+
+
+@pytest.mark.parametrize("refine_k", [1, 4])
+def test_ivfpq_refine_parity(kb, ref, refine_k):
+    nb, d, nlist, m, nprobe, nq, k = 30000, 128, 64, 16, 16, 100, 10
+    xb = datagen.clustered(nb, d, 42)
+    xq = datagen.clustered(nq, d, 43)
+    r = _mk_ref(ref, "IVF_PQ", xb, 0, nlist, m, refine=True)
+    ix = _import(kb, r, "IVF_PQ", 0, xb, refine=True)
+    I0, D0 = r.search(xq, k, nprobe, refine_k=float(refine_k))
+    ids, dist = ix.search(xq, k, {"nprobe": nprobe, "refine_k": refine_k})
+    assert_topk_parity(ids, dist, I0, D0, what="IVF_PQ+refine")
+    gt, _ = ref.flat_search(xb, xq, k, 0)
+    assert recall_at_k(gt, ids) >= recall_at_k(gt, I0) - 1e-9
+
+
+def test_ivfpq_export_roundtrip(kb, ref):
+    nb, d, nlist, m = 8000, 64, 32, 16
+    xb = datagen.clustered(nb, d, 1)
+    r = _mk_ref(ref, "IVF_PQ", xb, 0, nlist, m)
+    ix = _import(kb, r, "IVF_PQ", 0, xb)
+    for l in (0, 5, 31):
+        ids0, codes0 = r.get_list(l)
+        ids1, codes1 = ix.ivf_export_list(l, m)
+        assert np.array_equal(ids0, ids1) and np.array_equal(codes0, codes1)
+
+
+@pytest.mark.parametrize("kind,m", [("IVF_FLAT", 0), ("IVF_PQ", 16)])
+def test_ivf_gpu_build_recall_vs_reference(kb, ref, kind, m):
+    """Index built entirely on the GPU (own k-means / PQ / encoding): recall@10 must reach the
+    reference-built index's recall at identical parameters (north_star parity bar for IVF)."""
+    nb, d, nlist, nprobe, nq, k = 40000, 128, 128, 16, 200, 10
+    xb = datagen.clustered(nb, d, 42)
+    xq = datagen.clustered(nq, d, 43)
+    gt, _ = ref.flat_search(xb, xq, k, 0)
+    r = _mk_ref(ref, kind, xb, 0, nlist, m)
+    I0, _ = r.search(xq, k, nprobe)
+    cfg = {"nlist": nlist}
+    if m:
+        cfg.update(m=m, nbits=8)
+    ix = kb.Index(kind, "L2", d, cfg)
+    ix.build(xb)
+    ids, dist = ix.search(xq, k, {"nprobe": nprobe})
+    rec_ref, rec_gpu = recall_at_k(gt, I0), recall_at_k(gt, ids)
+    print(f"{kind}: recall ref={rec_ref:.4f} gpu={rec_gpu:.4f}")
+    assert rec_gpu >= rec_ref - 0.02
+    # and the GPU-built index exported to the reference gives the same answers on the CPU
+    r2 = ref.RefIvf(kind, d, 0, nlist, m, 8)
+    c, pq = ix.ivf_export_centroids(m)
+    cs = m if m else d * 4
+    r2.import_state(c, pq, [(l,) + ix.ivf_export_list(l, cs) for l in range(nlist)])
+    I2, D2 = r2.search(xq, k, nprobe)
+    assert_topk_parity(ids, dist, I2, D2, rtol=1e-4, atol=1e-3, what=f"{kind} gpu-built vs cpu search")
+
+
+def test_ivf_small_batch_splits_probes(kb, ref):
+    # nq < 2*SMs => several CTAs per query; results must not depend on the split
+    nb, d, nlist, m = 20000, 64, 64, 16
+    xb = datagen.clustered(nb, d, 3)
+    xq = datagen.clustered(300, d, 4)
+    r = _mk_ref(ref, "IVF_PQ", xb, 0, nlist, m)
+    ix = _import(kb, r, "IVF_PQ", 0, xb)
+    a = ix.search(xq, 10, {"nprobe": 32})
+    b = ix.search(xq[:3].copy(), 10, {"nprobe": 32})
+    assert np.array_equal(a[0][:3], b[0]) and np.array_equal(a[1][:3], b[1])
+
+
+def test_ivf_bitset_and_serialize(kb, ref):
+    nb, d, nlist, m = 10000, 64, 32, 16
+    xb = datagen.clustered(nb, d, 5)
+    xq = datagen.clustered(20, d, 6)
+    ix = kb.Index("IVF_PQ", "L2", d, {"nlist": nlist, "m": m})
+    ix.build(xb)
+    mask = np.zeros(nb, bool)
+    mask[1::2] = True
+    ids, _ = ix.search(xq, 10, {"nprobe": 32}, bitset=np.packbits(mask, bitorder="little"))
+    assert not mask[ids[ids >= 0]].any()
+    a = ix.search(xq, 10, {"nprobe": 8})
+    ix2 = kb.Index.deserialize(ix.serialize())
+    b = ix2.search(xq, 10, {"nprobe": 8})
+    assert np.array_equal(a[0], b[0]) and np.allclose(a[1], b[1])
+
+
+def test_ivf_errors(kb):
+    ix = kb.Index("IVF_FLAT", "L2", 16, {"nlist": 4})
+    with pytest.raises(kb.KnowhereError) as e:
+        ix.add(np.zeros((10, 16), np.float32))
+    assert e.value.status == 8          # index_not_trained
+    with pytest.raises(kb.KnowhereError) as e:
+        kb.Index("IVF_PQ", "L2", 30, {"nlist": 4, "m": 16})
+    assert e.value.status == 1          # invalid_args (dim % m)
+    with pytest.raises(kb.KnowhereError):
+        kb.Index("NOPE", "L2", 16)
