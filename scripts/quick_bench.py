@@ -1,4 +1,6 @@
 """Quick IVF_PQ throughput probe (development aid, not the judged bench)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import sys
 import time
 
