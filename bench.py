@@ -1,0 +1,433 @@
+#!/usr/bin/env python3
+"""bench.py — queries/sec at recall@10 >= 0.95 on IVF_PQ L2 10M x 128 (m=16 nbits=8 nlist=4096 nprobe=64,
+batch=10000): BASELINE.json's metric on BASELINE.json configs[2].
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA path through the C ABI)
+  python bench.py --impl reference --gpus N ...           the reference's CPU implementation (oracle/_ref =
+                                                          the unmodified faiss/knowhere sources) on the host cores
+
+A "step" = one Search() of the whole 10000-query batch.  `value` times the search with queries and
+outputs resident in HBM; `e2e` times the same call with pinned HOST buffers (H2D of the queries and
+D2H of ids+distances inside the timed region).  Inputs (200 MB of codes, 5 GB of refine vectors) are
+larger than L2, so no explicit flush is needed between iterations.
+N>1: inverted lists are sharded (list l -> rank l % N), every rank scans its lists for the full batch,
+one NCCL all-gather of the per-shard top-k, merge kernel on every rank ("strong" scaling: fixed index
+and batch).  torch is plumbing here (device buffers, RNG, events, torch.distributed).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (index, metric, n, d, params, nq, k)
+    "ivf_pq_10m": dict(index="IVF_PQ", metric="L2", n=10_000_000, d=128, nq=10000, k=10,
+                       build={"nlist": 4096, "m": 16, "nbits": 8, "refine": True, "refine_type": "flat"},
+                       search={"nprobe": 64}),
+    "ivf_pq_1m": dict(index="IVF_PQ", metric="L2", n=1_000_000, d=128, nq=10000, k=10,
+                      build={"nlist": 1024, "m": 16, "nbits": 8, "refine": True, "refine_type": "flat"},
+                      search={"nprobe": 64}),
+    "ivf_flat_1m": dict(index="IVF_FLAT", metric="L2", n=1_000_000, d=128, nq=1000, k=10,
+                        build={"nlist": 1024}, search={"nprobe": 32}),
+}
+METRIC_NAME = "queries/sec at recall@10>=0.95, 10Mx128 f32 IVF_PQ"
+TARGET_RECALL = 0.95
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle sampling DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.p:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 8]
+        os.unlink(self.f.name)
+        if not rows:
+            return out
+        sm = [float(r[1]) for r in rows if r[1].strip().replace(".", "").isdigit()]
+        out["sm_mhz"] = statistics.median(sm) if sm else None
+        out["sm_max_mhz"] = float(rows[0][2]) if rows[0][2].strip().replace(".", "").isdigit() else None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for i, nm in enumerate(names):
+            if any("Active" == r[5 + i].strip() for r in rows):
+                out["reasons"].append(nm)
+        out["samples"] = len(rows)
+        return out
+
+
+def ground_truth(kb, torch, xb, xq_sub, k, metric):
+    ids, _ = kb.brute_force_search(xb, xq_sub, k, metric, stream=torch.cuda.current_stream().cuda_stream)
+    return ids.cpu().numpy()
+
+
+def recall_of(gt, ids):
+    hit = 0
+    for a, b in zip(gt, ids):
+        hit += len(set(a.tolist()) & set(b.tolist()) - {-1})
+    return hit / float(gt.shape[0] * gt.shape[1])
+
+
+def build_index(kb, torch, dist, wl, xb, rank, world, stream):
+    """GPU build; for world>1 rank 0 trains and broadcasts centroids/codebooks so that every rank
+    encodes against the same quantizers, then each rank keeps the lists l % world == rank."""
+    d = wl["d"]
+    ix = kb.Index(wl["index"], wl["metric"], d, wl["build"])
+    ix.set_stream(stream)
+    m = wl["build"].get("m", 0)
+    if world == 1:
+        ix.train(xb)
+    else:
+        ix.set_shard(rank, world)
+        nlist = wl["build"]["nlist"]
+        cent = torch.empty((nlist, d), dtype=torch.float32, device=xb.device)
+        pq = torch.empty((max(m, 1), 256, d // max(m, 1)), dtype=torch.float32, device=xb.device)
+        if rank == 0:
+            t = kb.Index(wl["index"], wl["metric"], d, wl["build"])
+            t.set_stream(stream)
+            t.train(xb)
+            c_h, pq_h = t.ivf_export_centroids(m)
+            cent.copy_(torch.from_numpy(c_h))
+            if m:
+                pq.copy_(torch.from_numpy(pq_h))
+            del t
+        dist.broadcast(cent, 0)
+        dist.broadcast(pq, 0)
+        torch.cuda.synchronize()
+        kb._check(kb.lib().kb2_ivf_import_begin(ix.h, nlist, cent.data_ptr(), pq.data_ptr() if m else None))
+    ix.add(xb)
+    return ix
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import knowhere_b200 as kb
+    from knowhere_b200 import datagen
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    wl = WORKLOADS[args.workload]
+    n, d, nq, k = wl["n"], wl["d"], wl["nq"], wl["k"]
+    stream = torch.cuda.current_stream().cuda_stream
+
+    t0 = time.time()
+    xb = datagen.clustered_torch(n, d, 42, dev)
+    xq = datagen.clustered_torch(nq, d, 43, dev)
+    torch.cuda.synchronize()
+    t_gen = time.time() - t0
+    t0 = time.time()
+    ix = build_index(kb, torch, dist, wl, xb, rank, world, stream)
+    torch.cuda.synchronize()
+    t_build = time.time() - t0
+
+    # ---- search closure (device-resident I/O)
+    ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    dis = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    if world > 1:
+        pack = torch.empty((nq, 2 * k), dtype=torch.int64, device=dev)
+        gathered = torch.empty((world, nq, 2 * k), dtype=torch.int64, device=dev)
+        g_ids = torch.empty((world, nq, k), dtype=torch.int64, device=dev)
+        g_dis = torch.empty((world, nq, k), dtype=torch.float32, device=dev)
+        m_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        m_dis = torch.empty((nq, k), dtype=torch.float32, device=dev)
+
+    def search_dev(cfg, q=None):
+        ix.search(xq if q is None else q, k, cfg, out=(ids, dis))
+        if world == 1:
+            return ids, dis
+        # ONE all-gather of the per-shard (id, distance) candidates, then the merge kernel
+        pack[:, :k] = ids
+        pack[:, k:] = dis.view(torch.int32).to(torch.int64)
+        dist.all_gather_into_tensor(gathered, pack)
+        g_ids.copy_(gathered[:, :, :k])
+        g_dis.copy_(gathered[:, :, k:].to(torch.int32).view(torch.float32))
+        kb._check(kb.lib().kb2_merge_topk(0 if wl["metric"] == "L2" else 1, world, nq, k, g_ids.data_ptr(),
+                                          g_dis.data_ptr(), m_ids.data_ptr(), m_dis.data_ptr(), local_rank, stream))
+        return m_ids, m_dis
+
+    # ---- recall calibration: smallest refine_k reaching the target (benchmark_float_qps.cpp:80-108 method)
+    cfg = dict(wl["search"])
+    recall = None
+    n_gt = min(nq, 1000)
+    gt = ground_truth(kb, torch, xb, xq[:n_gt].contiguous(), k, wl["metric"])
+    if wl["index"] == "IVF_PQ":
+        for rk in (1, 2, 4, 8, 16, 32):
+            cfg["refine_k"] = rk
+            r_ids, _ = search_dev(cfg)
+            recall = recall_of(gt, r_ids[:n_gt].cpu().numpy())
+            if recall >= TARGET_RECALL:
+                break
+    else:
+        r_ids, _ = search_dev(cfg)
+        recall = recall_of(gt, r_ids[:n_gt].cpu().numpy())
+
+    # ---- timed region: device-resident
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        search_dev(cfg)
+    ix.enable_kernel_timing(True)
+    kernel_ms = []
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    launches = 0
+    for _ in range(args.steps):
+        search_dev(cfg)
+        kernel_ms.append(ix.last_kernel_ms())
+        launches += ix.last_counters()["launches"] + (5 if world > 1 else 0)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ctr = ix.last_counters()
+    ix.enable_kernel_timing(False)
+
+    # ---- end to end: pinned host queries in, host results out, through the same public call
+    xq_h = torch.empty((nq, d), dtype=torch.float32).pin_memory()
+    xq_h.copy_(xq.cpu())
+    ids_h = torch.empty((nq, k), dtype=torch.int64).pin_memory()
+    dis_h = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+    xq_np, ids_np, dis_np = xq_h.numpy(), ids_h.numpy(), dis_h.numpy()
+
+    def search_e2e():
+        if world == 1:
+            ix.search(xq_np, k, cfg, out=(ids_np, dis_np))
+        else:
+            xq.copy_(xq_h, non_blocking=True)
+            mi, md = search_dev(cfg)
+            ids_h.copy_(mi, non_blocking=True)
+            dis_h.copy_(md, non_blocking=True)
+            torch.cuda.synchronize()
+
+    for _ in range(max(1, args.warmup)):
+        search_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        search_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_ok = bool(np.array_equal(ids_np, (ids if world == 1 else m_ids).cpu().numpy()))
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    qps = nq * args.steps / (ms_total / 1e3)
+    e2e_qps = nq * args.steps / e2e_s
+    peak, peak_src = peaks()
+    # roofline of the dominant kernel (ivfpq_scan / ivfflat_scan): algorithmic bytes per launch =
+    # codes scanned x code_size (16 B per PQ code, ids excluded) / live CUDA-event duration
+    k_ms = statistics.mean(kernel_ms)
+    alg_bytes = ctr["code_bytes"]
+    achieved = alg_bytes / (k_ms / 1e3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "scan_kernel_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(args.workload)
+        except Exception:
+            traffic = None
+    out = {
+        "metric": METRIC_NAME if args.workload == "ivf_pq_10m" else f"queries/sec, {args.workload}",
+        "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{wl['index']} {wl['metric']} {n}x{d} f32, " +
+                               ", ".join(f"{a}={b}" for a, b in {**wl['build'], **cfg}.items()) +
+                               f", batch={nq}, k={k}",
+                   "recall_at_10": recall, "recall_queries": n_gt, "refine_k": cfg.get("refine_k"),
+                   "data": "clustered low-rank gaussian mixture, seeds base 42 / query 43 (SURVEY 8d)",
+                   "l2_policy": "inputs larger than L2 (codes 200 MB + refine vectors 5 GB per pass)",
+                   "sharding": "replica-free list sharding, l % N" if world > 1 else "single GPU",
+                   "build_s": round(t_build, 2), "datagen_s": round(t_gen, 2)},
+        "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": nq * d * 4,
+                "d2h_bytes_per_step": nq * k * 12, "results_equal_device_path": e2e_ok},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "ivfpq_scan_kernel" if wl["index"] == "IVF_PQ" else "ivfflat_scan_kernel",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_source": peak_src, "traffic": traffic, "kernel_ms": k_ms,
+                     "algorithmic_bytes_per_launch": alg_bytes, "codes_scanned_per_launch": ctr["codes"],
+                     "kernel_share_of_step": k_ms / (ms_total / args.steps)},
+    }
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): the reference's own CPU code on the host cores
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            out["cpu_baseline"] = cpu_baseline(kb, wl, ix, xb, xq_np, cfg, gt, n_gt, k)
+        except Exception as e:  # the baseline is a reported extra; never lose the GPU line over it
+            out["cpu_baseline"] = {"error": str(e)[:200]}
+    print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def export_to_reference(kb, wl, ix, xb):
+    """hand the GPU-built index to the reference classes so both sides search the same index"""
+    from oracle import ref
+    d = wl["d"]
+    m = wl["build"].get("m", 0)
+    nlist = ix.ivf_nlist()
+    refine = bool(wl["build"].get("refine"))
+    r = ref.RefIvf(wl["index"], d, 0 if wl["metric"] == "L2" else 1, nlist, m, 8, refine=refine)
+    cent, pq = ix.ivf_export_centroids(m)
+    cs = m if m else d * 4
+    raw = xb.cpu().numpy() if refine else None
+    r.import_state(cent, pq, ((l,) + ix.ivf_export_list(l, cs) for l in range(nlist)), raw=raw)
+    return r
+
+
+def time_reference(r, xq_np, k, cfg, min_seconds=10.0, max_reps=5):
+    nthreads = os.cpu_count() or 1
+    rk = float(cfg.get("refine_k", 0) or 0)
+    r.search(xq_np[:256], k, cfg["nprobe"], refine_k=rk, nthreads=nthreads)  # warm-up
+    times = []
+    t_all = time.perf_counter()
+    I = None
+    while len(times) < max_reps and (time.perf_counter() - t_all < min_seconds or len(times) < 3):
+        t0 = time.perf_counter()
+        I, _ = r.search(xq_np, k, cfg["nprobe"], refine_k=rk, nthreads=nthreads)
+        times.append(time.perf_counter() - t0)
+    return I, times, nthreads
+
+
+def cpu_baseline(kb, wl, ix, xb, xq_np, cfg, gt, n_gt, k):
+    r = export_to_reference(kb, wl, ix, xb)
+    I, times, nthreads = time_reference(r, xq_np, k, cfg)
+    med = statistics.median(times)
+    return {"value": len(xq_np) / med, "unit": "queries/s", "cores": nthreads, "kind": "reference",
+            "sample": f"full {len(xq_np)}-query batch x {len(times)} reps (median), one query per OpenMP task "
+                      f"(= Knowhere's one task per query), same index exported from the GPU build",
+            "recall_at_10": recall_of(gt, I[:n_gt])}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle/_ref) on the host cores."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    import knowhere_b200 as kb
+    from knowhere_b200 import datagen
+    wl = WORKLOADS[args.workload]
+    n, d, nq, k = wl["n"], wl["d"], wl["nq"], wl["k"]
+    dev = torch.device("cuda", 0)
+    xb = datagen.clustered_torch(n, d, 42, dev)
+    xq = datagen.clustered_torch(nq, d, 43, dev)
+    # the index is built once on the GPU and exported; the TIMED path below is 100% reference CPU code
+    ix = kb.Index(wl["index"], wl["metric"], d, wl["build"])
+    ix.build(xb)
+    cfg = dict(wl["search"])
+    gt = ground_truth(kb, torch, xb, xq[:1000].contiguous(), k, wl["metric"])
+    r = export_to_reference(kb, wl, ix, xb)
+    xq_np = xq.cpu().numpy()
+    del ix
+    recall = None
+    if wl["index"] == "IVF_PQ":
+        for rk in (1, 2, 4, 8, 16, 32):
+            cfg["refine_k"] = rk
+            I, _ = r.search(xq_np[:1000], k, cfg["nprobe"], refine_k=float(rk))
+            recall = recall_of(gt, I)
+            if recall >= TARGET_RECALL:
+                break
+    nthreads = os.cpu_count() or 1
+    rk = float(cfg.get("refine_k", 0) or 0)
+    for _ in range(args.warmup):
+        r.search(xq_np, k, cfg["nprobe"], refine_k=rk, nthreads=nthreads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r.search(xq_np, k, cfg["nprobe"], refine_k=rk, nthreads=nthreads)
+    el = time.perf_counter() - t0
+    qps = nq * args.steps / el
+    out = {"impl": "reference", "metric": METRIC_NAME if args.workload == "ivf_pq_10m" else f"queries/sec, {args.workload}",
+           "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"{wl['index']} {wl['metric']} {n}x{d} f32, " +
+                                  ", ".join(f"{a}={b}" for a, b in {**wl['build'], **cfg}.items()) + f", batch={nq}, k={k}",
+                      "recall_at_10": recall, "refine_k": cfg.get("refine_k")},
+           "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": nthreads, "kind": "reference",
+                            "sample": f"full {nq}-query batch per step, faiss IndexIVFPQ+IndexRefine via oracle/_ref, "
+                                      f"one query per OpenMP task"},
+           "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ivf_pq_10m", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -54,7 +54,8 @@ def test_ivfpq_imported_index_parity(kb, ref, metric, m, d):
     I0, D0 = r.search(xq, k, nprobe)
     ids, dist = ix.search(xq, k, {"nprobe": nprobe})
     # PQ codes collide (identical codes => identical ADC distance): allow tie rows, compare sets
-    assert_topk_parity(ids, dist, I0, D0, rtol=1e-4, atol=1e-3, what=f"IVF_PQ m={m}")
+    # (every differing id is still verified to sit exactly at the k-th distance)
+    assert_topk_parity(ids, dist, I0, D0, rtol=1e-4, atol=1e-3, what=f"IVF_PQ m={m}", max_tie_rows=nq // 4)
     # coarse stage must agree exactly with the reference quantizer
     CI, CD = r.coarse(xq, nprobe)
     # (indirectly checked by the result parity above; direct check through nprobe=1 results)
@@ -113,7 +114,8 @@ def test_ivf_gpu_build_recall_vs_reference(kb, ref, kind, m):
     cs = m if m else d * 4
     r2.import_state(c, pq, [(l,) + ix.ivf_export_list(l, cs) for l in range(nlist)])
     I2, D2 = r2.search(xq, k, nprobe)
-    assert_topk_parity(ids, dist, I2, D2, rtol=1e-4, atol=1e-3, what=f"{kind} gpu-built vs cpu search")
+    assert_topk_parity(ids, dist, I2, D2, rtol=1e-4, atol=1e-3, what=f"{kind} gpu-built vs cpu search",
+                       max_tie_rows=nq // 4)
 
 
 def test_ivf_small_batch_splits_probes(kb, ref):
