@@ -158,7 +158,7 @@ select_keys_kernel(const float* __restrict__ keys, int64_t ldk, int ncols, int K
     const int c1 = min(ncols, c0 + per);
 
     WarpTopK tk;
-    tk.init(lists + warp * K, K, lane);
+    tk.init(lists + warp * 2 * K, K, lane);
     const float* row = keys + q * ldk;
     for (int base = c0 + warp * kWarp; base < c1; base += kScanWarps * kWarp) {
         const int c = base + lane;
@@ -168,6 +168,7 @@ select_keys_kernel(const float* __restrict__ keys, int64_t ldk, int ncols, int K
         tk.push(pack_kp(key, pos_base + (uint32_t)c), valid && key < INFINITY, lane);
     }
     uint64_t* out = partial + (q * slots_per_query + slot_base + s) * (int64_t)kout;
+    tk.finish(lane);
     block_emit_topk(lists, K, out, kout);
 }
 

@@ -180,7 +180,7 @@ dense_candidates(IndexBase& ix, const float* Q, int64_t nq, const float* X, cons
     int nsplit = (int)std::min<int64_t>(std::max<int64_t>(1, (2 * kNumSMs + nq - 1) / nq),
                                         std::max<int64_t>(1, chunk / 512));
     nsplit = std::min(nsplit, pl.S - 1);
-    const size_t sel_smem = (size_t)kScanWarps * pl.Ksel * 8;
+    const size_t sel_smem = (size_t)kScanWarps * 2 * pl.Ksel * 8;
     for (int64_t c0 = 0; c0 < n; c0 += chunk) {
         const int64_t cols = std::min(chunk, n - c0);
         if (pl.used + nsplit > pl.S) {
@@ -687,7 +687,7 @@ struct IvfIndex : IndexBase {
         sp.npad = npad;
         sp.t1 = t1.p;
         sp.counters = d_counter.p;
-        const size_t common_smem = (size_t)kScanWarps * Ksel * 8 + (size_t)(np_max + 1) * 4 + (size_t)np_max * 12 +
+        const size_t common_smem = (size_t)kScanWarps * 2 * Ksel * 8 + (size_t)(np_max + 1) * 4 + (size_t)np_max * 12 +
                                    (size_t)dim * 4 + 64;
         const unsigned grid = (unsigned)(nq * nsplit);
         if (timing) KB2_CUDA_CHECK(cudaEventRecord(ev0, st));

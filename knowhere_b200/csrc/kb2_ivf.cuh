@@ -125,7 +125,7 @@ pq_group_sum(const uint4& w, uint32_t lane4, float& acc0, float& acc1) {
 
 // =====================================================================================
 // IVF_PQ scan.  G = M/16 groups.  grid = nq * nsplit, block = 256.
-// dynamic smem: G*65536 (LUT, first) | kScanWarps*K*8 (lists) | probes | query
+// dynamic smem: G*65536 (LUT, first) | kScanWarps*2K*8 (candidate buffers) | probes | query
 // =====================================================================================
 template <int G, int METRIC>
 __global__ void __launch_bounds__(kScanThreads)
@@ -135,7 +135,7 @@ ivfpq_scan_kernel(IvfScanParams p) {
     uint64_t* lists = (uint64_t*)(smem_raw + (size_t)G * 65536);
     const int np_max = (p.nprobe + p.nsplit - 1) / p.nsplit;
     ProbeSmem ps;
-    ps.start = (uint32_t*)(lists + kScanWarps * p.K);
+    ps.start = (uint32_t*)(lists + kScanWarps * 2 * p.K);
     ps.off = ps.start + np_max + 1;
     ps.len = (int32_t*)(ps.off + np_max);
     ps.dis0 = (float*)(ps.len + np_max);
@@ -184,7 +184,7 @@ ivfpq_scan_kernel(IvfScanParams p) {
         }
     }
     WarpTopK tk;
-    tk.init(lists + warp * p.K, p.K, lane);
+    tk.init(lists + warp * 2 * p.K, p.K, lane);
     __syncthreads();
 
     // ---- scan
@@ -238,6 +238,7 @@ ivfpq_scan_kernel(IvfScanParams p) {
         if (lane == 0) atomicAdd(p.counters, scanned);
     }
     uint64_t* out = p.partial + ((int64_t)q * p.nsplit + split) * p.kout;
+    tk.finish(lane);
     block_emit_topk(lists, p.K, out, p.kout);
 }
 
@@ -254,7 +255,7 @@ ivfpq_scan_generic_kernel(IvfScanParams p, const uint8_t* __restrict__ codes_b) 
     uint64_t* lists = (uint64_t*)(smem_raw + (size_t)p.M * 1024);
     const int np_max = (p.nprobe + p.nsplit - 1) / p.nsplit;
     ProbeSmem ps;
-    ps.start = (uint32_t*)(lists + kScanWarps * p.K);
+    ps.start = (uint32_t*)(lists + kScanWarps * 2 * p.K);
     ps.off = ps.start + np_max + 1;
     ps.len = (int32_t*)(ps.off + np_max);
     ps.dis0 = (float*)(ps.len + np_max);
@@ -275,7 +276,7 @@ ivfpq_scan_generic_kernel(IvfScanParams p, const uint8_t* __restrict__ codes_b) 
         lut[e] = acc * scale;
     }
     WarpTopK tk;
-    tk.init(lists + warp * p.K, p.K, lane);
+    tk.init(lists + warp * 2 * p.K, p.K, lane);
     __syncthreads();
     int cur = 0;
     for (int c = warp; c < nchunks; c += kScanWarps) {
@@ -293,6 +294,7 @@ ivfpq_scan_generic_kernel(IvfScanParams p, const uint8_t* __restrict__ codes_b) 
         tk.push(pack_kp(ps.dis0[cur] + acc, pos), valid, lane);
     }
     uint64_t* out = p.partial + ((int64_t)q * p.nsplit + split) * p.kout;
+    tk.finish(lane);
     block_emit_topk(lists, p.K, out, p.kout);
 }
 
@@ -310,7 +312,7 @@ ivfflat_scan_kernel(IvfScanParams p) {
     uint64_t* lists = (uint64_t*)(s_q + p.d);
     const int np_max = (p.nprobe + p.nsplit - 1) / p.nsplit;
     ProbeSmem ps;
-    ps.start = (uint32_t*)(lists + kScanWarps * p.K);
+    ps.start = (uint32_t*)(lists + kScanWarps * 2 * p.K);
     ps.off = ps.start + np_max + 1;
     ps.len = (int32_t*)(ps.off + np_max);
     ps.dis0 = (float*)(ps.len + np_max);
@@ -322,7 +324,7 @@ ivfflat_scan_kernel(IvfScanParams p) {
     for (int i = threadIdx.x; i < p.d; i += blockDim.x) s_q[i] = p.queries[q * p.d + i];
     const int nchunks = setup_probes(p, q, j0, j1, ps);
     WarpTopK tk;
-    tk.init(lists + warp * p.K, p.K, lane);
+    tk.init(lists + warp * 2 * p.K, p.K, lane);
     __syncthreads();
 
     const int nv = p.d >> 2;  // float4 per row
@@ -380,6 +382,7 @@ ivfflat_scan_kernel(IvfScanParams p) {
         if (lane == 0) atomicAdd(p.counters, scanned);
     }
     uint64_t* out = p.partial + ((int64_t)q * p.nsplit + split) * p.kout;
+    tk.finish(lane);
     block_emit_topk(lists, p.K, out, p.kout);
 }
 

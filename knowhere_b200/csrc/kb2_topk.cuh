@@ -14,58 +14,72 @@
 namespace kb2 {
 
 // --------------------------------------------------------------------------------------------
-// Per-warp top-K: unsorted list of K packed (key,pos) entries in shared memory, replace-the-max
-// admission with a warp-uniform threshold.  After the first few hundred candidates the common
-// path is ONE ballot per 32 candidates.
+// Per-warp top-K, "append and prune".  The warp owns a buffer of 2K packed (key,pos) entries in
+// shared memory.  Candidates below the warp-uniform threshold are appended (one ballot + one
+// predicated store per 32 candidates); when the buffer would overflow it is bitonic-sorted in place
+// and cut back to the best K, which also tightens the threshold to the K-th best seen so far.
+// Cost: ~2 ln(N/K) prunes per warp instead of ~K ln(N/K) list updates.
 // --------------------------------------------------------------------------------------------
 struct WarpTopK {
-    uint64_t* list;  // shared memory, K entries
-    int K;           // multiple of 32
-    uint64_t thr;    // current maximum of the list (kEmpty until full); warp-uniform
-    int maxpos;
+    uint64_t* buf;   // shared memory, 2K entries
+    int K;           // power of two, >= 32
+    int cnt;         // entries in buf (warp-uniform)
+    uint64_t thr;    // admission threshold (kEmpty until the first prune); warp-uniform
 
     __device__ __forceinline__ void
-    init(uint64_t* l, int k, int lane) {
-        list = l;
+    init(uint64_t* b, int k, int lane) {
+        buf = b;
         K = k;
-        for (int i = lane; i < K; i += kWarp) list[i] = kEmpty;
+        cnt = 0;
         thr = kEmpty;
-        maxpos = 0;
-        __syncwarp();
+        (void)lane;
     }
 
+    // in-place ascending bitonic sort of the 2K-entry buffer by one warp (unused tail = kEmpty)
     __device__ __forceinline__ void
-    recompute_max(int lane) {
-        uint64_t lm = list[lane];  // K >= 32
-        int lp = lane;
-        for (int i = lane + kWarp; i < K; i += kWarp) {
-            uint64_t v = list[i];
-            if (v > lm) { lm = v; lp = i; }
+    prune(int lane) {
+        const int n = 2 * K;
+        for (int i = cnt + lane; i < n; i += kWarp) buf[i] = kEmpty;
+        __syncwarp();
+        for (int k2 = 2; k2 <= n; k2 <<= 1) {
+            for (int j = k2 >> 1; j > 0; j >>= 1) {
+                for (int t = lane; t < (n >> 1); t += kWarp) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // index with bit j clear
+                    const int p = i | j;
+                    const uint64_t a = buf[i], b = buf[p];
+                    const bool asc = ((i & k2) == 0);
+                    if ((a > b) == asc) { buf[i] = b; buf[p] = a; }
+                }
+                __syncwarp();
+            }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            uint64_t ov = __shfl_xor_sync(0xffffffffu, lm, o);
-            int op = __shfl_xor_sync(0xffffffffu, lp, o);
-            if (ov > lm || (ov == lm && op < lp)) { lm = ov; lp = op; }
-        }
-        thr = lm;
-        maxpos = lp;
+        cnt = min(cnt, K);
+        thr = buf[K - 1];  // kEmpty while fewer than K candidates exist
     }
 
     // all 32 lanes must call; `valid` lanes offer `cand`
     __device__ __forceinline__ void
     push(uint64_t cand, bool valid, int lane) {
-        unsigned m = __ballot_sync(0xffffffffu, valid && cand < thr);
-        while (m) {
-            int src = __ffs(m) - 1;
-            m &= m - 1;
-            uint64_t c = __shfl_sync(0xffffffffu, cand, src);
-            if (c < thr) {  // thr shrinks while we drain the ballot
-                if (lane == 0) list[maxpos] = c;
-                __syncwarp();
-                recompute_max(lane);
-            }
+        bool pass = valid && cand < thr;
+        unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (m == 0) return;
+        if (cnt + __popc(m) > 2 * K) {
+            prune(lane);
+            pass = valid && cand < thr;
+            m = __ballot_sync(0xffffffffu, pass);
+            if (m == 0) return;
         }
+        if (pass) buf[cnt + __popc(m & ((1u << lane) - 1u))] = cand;
+        cnt += __popc(m);
+    }
+
+    // final prune: afterwards buf[0..K) is sorted ascending (kEmpty padded), buf[K..2K) = kEmpty
+    __device__ __forceinline__ void
+    finish(int lane) {
+        __syncwarp();
+        prune(lane);
+        for (int i = K + lane; i < 2 * K; i += kWarp) buf[i] = kEmpty;
+        __syncwarp();
     }
 };
 
@@ -89,12 +103,12 @@ block_bitonic_sort(uint64_t* s, int n) {
     }
 }
 
-// After the per-warp lists (kScanWarps * K contiguous u64 in `lists`) are complete: sort them
-// CTA-wide and write the best `kout` to out[0..kout).  Requires kScanWarps*K to be a power of two.
+// After every warp called WarpTopK::finish(): the kScanWarps buffers (2K entries each, contiguous in
+// `lists`) are sorted CTA-wide and the best `kout` written to out[0..kout).
 __device__ __forceinline__ void
 block_emit_topk(uint64_t* lists, int K, uint64_t* __restrict__ out, int kout) {
     __syncthreads();
-    block_bitonic_sort(lists, kScanWarps * K);
+    block_bitonic_sort(lists, kScanWarps * 2 * K);
     for (int i = threadIdx.x; i < kout; i += blockDim.x) out[i] = lists[i];
 }
 
