@@ -138,7 +138,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     import knowhere_b200 as kb
-    from knowhere_b200 import datagen
+    from knowhere_b200 import datagen, sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -165,26 +165,21 @@ def run_ours(args):
     ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
     dis = torch.empty((nq, k), dtype=torch.float32, device=dev)
     if world > 1:
-        pack = torch.empty((nq, 2 * k), dtype=torch.int64, device=dev)
-        gathered = torch.empty((world, nq, 2 * k), dtype=torch.int64, device=dev)
-        g_ids = torch.empty((world, nq, k), dtype=torch.int64, device=dev)
-        g_dis = torch.empty((world, nq, k), dtype=torch.float32, device=dev)
         m_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
         m_dis = torch.empty((nq, k), dtype=torch.float32, device=dev)
+
+    def merge_fn(g_ids, g_dis):
+        # the kernel that consumes the all-gather: per-query merge of the world x k candidates
+        kb._check(kb.lib().kb2_merge_topk(0 if wl["metric"] == "L2" else 1, world, nq, k, g_ids.data_ptr(),
+                                          g_dis.data_ptr(), m_ids.data_ptr(), m_dis.data_ptr(), local_rank, stream))
+        return m_ids, m_dis
 
     def search_dev(cfg, q=None):
         ix.search(xq if q is None else q, k, cfg, out=(ids, dis))
         if world == 1:
             return ids, dis
-        # ONE all-gather of the per-shard (id, distance) candidates, then the merge kernel
-        pack[:, :k] = ids
-        pack[:, k:] = dis.view(torch.int32).to(torch.int64)
-        dist.all_gather_into_tensor(gathered, pack)
-        g_ids.copy_(gathered[:, :, :k])
-        g_dis.copy_(gathered[:, :, k:].to(torch.int32).view(torch.float32))
-        kb._check(kb.lib().kb2_merge_topk(0 if wl["metric"] == "L2" else 1, world, nq, k, g_ids.data_ptr(),
-                                          g_dis.data_ptr(), m_ids.data_ptr(), m_dis.data_ptr(), local_rank, stream))
-        return m_ids, m_dis
+        # ONE all-gather of the packed per-shard (id, distance) candidates, then the merge kernel
+        return sharding.gather_and_merge(torch, dist, ids, dis, merge_fn, world)
 
     # ---- recall calibration: smallest refine_k reaching the target (benchmark_float_qps.cpp:80-108 method)
     cfg = dict(wl["search"])

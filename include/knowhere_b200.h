@@ -182,6 +182,13 @@ int kb2_index_last_search_counters(kb2_index_t h, int64_t* out8);
 int kb2_index_enable_kernel_timing(kb2_index_t h, int on);
 int kb2_index_last_kernel_ms(kb2_index_t h, float* out_ms);
 
+/* validation hook: writes the full key matrix [nq][round_up(nb,4)] of the dense contraction
+ * (|q|^2+|x|^2-2qx for L2, -qx for IP) computed by the fp32 CUDA-core kernel (use_tc=0) or by the
+ * tcgen05 tensor-core kernel (use_tc=1).  Device pointers only.  Used by tests to hold the tensor-core
+ * path to the fp32 one (the reference computes these distances with src/simd fvec_L2sqr_ny). */
+int kb2_debug_gemm_keys(const float* q, int64_t nq, const float* x, int64_t nb, int dim, int metric, int use_tc,
+                        float* out_keys, int device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -222,6 +222,17 @@ gather_f32_kernel(const float* __restrict__ src, const int32_t* __restrict__ row
     out[t] = (r >= 0) ? src[r] : fill;
 }
 
+// key = nearest list of each query (first entry of its probe row), value = query index
+__global__ void
+first_probe_kernel(const int64_t* __restrict__ probe_ids, int nprobe, int64_t nq, int32_t* __restrict__ key,
+                   int32_t* __restrict__ idx) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    const int64_t l = probe_ids[i * nprobe];
+    key[i] = l < 0 ? 0 : (int32_t)l;
+    idx[i] = (int32_t)i;
+}
+
 static inline dim3
 grid1d(int64_t n, int block) {
     return dim3((unsigned)((n + block - 1) / block));

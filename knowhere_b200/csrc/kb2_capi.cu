@@ -480,6 +480,28 @@ kb2_merge_topk(int metric, int world, int64_t nq, int k, const int64_t* in_ids, 
     });
 }
 
+// ---------------------------------------------------------------- validation hook for the two contractions
+int
+kb2_debug_gemm_keys(const float* q, int64_t nq, const float* x, int64_t nb, int dim, int metric, int use_tc, float* out_keys,
+                    int device) {
+    return guarded([&] {
+        require_device(device);
+        KB2_REQUIRE(is_device_ptr(q) && is_device_ptr(x) && is_device_ptr(out_keys), KB2_INVALID_ARGS,
+                    "debug_gemm_keys takes device pointers");
+        const int64_t ldk = (nb + 3) & ~(int64_t)3;
+        DevBuf<float> qn, xn;
+        qn.ensure(nq);
+        xn.ensure(nb);
+        row_norms_kernel<<<grid1d(nq * 32, 256), 256>>>(q, nq, dim, qn.p);
+        row_norms_kernel<<<grid1d(nb * 32, 256), 256>>>(x, nb, dim, xn.p);
+        const bool ran_tc = launch_gemm_keys(nullptr, use_tc ? 1 : 0, metric, q, x, qn.p, xn.p, (int)nq, (int)nb, dim, out_keys,
+                                             ldk, nullptr, nullptr, 0);
+        KB2_CUDA_CHECK(cudaGetLastError());
+        KB2_CUDA_CHECK(cudaDeviceSynchronize());
+        KB2_REQUIRE(!use_tc || ran_tc, KB2_INTERNAL_ERROR, "tensor-core contraction unavailable (tensor map / alignment)");
+    });
+}
+
 // ---------------------------------------------------------------- introspection
 int
 kb2_index_last_search_counters(kb2_index_t h, int64_t* out8) {

@@ -172,4 +172,100 @@ select_keys_kernel(const float* __restrict__ keys, int64_t ldk, int ncols, int K
     block_emit_topk(lists, K, out, kout);
 }
 
+
+// ---------------------------------------------------------------- key selection by radix select
+// Same contract as select_keys_kernel but O(slice) work: the K-th smallest key of the slice is found
+// with four 8-bit histogram passes over the order-preserving integer image of the keys held in shared
+// memory, then everything below it (plus position-ordered ties) is emitted UNSORTED — finalize /
+// reduce sort their input anyway.  Used for wide selections (IVF coarse: top-(nprobe+16) of nlist).
+// grid (nq, nsplit), dynamic smem: slice*4 + 1040 bytes.
+__global__ void __launch_bounds__(256)
+select_keys_radix_kernel(const float* __restrict__ keys, int64_t ldk, int ncols, int K, uint64_t* __restrict__ partial,
+                         int slots_per_query, int slot_base, uint32_t pos_base) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* hist = (uint32_t*)smem_raw;          // 256 bins
+    uint32_t* ctl = hist + 256;                    // [0] prefix [1] remaining [2] out cursor [3] count_eq
+    uint32_t* ord = ctl + 4;                       // slice
+    const int64_t q = blockIdx.x;
+    const int nsplit = gridDim.y, s = blockIdx.y;
+    const int per = (((ncols + nsplit - 1) / nsplit) + 31) / 32 * 32;
+    const int c0 = min(ncols, s * per);
+    const int c1 = min(ncols, c0 + per);
+    const int n = c1 - c0;
+    const float* row = keys + q * ldk + c0;
+    uint64_t* out = partial + (q * slots_per_query + slot_base + s) * (int64_t)K;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) ord[i] = f2ord(row[i]);
+    if (threadIdx.x == 0) { ctl[0] = 0; ctl[1] = (uint32_t)K; ctl[2] = 0; ctl[3] = 0; }
+    __syncthreads();
+    const uint32_t kInfOrd = f2ord(INFINITY);      // filtered entries: never emitted
+    if (n <= K) {
+        for (int i = threadIdx.x; i < K; i += blockDim.x)
+            out[i] = (i < n && ord[i] < kInfOrd) ? (((uint64_t)ord[i] << 32) | (pos_base + (uint32_t)(c0 + i))) : kEmpty;
+        return;
+    }
+    uint32_t prefix = 0, fixed_mask = 0;
+    for (int pass = 0; pass < 4; pass++) {
+        const int shift = 24 - 8 * pass;
+        hist[threadIdx.x] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint32_t v = ord[i];
+            if ((v & fixed_mask) == prefix) atomicAdd(&hist[(v >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            // warp 0: find the digit where the running count reaches `remaining`
+            const uint32_t remaining = ctl[1];
+            uint32_t local[8], sum = 0;
+#pragma unroll
+            for (int t = 0; t < 8; t++) { local[t] = hist[threadIdx.x * 8 + t]; sum += local[t]; }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)threadIdx.x >= o) incl += v;
+            }
+            const uint32_t excl = incl - sum;
+            if (excl < remaining && remaining <= incl) {   // exactly one lane
+                uint32_t run = excl;
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    if (run < remaining && remaining <= run + local[t]) {
+                        ctl[0] = prefix | ((uint32_t)(threadIdx.x * 8 + t) << shift);
+                        ctl[1] = remaining - run;
+                    }
+                    run += local[t];
+                }
+            }
+        }
+        __syncthreads();
+        prefix = ctl[0];
+        fixed_mask |= 0xffu << shift;
+        __syncthreads();
+    }
+    const uint32_t T = prefix;                 // exact K-th smallest key image
+    const uint32_t need_eq = ctl[1];           // how many entries equal to T belong to the selection
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t v = ord[i];
+        if (v < T && v < kInfOrd) {
+            const uint32_t slot = atomicAdd(&ctl[2], 1u);
+            out[slot] = ((uint64_t)v << 32) | (pos_base + (uint32_t)(c0 + i));
+        } else if (v == T) {
+            atomicAdd(&ctl[3], 1u);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // ties on the K-th key: lowest positions first (deterministic); rare, so serial
+        uint32_t slot = ctl[2], left = need_eq;
+        if (T < kInfOrd) {
+            for (int i = 0; i < n && left > 0; i++)
+                if (ord[i] == T) { out[slot++] = ((uint64_t)T << 32) | (pos_base + (uint32_t)(c0 + i)); left--; }
+        }
+        ctl[2] = slot;
+    }
+    __syncthreads();
+    for (int i = ctl[2] + threadIdx.x; i < K; i += blockDim.x) out[i] = kEmpty;
+}
+
 }  // namespace kb2

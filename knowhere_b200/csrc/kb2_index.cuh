@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "kb2_build.cuh"
+#include "kb2_gemm_tc.cuh"
 #include "kb2_ivf.cuh"
 #include "kb2_json.h"
 
@@ -17,6 +18,9 @@ namespace kb2 {
 constexpr int kMaxK = 1024;            // largest k' any selection kernel keeps
 constexpr int kMaxSortEntries = 8192;  // finalize sorts at most this many candidates per query
 constexpr int kMaxDynSmem = 227 * 1024;
+#ifndef KB2_DEFAULT_GEMM_MODE
+#define KB2_DEFAULT_GEMM_MODE 0
+#endif
 
 inline void
 init_kernel_attributes() {
@@ -28,18 +32,70 @@ init_kernel_attributes() {
         set((const void*)finalize_kernel);
         set((const void*)reduce_partials_kernel);
         set((const void*)select_keys_kernel);
-        set((const void*)ivfpq_scan_kernel<1, KB2_METRIC_L2>);
-        set((const void*)ivfpq_scan_kernel<1, KB2_METRIC_IP>);
-        set((const void*)ivfpq_scan_kernel<2, KB2_METRIC_L2>);
-        set((const void*)ivfpq_scan_kernel<2, KB2_METRIC_IP>);
-        set((const void*)ivfpq_scan_kernel<3, KB2_METRIC_L2>);
-        set((const void*)ivfpq_scan_kernel<3, KB2_METRIC_IP>);
+        set((const void*)select_keys_radix_kernel);
+        set((const void*)ivfpq_scan_kernel<1, KB2_METRIC_L2, false>);
+        set((const void*)ivfpq_scan_kernel<1, KB2_METRIC_IP, false>);
+        set((const void*)ivfpq_scan_kernel<2, KB2_METRIC_L2, false>);
+        set((const void*)ivfpq_scan_kernel<2, KB2_METRIC_IP, false>);
+        set((const void*)ivfpq_scan_kernel<3, KB2_METRIC_L2, false>);
+        set((const void*)ivfpq_scan_kernel<3, KB2_METRIC_IP, false>);
+        set((const void*)ivfpq_scan_kernel<1, KB2_METRIC_L2, true>);
+        set((const void*)ivfpq_scan_kernel<1, KB2_METRIC_IP, true>);
+        set((const void*)ivfpq_scan_kernel<2, KB2_METRIC_L2, true>);
+        set((const void*)ivfpq_scan_kernel<2, KB2_METRIC_IP, true>);
+        set((const void*)ivfpq_scan_kernel<3, KB2_METRIC_L2, true>);
+        set((const void*)ivfpq_scan_kernel<3, KB2_METRIC_IP, true>);
         set((const void*)ivfpq_scan_generic_kernel<KB2_METRIC_L2>);
         set((const void*)ivfpq_scan_generic_kernel<KB2_METRIC_IP>);
         set((const void*)ivfflat_scan_kernel<KB2_METRIC_L2>);
         set((const void*)ivfflat_scan_kernel<KB2_METRIC_IP>);
         cudaGetLastError();
     });
+}
+
+// 0 = fp32 CUDA-core contraction, 1 = tcgen05 (3xTF32) contraction.  KB2_GEMM=fp32|tc overrides.
+inline int
+gemm_mode() {
+    static int mode = [] {
+        const char* e = getenv("KB2_GEMM");
+        if (e && strcmp(e, "fp32") == 0) return 0;
+        if (e && strcmp(e, "tc") == 0) return 1;
+        return KB2_DEFAULT_GEMM_MODE;
+    }();
+    return mode;
+}
+
+// keys[nq][ldk] <- contraction of Q[nq][d] with X[cols][d]; returns true if the tensor-core path ran
+inline bool
+launch_gemm_keys(cudaStream_t st, int mode, int metric, const float* Q, const float* X, const float* qn,
+                 const float* xn, int nq, int cols, int d, float* keys, int64_t ldk, const uint8_t* bitset,
+                 const int32_t* rows, int64_t row_base) {
+    if (mode == 1 && (ldk & 3) == 0) {
+        CUtensorMap tq, tx;
+        if (tc::make_tmap(&tq, Q, nq, d) && tc::make_tmap(&tx, X, cols, d)) {
+            static std::once_flag once;
+            std::call_once(once, [] {
+                cudaFuncSetAttribute((const void*)tc::gemm_keys_tc_kernel<KB2_METRIC_L2>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
+                cudaFuncSetAttribute((const void*)tc::gemm_keys_tc_kernel<KB2_METRIC_IP>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
+            });
+            dim3 g((unsigned)((cols + tc::BN - 1) / tc::BN), (unsigned)((nq + tc::BM - 1) / tc::BM));
+            if (metric == KB2_METRIC_L2)
+                tc::gemm_keys_tc_kernel<KB2_METRIC_L2><<<g, tc::THREADS, tc::SMEM_BYTES, st>>>(tq, tx, qn, xn, nq, cols, d, keys,
+                                                                                           ldk, bitset, rows, row_base);
+            else
+                tc::gemm_keys_tc_kernel<KB2_METRIC_IP><<<g, tc::THREADS, tc::SMEM_BYTES, st>>>(tq, tx, qn, xn, nq, cols, d, keys,
+                                                                                           ldk, bitset, rows, row_base);
+            return true;
+        }
+    }
+    dim3 g((unsigned)((cols + GK_BN - 1) / GK_BN), (unsigned)((nq + GK_BM - 1) / GK_BM));
+    if (metric == KB2_METRIC_L2)
+        gemm_keys_kernel<KB2_METRIC_L2><<<g, 256, 0, st>>>(Q, X, qn, xn, nq, cols, d, keys, ldk, bitset, rows, row_base);
+    else
+        gemm_keys_kernel<KB2_METRIC_IP><<<g, 256, 0, st>>>(Q, X, qn, xn, nq, cols, d, keys, ldk, bitset, rows, row_base);
+    return false;
 }
 
 struct Counters {
@@ -176,7 +232,8 @@ dense_candidates(IndexBase& ix, const float* Q, int64_t nq, const float* X, cons
     const int64_t max_key_elems = 64ll << 20;  // 256 MB of keys
     int64_t chunk = std::min<int64_t>(n, std::max<int64_t>(1024, max_key_elems / std::max<int64_t>(nq, 1)));
     if (chunk < n) chunk = std::max<int64_t>(128, chunk / 128 * 128);
-    ix.s_keys.ensure((size_t)nq * chunk);
+    const int64_t ldk = (chunk + 3) & ~(int64_t)3;   // 16-byte aligned key rows (vector stores in the epilogues)
+    ix.s_keys.ensure((size_t)nq * ldk);
     int nsplit = (int)std::min<int64_t>(std::max<int64_t>(1, (2 * kNumSMs + nq - 1) / nq),
                                         std::max<int64_t>(1, chunk / 512));
     nsplit = std::min(nsplit, pl.S - 1);
@@ -191,15 +248,17 @@ dense_candidates(IndexBase& ix, const float* Q, int64_t nq, const float* X, cons
             ix.last.launches++;
             pl.used = 1;
         }
-        dim3 g((unsigned)((cols + GK_BN - 1) / GK_BN), (unsigned)((nq + GK_BM - 1) / GK_BM));
-        if (metric == KB2_METRIC_L2)
-            gemm_keys_kernel<KB2_METRIC_L2><<<g, 256, 0, st>>>(Q, X + c0 * d, ix.s_qn.p, xn + c0, (int)nq, (int)cols, d,
-                                                               ix.s_keys.p, chunk, bitset, rows, c0);
-        else
-            gemm_keys_kernel<KB2_METRIC_IP><<<g, 256, 0, st>>>(Q, X + c0 * d, ix.s_qn.p, xn, (int)nq, (int)cols, d,
-                                                               ix.s_keys.p, chunk, bitset, rows, c0);
-        select_keys_kernel<<<dim3((unsigned)nq, nsplit), kScanThreads, sel_smem, st>>>(
-            ix.s_keys.p, chunk, (int)cols, pl.Ksel, pl.Ksel, ix.s_partial.p, pl.S, pl.used, (uint32_t)c0);
+        launch_gemm_keys(st, gemm_mode(), metric, Q, X + c0 * d, ix.s_qn.p, xn + c0, (int)nq, (int)cols, d, ix.s_keys.p, ldk,
+                         bitset, rows, c0);
+        const int per_slice = (int)(((cols + nsplit - 1) / nsplit + 31) / 32 * 32);
+        const size_t radix_smem = (size_t)per_slice * 4 + 1040;
+        if (pl.Ksel >= 64 && radix_smem <= (size_t)kMaxDynSmem) {
+            select_keys_radix_kernel<<<dim3((unsigned)nq, nsplit), 256, radix_smem, st>>>(
+                ix.s_keys.p, ldk, (int)cols, pl.Ksel, ix.s_partial.p, pl.S, pl.used, (uint32_t)c0);
+        } else {
+            select_keys_kernel<<<dim3((unsigned)nq, nsplit), kScanThreads, sel_smem, st>>>(
+                ix.s_keys.p, ldk, (int)cols, pl.Ksel, pl.Ksel, ix.s_partial.p, pl.S, pl.used, (uint32_t)c0);
+        }
         ix.last.launches += 2;
         pl.used += nsplit;
     }
@@ -374,6 +433,8 @@ struct IvfIndex : IndexBase {
     DevBuf<uint8_t> codes;     // [G][npad][16] or [npad][M]
     DevBuf<float> t1, vecs;
     DevBuf<int64_t> labels;    // row -> label (sealed copy of f_labels)
+    DevBuf<int32_t> s_qkey, s_qkey2, s_qidx, s_qperm;
+    DevBuf<uint8_t> s_sort_tmp;
 
     bool keeps_vecs() const { return !is_pq || refine; }
     bool is_trained() const override { return trained; }
@@ -655,6 +716,23 @@ struct IvfIndex : IndexBase {
             launch_finalize(*this, fp, nq);
         }
 
+        // ---- visiting order of the queries: sorted by nearest list, so that CTAs resident at the same
+        //      time probe the same lists (L2 reuse of codes; results are order-independent)
+        const int32_t* qperm = nullptr;
+        if (nq >= 2 * kNumSMs) {
+            s_qkey.ensure(nq); s_qkey2.ensure(nq); s_qidx.ensure(nq); s_qperm.ensure(nq);
+            first_probe_kernel<<<grid1d(nq, 256), 256, 0, st>>>(s_probe_ids.p, nprobe, nq, s_qkey.p, s_qidx.p);
+            size_t tmp_bytes = 0;
+            int end_bit = 1;
+            while ((1ll << end_bit) < nlist) end_bit++;
+            cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, s_qkey.p, s_qkey2.p, s_qidx.p, s_qperm.p, (int)nq, 0, end_bit, st);
+            s_sort_tmp.ensure(tmp_bytes);
+            cub::DeviceRadixSort::SortPairs(s_sort_tmp.p, tmp_bytes, s_qkey.p, s_qkey2.p, s_qidx.p, s_qperm.p, (int)nq, 0,
+                                            end_bit, st);
+            qperm = s_qperm.p;
+            last.launches += 3;
+        }
+
         // ---- list scan
         int nsplit = 1;
         if (nq < 2 * kNumSMs) nsplit = (int)std::min<int64_t>(nprobe, (2 * kNumSMs + nq - 1) / nq);
@@ -687,6 +765,7 @@ struct IvfIndex : IndexBase {
         sp.npad = npad;
         sp.t1 = t1.p;
         sp.counters = d_counter.p;
+        sp.qperm = qperm;
         const size_t common_smem = (size_t)kScanWarps * 2 * Ksel * 8 + (size_t)(np_max + 1) * 4 + (size_t)np_max * 12 +
                                    (size_t)dim * 4 + 64;
         const unsigned grid = (unsigned)(nq * nsplit);
@@ -696,10 +775,13 @@ struct IvfIndex : IndexBase {
                 const size_t smem = (size_t)G * 65536 + common_smem;
                 KB2_REQUIRE(smem <= (size_t)kMaxDynSmem, KB2_INVALID_ARGS, "IVF_PQ: k too large for shared memory");
 #define KB2_LAUNCH_PQ(GG)                                                                             \
-    if (metric == KB2_METRIC_L2)                                                                      \
-        ivfpq_scan_kernel<GG, KB2_METRIC_L2><<<grid, kScanThreads, smem, st>>>(sp);                   \
-    else                                                                                              \
-        ivfpq_scan_kernel<GG, KB2_METRIC_IP><<<grid, kScanThreads, smem, st>>>(sp);
+    if (metric == KB2_METRIC_L2) {                                                                    \
+        if (dbits) ivfpq_scan_kernel<GG, KB2_METRIC_L2, true><<<grid, kScanThreads, smem, st>>>(sp);  \
+        else ivfpq_scan_kernel<GG, KB2_METRIC_L2, false><<<grid, kScanThreads, smem, st>>>(sp);       \
+    } else {                                                                                          \
+        if (dbits) ivfpq_scan_kernel<GG, KB2_METRIC_IP, true><<<grid, kScanThreads, smem, st>>>(sp);  \
+        else ivfpq_scan_kernel<GG, KB2_METRIC_IP, false><<<grid, kScanThreads, smem, st>>>(sp);       \
+    }
                 if (G == 1) { KB2_LAUNCH_PQ(1) } else if (G == 2) { KB2_LAUNCH_PQ(2) } else { KB2_LAUNCH_PQ(3) }
 #undef KB2_LAUNCH_PQ
             } else {

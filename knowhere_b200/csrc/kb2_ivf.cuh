@@ -59,6 +59,7 @@ struct IvfScanParams {
     int64_t npad;
     const float* t1;           // [npad] or NULL
     unsigned long long* counters;  // [0] codes scanned (optional, NULL to skip)
+    const int32_t* qperm;          // [nq] visiting order of the queries (NULL: identity)
 };
 
 // probe bookkeeping in shared memory
@@ -127,7 +128,18 @@ pq_group_sum(const uint4& w, uint32_t lane4, float& acc0, float& acc1) {
 // IVF_PQ scan.  G = M/16 groups.  grid = nq * nsplit, block = 256.
 // dynamic smem: G*65536 (LUT, first) | kScanWarps*2K*8 (candidate buffers) | probes | query
 // =====================================================================================
-template <int G, int METRIC>
+// one in-flight 32-code chunk of the software pipeline (all warp-uniform except w/t/pos/ok)
+template <int G>
+struct PqStage {
+    uint4 w[G];
+    float t;        // t1[pos]
+    float d0;       // key base of the probe this chunk belongs to
+    uint32_t pos;
+    bool ok;        // lane's position is inside the list
+    bool valid;     // stage holds a chunk (warp-uniform)
+};
+
+template <int G, int METRIC, bool HAS_BITSET>
 __global__ void __launch_bounds__(kScanThreads)
 ivfpq_scan_kernel(IvfScanParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -142,9 +154,13 @@ ivfpq_scan_kernel(IvfScanParams p) {
     float* s_q = ps.dis0 + np_max;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t q = blockIdx.x / p.nsplit;
+    // queries are visited in the order given by qperm (sorted by nearest list => CTAs that run
+    // together probe the same lists and hit them in L2)
+    const int64_t bq = blockIdx.x / p.nsplit;
+    const int64_t q = p.qperm ? (int64_t)p.qperm[bq] : bq;
     const int split = blockIdx.x % p.nsplit;
     const int j0 = min(p.nprobe, split * np_max), j1 = min(p.nprobe, j0 + np_max);
+    const int np = j1 - j0;
     if ((uint32_t)__cvta_generic_to_shared(smem_raw) != (uint32_t)KB2_SMEM_BASE) {
         // layout assumption violated: flag it, the host turns this into an error (never a silent wrong answer)
         if (threadIdx.x == 0 && p.counters) atomicExch(p.counters + 1, 0xBAD5ull);
@@ -152,7 +168,12 @@ ivfpq_scan_kernel(IvfScanParams p) {
     }
 
     for (int i = threadIdx.x; i < p.d; i += blockDim.x) s_q[i] = p.queries[q * p.d + i];
-    const int nchunks = setup_probes(p, q, j0, j1, ps);  // contains __syncthreads
+    setup_probes(p, q, j0, j1, ps);  // contains __syncthreads
+    if (p.counters && threadIdx.x == 0) {
+        unsigned long long tot = 0;
+        for (int j = 0; j < np; j++) tot += (unsigned long long)ps.len[j];
+        atomicAdd(p.counters, tot);   // codes scanned by this CTA
+    }
 
     // ---- LUT build: value(m, j) = scale * <q_m, c_pq[m][j]>, replicated at words m%16 + 16t
     {
@@ -187,56 +208,66 @@ ivfpq_scan_kernel(IvfScanParams p) {
     tk.init(lists + warp * 2 * p.K, p.K, lane);
     __syncthreads();
 
-    // ---- scan
+    // ---- scan: the warps stride the 32-code chunks of all probed lists; three chunks in flight
     const uint32_t lane4 = (uint32_t)lane << 2;
-    int cur = 0;  // probe cursor (warp-uniform, monotone)
-    unsigned long long scanned = 0;
+    // chunk iterator (warp-uniform registers; probe arrays are touched only when the probe changes)
+    int it_j = 0, it_ci = warp, it_nch = 0, it_len = 0;
+    uint32_t it_off = 0;
+    float it_d0 = 0.f;
+    auto it_load = [&]() {
+        while (it_j < np) {
+            it_len = ps.len[it_j];
+            it_nch = (it_len + 31) >> 5;
+            if (it_ci < it_nch) {
+                it_off = ps.off[it_j];
+                it_d0 = ps.dis0[it_j];
+                return;
+            }
+            it_ci -= it_nch;
+            it_j++;
+        }
+    };
+    it_load();
 
-    // software pipeline: registers for the chunk being computed and the next one
-    uint4 w_cur[G], w_nxt[G];
-    float t_cur = 0.f, t_nxt = 0.f;
-    uint32_t pos_cur = 0, pos_nxt = 0;
-    float d0_cur = 0.f, d0_nxt = 0.f;
-    bool ok_cur = false, ok_nxt = false;
-
-    auto fetch = [&](int c, uint4* w, float& t, uint32_t& pos, float& d0, bool& ok) {
-        while (c >= (int)ps.start[cur + 1]) cur++;
-        const uint32_t rel = ((uint32_t)c - ps.start[cur]) * 32u + lane;
-        pos = ps.off[cur] + rel;
-        ok = (int)rel < ps.len[cur];
-        d0 = ps.dis0[cur];
+    auto fetch = [&](PqStage<G>& st) {
+        st.valid = it_j < np;
+        if (!st.valid) return;
+        const uint32_t rel = (uint32_t)it_ci * 32u + lane;
+        st.pos = it_off + rel;
+        st.ok = (int)rel < it_len;
+        st.d0 = it_d0;
 #pragma unroll
-        for (int g = 0; g < G; g++) w[g] = ldg_stream_u4(p.codes + (int64_t)g * p.npad + pos);
-        t = (METRIC == KB2_METRIC_L2) ? __ldg(p.t1 + pos) : 0.f;
+        for (int g = 0; g < G; g++) st.w[g] = ldg_stream_u4(p.codes + (int64_t)g * p.npad + st.pos);
+        st.t = (METRIC == KB2_METRIC_L2) ? __ldg(p.t1 + st.pos) : 0.f;
+        it_ci += kScanWarps;
+        if (it_ci >= it_nch) it_load();
+    };
+    auto process = [&](const PqStage<G>& st) {
+        float acc0 = st.t, acc1 = 0.f;
+        pq_group_sum<0>(st.w[0], lane4, acc0, acc1);
+        if (G > 1) pq_group_sum<1>(st.w[G > 1 ? 1 : 0], lane4, acc0, acc1);
+        if (G > 2) pq_group_sum<2>(st.w[G > 2 ? 2 : 0], lane4, acc0, acc1);
+        const float key = st.d0 + (acc0 + acc1);
+        bool pass = st.ok && key <= tk.thr_key;          // one float compare on the hot path
+        if (HAS_BITSET && pass) pass = !bit_is_set(p.bitset, p.rows[st.pos]);
+        if (__any_sync(0xffffffffu, pass)) tk.push(pack_kp(key, st.pos), pass, lane);
     };
 
-    int c = warp;
-    if (c < nchunks) fetch(c, w_cur, t_cur, pos_cur, d0_cur, ok_cur);
-    while (c < nchunks) {
-        const int cn = c + kScanWarps;
-        if (cn < nchunks) fetch(cn, w_nxt, t_nxt, pos_nxt, d0_nxt, ok_nxt);
-
-        float acc0 = t_cur, acc1 = 0.f;
-        pq_group_sum<0>(w_cur[0], lane4, acc0, acc1);
-        if (G > 1) pq_group_sum<1>(w_cur[G > 1 ? 1 : 0], lane4, acc0, acc1);
-        if (G > 2) pq_group_sum<2>(w_cur[G > 2 ? 2 : 0], lane4, acc0, acc1);
-        const float key = d0_cur + (acc0 + acc1);
-        bool valid = ok_cur;
-        if (p.bitset && valid) valid = !bit_is_set(p.bitset, p.rows[pos_cur]);
-        scanned += ok_cur ? 1ull : 0ull;
-        tk.push(pack_kp(key, pos_cur), valid, lane);
-
-#pragma unroll
-        for (int g = 0; g < G; g++) w_cur[g] = w_nxt[g];
-        t_cur = t_nxt; pos_cur = pos_nxt; d0_cur = d0_nxt; ok_cur = ok_nxt;
-        c = cn;
+    PqStage<G> s0, s1, s2;
+    fetch(s0);
+    fetch(s1);
+    for (;;) {
+        fetch(s2);
+        if (!s0.valid) break;
+        process(s0);
+        fetch(s0);
+        if (!s1.valid) break;
+        process(s1);
+        fetch(s1);
+        if (!s2.valid) break;
+        process(s2);
     }
 
-    if (p.counters) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) scanned += __shfl_xor_sync(0xffffffffu, scanned, o);
-        if (lane == 0) atomicAdd(p.counters, scanned);
-    }
     uint64_t* out = p.partial + ((int64_t)q * p.nsplit + split) * p.kout;
     tk.finish(lane);
     block_emit_topk(lists, p.K, out, p.kout);

@@ -25,6 +25,7 @@ struct WarpTopK {
     int K;           // power of two, >= 32
     int cnt;         // entries in buf (warp-uniform)
     uint64_t thr;    // admission threshold (kEmpty until the first prune); warp-uniform
+    float thr_key;   // key part of thr (+inf until the first prune): cheap float pre-filter `key <= thr_key`
 
     __device__ __forceinline__ void
     init(uint64_t* b, int k, int lane) {
@@ -32,6 +33,7 @@ struct WarpTopK {
         K = k;
         cnt = 0;
         thr = kEmpty;
+        thr_key = INFINITY;
         (void)lane;
     }
 
@@ -55,6 +57,7 @@ struct WarpTopK {
         }
         cnt = min(cnt, K);
         thr = buf[K - 1];  // kEmpty while fewer than K candidates exist
+        thr_key = (thr == kEmpty) ? INFINITY : unpack_key(thr);
     }
 
     // all 32 lanes must call; `valid` lanes offer `cand`
