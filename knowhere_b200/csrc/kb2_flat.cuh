@@ -173,19 +173,20 @@ select_keys_kernel(const float* __restrict__ keys, int64_t ldk, int ncols, int K
 }
 
 
-// ---------------------------------------------------------------- key selection by radix select
-// Same contract as select_keys_kernel but O(slice) work: the K-th smallest key of the slice is found
-// with four 8-bit histogram passes over the order-preserving integer image of the keys held in shared
-// memory, then everything below it (plus position-ordered ties) is emitted UNSORTED — finalize /
-// reduce sort their input anyway.  Used for wide selections (IVF coarse: top-(nprobe+16) of nlist).
-// grid (nq, nsplit), dynamic smem: slice*4 + 1040 bytes.
+// ---------------------------------------------------------------- wide key selection by value histogram
+// Same contract as select_keys_kernel, for wide selections (IVF coarse: best nprobe+16 of nlist keys).
+// One pass builds a 1024-bin histogram of the order-preserving integer image of the keys between the
+// slice minimum and maximum; the largest bin prefix holding at most K_cap keys is emitted UNSORTED
+// (finalize / reduce sort their input anyway).  It always contains the K_need smallest keys: if the
+// prefix would hold fewer than K_need, the next bin is drained in (key, position) order (rare).
+// grid (nq, nsplit), block 256, dynamic smem: slice*4 + 4160 bytes.
 __global__ void __launch_bounds__(256)
-select_keys_radix_kernel(const float* __restrict__ keys, int64_t ldk, int ncols, int K, uint64_t* __restrict__ partial,
-                         int slots_per_query, int slot_base, uint32_t pos_base) {
+select_keys_hist_kernel(const float* __restrict__ keys, int64_t ldk, int ncols, int K_need, int K_cap,
+                        uint64_t* __restrict__ partial, int slots_per_query, int slot_base, uint32_t pos_base) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t* hist = (uint32_t*)smem_raw;          // 256 bins
-    uint32_t* ctl = hist + 256;                    // [0] prefix [1] remaining [2] out cursor [3] count_eq
-    uint32_t* ord = ctl + 4;                       // slice
+    uint32_t* hist = (uint32_t*)smem_raw;          // 1024 bins (+1)
+    uint32_t* ctl = hist + 1032;                   // [0] min [1] max [2] out cursor [3] bstar+1 [4] cum(bstar) [5] shift
+    uint32_t* ord = ctl + 8;                       // slice
     const int64_t q = blockIdx.x;
     const int nsplit = gridDim.y, s = blockIdx.y;
     const int per = (((ncols + nsplit - 1) / nsplit) + 31) / 32 * 32;
@@ -193,79 +194,102 @@ select_keys_radix_kernel(const float* __restrict__ keys, int64_t ldk, int ncols,
     const int c1 = min(ncols, c0 + per);
     const int n = c1 - c0;
     const float* row = keys + q * ldk + c0;
-    uint64_t* out = partial + (q * slots_per_query + slot_base + s) * (int64_t)K;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) ord[i] = f2ord(row[i]);
-    if (threadIdx.x == 0) { ctl[0] = 0; ctl[1] = (uint32_t)K; ctl[2] = 0; ctl[3] = 0; }
-    __syncthreads();
+    uint64_t* out = partial + (q * slots_per_query + slot_base + s) * (int64_t)K_cap;
     const uint32_t kInfOrd = f2ord(INFINITY);      // filtered entries: never emitted
-    if (n <= K) {
-        for (int i = threadIdx.x; i < K; i += blockDim.x)
-            out[i] = (i < n && ord[i] < kInfOrd) ? (((uint64_t)ord[i] << 32) | (pos_base + (uint32_t)(c0 + i))) : kEmpty;
+    uint32_t lmin = 0xffffffffu, lmax = 0u;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t v = f2ord(row[i]);
+        ord[i] = v;
+        if (v < kInfOrd) { lmin = min(lmin, v); lmax = max(lmax, v); }
+    }
+    for (int i = threadIdx.x; i < 1032; i += blockDim.x) hist[i] = 0;
+    if (threadIdx.x == 0) { ctl[0] = 0xffffffffu; ctl[1] = 0; ctl[2] = 0; }
+    __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+        lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(&ctl[0], lmin); atomicMax(&ctl[1], lmax); }
+    __syncthreads();
+    const uint32_t vmin = ctl[0], vmax = ctl[1];
+    if (vmin > vmax || n <= K_cap) {
+        // nothing selectable, or the whole slice fits: emit every finite key
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x)
+            if (ord[i] < kInfOrd) out[atomicAdd(&ctl[2], 1u)] = ((uint64_t)ord[i] << 32) | (pos_base + (uint32_t)(c0 + i));
+        __syncthreads();
+        for (int i = ctl[2] + threadIdx.x; i < K_cap; i += blockDim.x) out[i] = kEmpty;
         return;
     }
-    uint32_t prefix = 0, fixed_mask = 0;
-    for (int pass = 0; pass < 4; pass++) {
-        const int shift = 24 - 8 * pass;
-        hist[threadIdx.x] = 0;
-        __syncthreads();
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const uint32_t v = ord[i];
-            if ((v & fixed_mask) == prefix) atomicAdd(&hist[(v >> shift) & 255u], 1u);
-        }
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            // warp 0: find the digit where the running count reaches `remaining`
-            const uint32_t remaining = ctl[1];
-            uint32_t local[8], sum = 0;
-#pragma unroll
-            for (int t = 0; t < 8; t++) { local[t] = hist[threadIdx.x * 8 + t]; sum += local[t]; }
-            uint32_t incl = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-                if ((int)threadIdx.x >= o) incl += v;
-            }
-            const uint32_t excl = incl - sum;
-            if (excl < remaining && remaining <= incl) {   // exactly one lane
-                uint32_t run = excl;
-#pragma unroll
-                for (int t = 0; t < 8; t++) {
-                    if (run < remaining && remaining <= run + local[t]) {
-                        ctl[0] = prefix | ((uint32_t)(threadIdx.x * 8 + t) << shift);
-                        ctl[1] = remaining - run;
-                    }
-                    run += local[t];
-                }
-            }
-        }
-        __syncthreads();
-        prefix = ctl[0];
-        fixed_mask |= 0xffu << shift;
-        __syncthreads();
-    }
-    const uint32_t T = prefix;                 // exact K-th smallest key image
-    const uint32_t need_eq = ctl[1];           // how many entries equal to T belong to the selection
+    const uint32_t range = vmax - vmin;
+    const int shift = range < 1024u ? 0 : (32 - __clz(range)) - 10;
+    const int nbins = (int)(range >> shift) + 1;   // <= 1024
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const uint32_t v = ord[i];
-        if (v < T && v < kInfOrd) {
-            const uint32_t slot = atomicAdd(&ctl[2], 1u);
-            out[slot] = ((uint64_t)v << 32) | (pos_base + (uint32_t)(c0 + i));
-        } else if (v == T) {
-            atomicAdd(&ctl[3], 1u);
+        if (v < kInfOrd) atomicAdd(&hist[(v - vmin) >> shift], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        // warp 0: scan 32 bins per lane, find the largest prefix with cumulative count <= K_cap
+        const int lane = threadIdx.x;
+        uint32_t sum = 0;
+        for (int t = 0; t < 32; t++) sum += hist[lane * 32 + t];
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const uint32_t excl = incl - sum;
+        // lane owning the crossing: excl <= K_cap < incl ; if total <= K_cap no lane crosses
+        const bool crosses = excl <= (uint32_t)K_cap && incl > (uint32_t)K_cap;
+        const unsigned who = __ballot_sync(0xffffffffu, crosses);
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (who == 0 && lane == 0) { ctl[3] = (uint32_t)nbins; ctl[4] = total; }
+        if (crosses) {
+            uint32_t run = excl;
+            int b = lane * 32;
+            for (int t = 0; t < 32; t++) {
+                const uint32_t h = hist[lane * 32 + t];
+                if (run + h > (uint32_t)K_cap) { b = lane * 32 + t; break; }
+                run += h;
+            }
+            ctl[3] = (uint32_t)b;   // bins [0, b) are taken: cum = run <= K_cap
+            ctl[4] = run;
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        // ties on the K-th key: lowest positions first (deterministic); rare, so serial
-        uint32_t slot = ctl[2], left = need_eq;
-        if (T < kInfOrd) {
-            for (int i = 0; i < n && left > 0; i++)
-                if (ord[i] == T) { out[slot++] = ((uint64_t)T << 32) | (pos_base + (uint32_t)(c0 + i)); left--; }
+    const uint32_t btake = ctl[3];
+    const uint32_t taken = ctl[4];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t v = ord[i];
+        if (v < kInfOrd && ((v - vmin) >> shift) < btake)
+            out[atomicAdd(&ctl[2], 1u)] = ((uint64_t)v << 32) | (pos_base + (uint32_t)(c0 + i));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && taken < (uint32_t)K_need && btake < (uint32_t)nbins) {
+        // the crossing bin holds more keys than fit: drain it in (key, position) order until K_need is reached
+        uint32_t slot = ctl[2];
+        uint64_t last = 0;
+        bool first = true;
+        for (uint32_t need = (uint32_t)K_need - taken; need > 0; need--) {
+            uint64_t best = kEmpty;
+            for (int i = 0; i < n; i++) {
+                const uint32_t v = ord[i];
+                if (v >= kInfOrd || ((v - vmin) >> shift) != btake) continue;
+                const uint64_t c = ((uint64_t)v << 32) | (pos_base + (uint32_t)(c0 + i));
+                if ((first || c > last) && c < best) best = c;
+            }
+            if (best == kEmpty) break;
+            out[slot++] = best;
+            last = best;
+            first = false;
         }
         ctl[2] = slot;
     }
     __syncthreads();
-    for (int i = ctl[2] + threadIdx.x; i < K; i += blockDim.x) out[i] = kEmpty;
+    for (int i = ctl[2] + threadIdx.x; i < K_cap; i += blockDim.x) out[i] = kEmpty;
 }
 
 }  // namespace kb2

@@ -10,7 +10,7 @@
 //   * operands: fp32 rows, K-major.  TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) brings 128 x 32-float
 //     boxes (one 128-byte swizzle row per tensor row) of Q and X into a 3-stage shared-memory ring.
 //   * fp32 fidelity on a tf32 pipe: 4 "converter" warps split every element into hi = top 19 bits and
-//     lo = x - hi (exact), writing hi in place and lo to a twin tile; the MMA warp issues
+//     lo = x - hi (both rounded to tf32), writing hi in place and lo to a twin tile; the MMA warp issues
 //     D += hi*hi + hi*lo + lo*hi  (3 x tcgen05.mma.kind::tf32, M=128 N=128 K=8) — error ~2^-21 relative,
 //     and the k+16 best candidates are re-ranked exactly afterwards anyway (finalize_kernel).
 //   * accumulator: 128 lanes x 128 columns of TMEM (fp32); tcgen05.commit signals stage release and
@@ -117,6 +117,12 @@ make_idesc() {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
+// round-to-nearest into the 19-bit tf32 container (low 13 mantissa bits cleared)
+__device__ __forceinline__ float
+tf32_rn(float x) {
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+
 template <int METRIC>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_keys_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
@@ -212,10 +218,12 @@ gemm_keys_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             for (int i = t; i < 2 * TILE_BYTES / 16; i += CONV_THREADS) {
                 float4 v = hi[i];
                 float4 h, l;
-                h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
-                h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
-                h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
-                h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+                // hi = x rounded to tf32 (nearest), lo = (x - hi) rounded to tf32: both exactly representable,
+                // so the tensor core's own truncation of the low 13 bits changes nothing
+                h.x = tf32_rn(v.x); l.x = tf32_rn(v.x - h.x);
+                h.y = tf32_rn(v.y); l.y = tf32_rn(v.y - h.y);
+                h.z = tf32_rn(v.z); l.z = tf32_rn(v.z - h.z);
+                h.w = tf32_rn(v.w); l.w = tf32_rn(v.w - h.w);
                 hi[i] = h;
                 lo[i] = l;
             }

@@ -32,7 +32,7 @@ init_kernel_attributes() {
         set((const void*)finalize_kernel);
         set((const void*)reduce_partials_kernel);
         set((const void*)select_keys_kernel);
-        set((const void*)select_keys_radix_kernel);
+        set((const void*)select_keys_hist_kernel);
         set((const void*)ivfpq_scan_kernel<1, KB2_METRIC_L2, false>);
         set((const void*)ivfpq_scan_kernel<1, KB2_METRIC_IP, false>);
         set((const void*)ivfpq_scan_kernel<2, KB2_METRIC_L2, false>);
@@ -251,10 +251,10 @@ dense_candidates(IndexBase& ix, const float* Q, int64_t nq, const float* X, cons
         launch_gemm_keys(st, gemm_mode(), metric, Q, X + c0 * d, ix.s_qn.p, xn + c0, (int)nq, (int)cols, d, ix.s_keys.p, ldk,
                          bitset, rows, c0);
         const int per_slice = (int)(((cols + nsplit - 1) / nsplit + 31) / 32 * 32);
-        const size_t radix_smem = (size_t)per_slice * 4 + 1040;
-        if (pl.Ksel >= 64 && radix_smem <= (size_t)kMaxDynSmem) {
-            select_keys_radix_kernel<<<dim3((unsigned)nq, nsplit), 256, radix_smem, st>>>(
-                ix.s_keys.p, ldk, (int)cols, pl.Ksel, ix.s_partial.p, pl.S, pl.used, (uint32_t)c0);
+        const size_t hist_smem = (size_t)per_slice * 4 + 4160;
+        if (pl.Ksel >= 64 && hist_smem <= (size_t)kMaxDynSmem) {
+            select_keys_hist_kernel<<<dim3((unsigned)nq, nsplit), 256, hist_smem, st>>>(
+                ix.s_keys.p, ldk, (int)cols, std::min(k_need, pl.Ksel), pl.Ksel, ix.s_partial.p, pl.S, pl.used, (uint32_t)c0);
         } else {
             select_keys_kernel<<<dim3((unsigned)nq, nsplit), kScanThreads, sel_smem, st>>>(
                 ix.s_keys.p, ldk, (int)cols, pl.Ksel, pl.Ksel, ix.s_partial.p, pl.S, pl.used, (uint32_t)c0);
@@ -497,7 +497,9 @@ struct IvfIndex : IndexBase {
             for (int m = 0; m < M; m++) {
                 slice_residual_kernel<<<grid1d(nt * dsub, 256), 256, 0, stream>>>(xt, centroids.p, asg.p, nt, dim, m, dsub,
                                                                                 sub.p);
-                kmeans_train(sub.p, nt, dsub, 256, KB2_METRIC_L2, 25, 1234 + m, pqc.p + (size_t)m * 256 * dsub, stream);
+                // every sub-quantizer is seeded identically, like the reference (one ClusteringParameters, seed 1234, for all
+                // M Clustering objects: F/impl/ProductQuantizer.cpp:130-180) => the M codebooks start from the same 256 rows
+                kmeans_train(sub.p, nt, dsub, 256, KB2_METRIC_L2, 25, 1234, pqc.p + (size_t)m * 256 * dsub, stream);
             }
         }
         KB2_CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -767,7 +769,7 @@ struct IvfIndex : IndexBase {
         sp.counters = d_counter.p;
         sp.qperm = qperm;
         const size_t common_smem = (size_t)kScanWarps * 2 * Ksel * 8 + (size_t)(np_max + 1) * 4 + (size_t)np_max * 12 +
-                                   (size_t)dim * 4 + 64;
+                                   (size_t)dim * 4 + 64 + 8 * (kScanWarps + 2);
         const unsigned grid = (unsigned)(nq * nsplit);
         if (timing) KB2_CUDA_CHECK(cudaEventRecord(ev0, st));
         if (is_pq) {

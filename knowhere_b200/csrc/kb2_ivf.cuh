@@ -117,11 +117,11 @@ setup_probes(const IvfScanParams& p, int64_t q, int j0, int j1, ProbeSmem ps) {
 // 16 conflict-free gathers of one 16-sub-quantizer group: PRMT + LDS + FADD per lookup
 template <int GRP>
 __device__ __forceinline__ void
-pq_group_sum(const uint4& w, uint32_t lane4, float& acc0, float& acc1) {
-    KB2_LUT_STEP(w.x, 0, 0, acc0)  KB2_LUT_STEP(w.x, 1, 1, acc1)  KB2_LUT_STEP(w.x, 2, 2, acc0)  KB2_LUT_STEP(w.x, 3, 3, acc1)
-    KB2_LUT_STEP(w.y, 0, 4, acc0)  KB2_LUT_STEP(w.y, 1, 5, acc1)  KB2_LUT_STEP(w.y, 2, 6, acc0)  KB2_LUT_STEP(w.y, 3, 7, acc1)
-    KB2_LUT_STEP(w.z, 0, 8, acc0)  KB2_LUT_STEP(w.z, 1, 9, acc1)  KB2_LUT_STEP(w.z, 2, 10, acc0) KB2_LUT_STEP(w.z, 3, 11, acc1)
-    KB2_LUT_STEP(w.w, 0, 12, acc0) KB2_LUT_STEP(w.w, 1, 13, acc1) KB2_LUT_STEP(w.w, 2, 14, acc0) KB2_LUT_STEP(w.w, 3, 15, acc1)
+pq_group_sum(const uint4& w, uint32_t lane4, float& acc0, float& acc1, float& acc2, float& acc3) {
+    KB2_LUT_STEP(w.x, 0, 0, acc0)  KB2_LUT_STEP(w.x, 1, 1, acc1)  KB2_LUT_STEP(w.x, 2, 2, acc2)  KB2_LUT_STEP(w.x, 3, 3, acc3)
+    KB2_LUT_STEP(w.y, 0, 4, acc0)  KB2_LUT_STEP(w.y, 1, 5, acc1)  KB2_LUT_STEP(w.y, 2, 6, acc2)  KB2_LUT_STEP(w.y, 3, 7, acc3)
+    KB2_LUT_STEP(w.z, 0, 8, acc0)  KB2_LUT_STEP(w.z, 1, 9, acc1)  KB2_LUT_STEP(w.z, 2, 10, acc2) KB2_LUT_STEP(w.z, 3, 11, acc3)
+    KB2_LUT_STEP(w.w, 0, 12, acc0) KB2_LUT_STEP(w.w, 1, 13, acc1) KB2_LUT_STEP(w.w, 2, 14, acc2) KB2_LUT_STEP(w.w, 3, 15, acc3)
 }
 
 // =====================================================================================
@@ -206,6 +206,11 @@ ivfpq_scan_kernel(IvfScanParams p) {
     }
     WarpTopK tk;
     tk.init(lists + warp * 2 * p.K, p.K, lane);
+    {
+        // CTA-wide admission bound (see WarpTopK): 8-byte aligned block after the query
+        unsigned long long* shb = (unsigned long long*)(((uintptr_t)(s_q + p.d) + 7) & ~(uintptr_t)7);
+        tk.share(shb, shb + kScanWarps, kScanWarps, warp, lane);
+    }
     __syncthreads();
 
     // ---- scan: the warps stride the 32-code chunks of all probed lists; three chunks in flight
@@ -243,11 +248,12 @@ ivfpq_scan_kernel(IvfScanParams p) {
         if (it_ci >= it_nch) it_load();
     };
     auto process = [&](const PqStage<G>& st) {
-        float acc0 = st.t, acc1 = 0.f;
-        pq_group_sum<0>(st.w[0], lane4, acc0, acc1);
-        if (G > 1) pq_group_sum<1>(st.w[G > 1 ? 1 : 0], lane4, acc0, acc1);
-        if (G > 2) pq_group_sum<2>(st.w[G > 2 ? 2 : 0], lane4, acc0, acc1);
-        const float key = st.d0 + (acc0 + acc1);
+        float acc0 = st.t, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;   // four independent FADD chains
+        pq_group_sum<0>(st.w[0], lane4, acc0, acc1, acc2, acc3);
+        if (G > 1) pq_group_sum<1>(st.w[G > 1 ? 1 : 0], lane4, acc0, acc1, acc2, acc3);
+        if (G > 2) pq_group_sum<2>(st.w[G > 2 ? 2 : 0], lane4, acc0, acc1, acc2, acc3);
+        const float key = st.d0 + ((acc0 + acc1) + (acc2 + acc3));
+        tk.refresh();
         bool pass = st.ok && key <= tk.thr_key;          // one float compare on the hot path
         if (HAS_BITSET && pass) pass = !bit_is_set(p.bitset, p.rows[st.pos]);
         if (__any_sync(0xffffffffu, pass)) tk.push(pack_kp(key, st.pos), pass, lane);

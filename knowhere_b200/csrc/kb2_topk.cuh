@@ -26,6 +26,13 @@ struct WarpTopK {
     int cnt;         // entries in buf (warp-uniform)
     uint64_t thr;    // admission threshold (kEmpty until the first prune); warp-uniform
     float thr_key;   // key part of thr (+inf until the first prune): cheap float pre-filter `key <= thr_key`
+    // CTA-wide bound exchange (optional): every warp publishes its (K/nwarps)-th best after a prune;
+    // V = max over warps of those values has at least nwarps*(K/nwarps) = K distinct candidates at or
+    // below it, so it is a valid admission bound for EVERY warp and ~nwarps times tighter (in quantile)
+    // than a warp's own K-th best.  Published values only ever decrease, so stale reads stay valid.
+    unsigned long long* sh_p;   // [nwarps] shared memory, or nullptr
+    unsigned long long* sh_V;   // shared memory scalar
+    int nwarps, warp_id;
 
     __device__ __forceinline__ void
     init(uint64_t* b, int k, int lane) {
@@ -34,7 +41,33 @@ struct WarpTopK {
         cnt = 0;
         thr = kEmpty;
         thr_key = INFINITY;
+        sh_p = nullptr;
+        sh_V = nullptr;
+        nwarps = 1;
+        warp_id = 0;
         (void)lane;
+    }
+    // call before the first push; the caller zero-initialises nothing: slots start at kEmpty here
+    __device__ __forceinline__ void
+    share(unsigned long long* p, unsigned long long* V, int nw, int w, int lane) {
+        if (K / nw < 1) return;
+        sh_p = p;
+        sh_V = V;
+        nwarps = nw;
+        warp_id = w;
+        if (lane == 0) sh_p[w] = kEmpty;
+        if (w == 0 && lane == 0) *sh_V = kEmpty;
+    }
+    // adopt the CTA-wide bound if it is tighter (one LDS.64 + compare)
+    __device__ __forceinline__ void
+    refresh() {
+        if (sh_V) {
+            const unsigned long long v = *(volatile unsigned long long*)sh_V;
+            if (v < thr) {
+                thr = v;
+                thr_key = unpack_key(v);
+            }
+        }
     }
 
     // in-place ascending bitonic sort of the 2K-entry buffer by one warp (unused tail = kEmpty)
@@ -56,7 +89,22 @@ struct WarpTopK {
             }
         }
         cnt = min(cnt, K);
-        thr = buf[K - 1];  // kEmpty while fewer than K candidates exist
+        uint64_t nt = buf[K - 1];  // kEmpty while fewer than K candidates exist
+        if (sh_p) {
+            if (lane == 0) {
+                sh_p[warp_id] = buf[K / nwarps - 1];
+                unsigned long long V = 0;
+                for (int w = 0; w < nwarps; w++) {
+                    const unsigned long long pw = ((volatile unsigned long long*)sh_p)[w];
+                    V = pw > V ? pw : V;
+                }
+                atomicMin(sh_V, V);
+            }
+            __syncwarp();
+            const unsigned long long v = *(volatile unsigned long long*)sh_V;
+            nt = v < nt ? v : nt;
+        }
+        if (nt < thr) thr = nt;
         thr_key = (thr == kEmpty) ? INFINITY : unpack_key(thr);
     }
 

@@ -40,4 +40,6 @@ def test_tc_contraction_matches_fp32(kb, metric, nq, nb, d):
     err_tc = np.abs(b - exact).max() / scale
     print(f"nq={nq} nb={nb} d={d} metric={metric}: max err / scale  fp32 {err_fp32:.2e}  tc {err_tc:.2e}")
     assert not np.isnan(b).any()
-    assert err_tc < 2e-6 and err_fp32 < 2e-6
+    # fp32 FMA chain: ~1e-6; 3xTF32 (hi*hi + hi*lo + lo*hi, lo*lo dropped): a few 1e-6 at d=768.  Both far below
+    # the spacing of candidate keys, and the k+16 best candidates are re-ranked exactly (finalize_kernel).
+    assert err_tc < 6e-6 and err_fp32 < 2e-6

@@ -156,3 +156,47 @@ def test_ivf_errors(kb):
     assert e.value.status == 1          # invalid_args (dim % m)
     with pytest.raises(kb.KnowhereError):
         kb.Index("NOPE", "L2", 16)
+
+
+def test_ivf_range_search(kb, ref):
+    """IVF RangeSearch (ivf.cc:1229-1500): with every list probed and the empty-bucket heuristic off,
+    IVF_FLAT must return exactly the FLAT range result; IVF_PQ must return exactly the ids whose ADC
+    distance (as reported by Search) is inside the radius."""
+    nb, d, nlist, m = 6000, 32, 16, 8
+    xb = datagen.clustered(nb, d, 11)
+    xq = datagen.clustered(15, d, 12)
+    I, D = ref.flat_search(xb, xq, 30, 0)
+    radius = float(np.median(D[:, 20]))
+    lims0, ids0, dis0 = ref.flat_range_search(xb, xq, radius, 0)
+    ix = kb.Index("IVF_FLAT", "L2", d, {"nlist": nlist})
+    ix.build(xb)
+    lims, ids, dis = ix.range_search(xq, radius, config={"nprobe": nlist, "max_empty_result_buckets": 0})
+    assert np.array_equal(lims, lims0)
+    for i in range(len(xq)):
+        assert set(ids[lims[i]:lims[i + 1]].tolist()) == set(ids0[lims0[i]:lims0[i + 1]].tolist())
+        assert (np.diff(dis[lims[i]:lims[i + 1]]) >= 0).all()
+    # range_filter: keep range_filter <= d < radius (range_util.h:23-26)
+    rf = float(np.median(D[:, 5]))
+    lims2, ids2, dis2 = ix.range_search(xq, radius, range_filter=rf, config={"nprobe": nlist, "max_empty_result_buckets": 0})
+    assert (dis2 >= rf).all() and (dis2 < radius).all()
+    # IVF_PQ: consistency with Search on the same ADC distances
+    pq = kb.Index("IVF_PQ", "L2", d, {"nlist": nlist, "m": m})
+    pq.build(xb)
+    sI, sD = pq.search(xq, 200, {"nprobe": nlist})
+    lims3, ids3, dis3 = pq.range_search(xq, radius, config={"nprobe": nlist, "max_empty_result_buckets": 0})
+    for i in range(len(xq)):
+        want = set(sI[i][sD[i] < radius].tolist())
+        got = set(ids3[lims3[i]:lims3[i + 1]].tolist())
+        if (sD[i] < radius).sum() < 200:          # top-200 covers the whole ball
+            assert got == want
+    # IP metric: radius < d
+    xbn = xb / np.linalg.norm(xb, axis=1, keepdims=True)
+    xqn = xq / np.linalg.norm(xq, axis=1, keepdims=True)
+    fi = kb.Index("IVF_FLAT", "IP", d, {"nlist": nlist})
+    fi.build(xbn)
+    l4, i4, d4 = fi.range_search(xqn, 0.9, config={"nprobe": nlist, "max_empty_result_buckets": 0})
+    ip = xqn @ xbn.T
+    for i in range(len(xq)):
+        assert set(i4[l4[i]:l4[i + 1]].tolist()) == set(np.nonzero(ip[i] > 0.9)[0].tolist()) or \
+            abs(len(i4[l4[i]:l4[i + 1]]) - (ip[i] > 0.9).sum()) <= 1   # fp32 boundary
+        assert (np.diff(d4[l4[i]:l4[i + 1]]) <= 0).all()
