@@ -18,6 +18,12 @@ namespace kb2 {
 constexpr int kMaxK = 1024;            // largest k' any selection kernel keeps
 constexpr int kMaxSortEntries = 8192;  // finalize sorts at most this many candidates per query
 constexpr int kMaxDynSmem = 227 * 1024;
+#ifndef KB2_DEFAULT_SCAN_PREFETCH
+#define KB2_DEFAULT_SCAN_PREFETCH 1
+#endif
+#ifndef KB2_DEFAULT_SCAN_NT
+#define KB2_DEFAULT_SCAN_NT 256
+#endif
 #ifndef KB2_DEFAULT_GEMM_MODE
 #define KB2_DEFAULT_GEMM_MODE 0
 #endif
@@ -33,18 +39,30 @@ init_kernel_attributes() {
         set((const void*)reduce_partials_kernel);
         set((const void*)select_keys_kernel);
         set((const void*)select_keys_hist_kernel);
-        set((const void*)ivfpq_scan_kernel<1, KB2_METRIC_L2, false>);
-        set((const void*)ivfpq_scan_kernel<1, KB2_METRIC_IP, false>);
-        set((const void*)ivfpq_scan_kernel<2, KB2_METRIC_L2, false>);
-        set((const void*)ivfpq_scan_kernel<2, KB2_METRIC_IP, false>);
-        set((const void*)ivfpq_scan_kernel<3, KB2_METRIC_L2, false>);
-        set((const void*)ivfpq_scan_kernel<3, KB2_METRIC_IP, false>);
-        set((const void*)ivfpq_scan_kernel<1, KB2_METRIC_L2, true>);
-        set((const void*)ivfpq_scan_kernel<1, KB2_METRIC_IP, true>);
-        set((const void*)ivfpq_scan_kernel<2, KB2_METRIC_L2, true>);
-        set((const void*)ivfpq_scan_kernel<2, KB2_METRIC_IP, true>);
-        set((const void*)ivfpq_scan_kernel<3, KB2_METRIC_L2, true>);
-        set((const void*)ivfpq_scan_kernel<3, KB2_METRIC_IP, true>);
+        set((const void*)ivfpq_scan_kernel<1, KB2_METRIC_L2, false, 256>);
+        set((const void*)ivfpq_scan_kernel<1, KB2_METRIC_L2, true, 256>);
+        set((const void*)ivfpq_scan_kernel<1, KB2_METRIC_IP, false, 256>);
+        set((const void*)ivfpq_scan_kernel<1, KB2_METRIC_IP, true, 256>);
+        set((const void*)ivfpq_scan_kernel<2, KB2_METRIC_L2, false, 256>);
+        set((const void*)ivfpq_scan_kernel<2, KB2_METRIC_L2, true, 256>);
+        set((const void*)ivfpq_scan_kernel<2, KB2_METRIC_IP, false, 256>);
+        set((const void*)ivfpq_scan_kernel<2, KB2_METRIC_IP, true, 256>);
+        set((const void*)ivfpq_scan_kernel<3, KB2_METRIC_L2, false, 256>);
+        set((const void*)ivfpq_scan_kernel<3, KB2_METRIC_L2, true, 256>);
+        set((const void*)ivfpq_scan_kernel<3, KB2_METRIC_IP, false, 256>);
+        set((const void*)ivfpq_scan_kernel<3, KB2_METRIC_IP, true, 256>);
+        set((const void*)ivfpq_scan_kernel<1, KB2_METRIC_L2, false, 512>);
+        set((const void*)ivfpq_scan_kernel<1, KB2_METRIC_L2, true, 512>);
+        set((const void*)ivfpq_scan_kernel<1, KB2_METRIC_IP, false, 512>);
+        set((const void*)ivfpq_scan_kernel<1, KB2_METRIC_IP, true, 512>);
+        set((const void*)ivfpq_scan_kernel<2, KB2_METRIC_L2, false, 512>);
+        set((const void*)ivfpq_scan_kernel<2, KB2_METRIC_L2, true, 512>);
+        set((const void*)ivfpq_scan_kernel<2, KB2_METRIC_IP, false, 512>);
+        set((const void*)ivfpq_scan_kernel<2, KB2_METRIC_IP, true, 512>);
+        set((const void*)ivfpq_scan_kernel<3, KB2_METRIC_L2, false, 512>);
+        set((const void*)ivfpq_scan_kernel<3, KB2_METRIC_L2, true, 512>);
+        set((const void*)ivfpq_scan_kernel<3, KB2_METRIC_IP, false, 512>);
+        set((const void*)ivfpq_scan_kernel<3, KB2_METRIC_IP, true, 512>);
         set((const void*)ivfpq_scan_generic_kernel<KB2_METRIC_L2>);
         set((const void*)ivfpq_scan_generic_kernel<KB2_METRIC_IP>);
         set((const void*)ivfflat_scan_kernel<KB2_METRIC_L2>);
@@ -774,18 +792,29 @@ struct IvfIndex : IndexBase {
         if (timing) KB2_CUDA_CHECK(cudaEventRecord(ev0, st));
         if (is_pq) {
             if (G > 0) {
-                const size_t smem = (size_t)G * 65536 + common_smem;
+                const int scan_nt_env = [] { const char* e = getenv("KB2_SCAN_NT"); return e ? atoi(e) : 0; }();
+                int scan_nt = (scan_nt_env == 256 || scan_nt_env == 512) ? scan_nt_env : KB2_DEFAULT_SCAN_NT;
+                size_t smem = (size_t)G * 65536 + common_smem;
+                if (scan_nt == 512) {
+                    const size_t smem512 = smem + (size_t)kScanWarps * 2 * Ksel * 8 + 8 * kScanWarps;  // 16 warp buffers
+                    if (smem512 <= (size_t)kMaxDynSmem) smem = smem512; else scan_nt = 256;
+                }
                 KB2_REQUIRE(smem <= (size_t)kMaxDynSmem, KB2_INVALID_ARGS, "IVF_PQ: k too large for shared memory");
-#define KB2_LAUNCH_PQ(GG)                                                                             \
-    if (metric == KB2_METRIC_L2) {                                                                    \
-        if (dbits) ivfpq_scan_kernel<GG, KB2_METRIC_L2, true><<<grid, kScanThreads, smem, st>>>(sp);  \
-        else ivfpq_scan_kernel<GG, KB2_METRIC_L2, false><<<grid, kScanThreads, smem, st>>>(sp);       \
-    } else {                                                                                          \
-        if (dbits) ivfpq_scan_kernel<GG, KB2_METRIC_IP, true><<<grid, kScanThreads, smem, st>>>(sp);  \
-        else ivfpq_scan_kernel<GG, KB2_METRIC_IP, false><<<grid, kScanThreads, smem, st>>>(sp);       \
+#define KB2_LAUNCH_PQ_NT(GG, NTT)                                                                              \
+    if (metric == KB2_METRIC_L2) {                                                                             \
+        if (dbits) ivfpq_scan_kernel<GG, KB2_METRIC_L2, true, NTT><<<grid, NTT, smem, st>>>(sp);               \
+        else ivfpq_scan_kernel<GG, KB2_METRIC_L2, false, NTT><<<grid, NTT, smem, st>>>(sp);                    \
+    } else {                                                                                                   \
+        if (dbits) ivfpq_scan_kernel<GG, KB2_METRIC_IP, true, NTT><<<grid, NTT, smem, st>>>(sp);               \
+        else ivfpq_scan_kernel<GG, KB2_METRIC_IP, false, NTT><<<grid, NTT, smem, st>>>(sp);                    \
     }
+#define KB2_LAUNCH_PQ(GG)                                     \
+    if (scan_nt == 512) { KB2_LAUNCH_PQ_NT(GG, 512) } else { KB2_LAUNCH_PQ_NT(GG, 256) }
+                const char* e_pf = getenv("KB2_SCAN_PREFETCH");
+                sp.flags = (e_pf ? atoi(e_pf) : KB2_DEFAULT_SCAN_PREFETCH) ? 2 : 0;
                 if (G == 1) { KB2_LAUNCH_PQ(1) } else if (G == 2) { KB2_LAUNCH_PQ(2) } else { KB2_LAUNCH_PQ(3) }
 #undef KB2_LAUNCH_PQ
+#undef KB2_LAUNCH_PQ_NT
             } else {
                 const size_t smem = (size_t)M * 1024 + common_smem;
                 KB2_REQUIRE(smem <= (size_t)kMaxDynSmem, KB2_NOT_IMPLEMENTED, "IVF_PQ: m too large for the generic kernel");

@@ -60,6 +60,7 @@ struct IvfScanParams {
     const float* t1;           // [npad] or NULL
     unsigned long long* counters;  // [0] codes scanned (optional, NULL to skip)
     const int32_t* qperm;          // [nq] visiting order of the queries (NULL: identity)
+    int flags;                     // bit1: software L2 prefetch of upcoming chunks (A/B switch)
 };
 
 // probe bookkeeping in shared memory
@@ -139,15 +140,16 @@ struct PqStage {
     bool valid;     // stage holds a chunk (warp-uniform)
 };
 
-template <int G, int METRIC, bool HAS_BITSET>
-__global__ void __launch_bounds__(kScanThreads)
+template <int G, int METRIC, bool HAS_BITSET, int NT, int NACC = 2>
+__global__ void __launch_bounds__(NT, G == 1 ? (NT == 512 ? 2 : 3) : 1)
 ivfpq_scan_kernel(IvfScanParams p) {
+    constexpr int NW = NT / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char* lut = smem_raw;
     uint64_t* lists = (uint64_t*)(smem_raw + (size_t)G * 65536);
     const int np_max = (p.nprobe + p.nsplit - 1) / p.nsplit;
     ProbeSmem ps;
-    ps.start = (uint32_t*)(lists + kScanWarps * 2 * p.K);
+    ps.start = (uint32_t*)(lists + NW * 2 * p.K);
     ps.off = ps.start + np_max + 1;
     ps.len = (int32_t*)(ps.off + np_max);
     ps.dis0 = (float*)(ps.len + np_max);
@@ -209,7 +211,7 @@ ivfpq_scan_kernel(IvfScanParams p) {
     {
         // CTA-wide admission bound (see WarpTopK): 8-byte aligned block after the query
         unsigned long long* shb = (unsigned long long*)(((uintptr_t)(s_q + p.d) + 7) & ~(uintptr_t)7);
-        tk.share(shb, shb + kScanWarps, kScanWarps, warp, lane);
+        tk.share(shb, shb + NW, NW, warp, lane);
     }
     __syncthreads();
 
@@ -242,19 +244,39 @@ ivfpq_scan_kernel(IvfScanParams p) {
         st.ok = (int)rel < it_len;
         st.d0 = it_d0;
 #pragma unroll
-        for (int g = 0; g < G; g++) st.w[g] = ldg_stream_u4(p.codes + (int64_t)g * p.npad + st.pos);
-        st.t = (METRIC == KB2_METRIC_L2) ? __ldg(p.t1 + st.pos) : 0.f;
-        it_ci += kScanWarps;
+        for (int g = 0; g < G; g++) {
+            const uint4* cp = p.codes + (int64_t)g * p.npad + st.pos;
+            st.w[g] = ldg_stream_u4(cp);
+            // pull the chunk this warp will want four iterations from now into L2 (same list most of the
+            // time; a stray prefetch into the next list or the tail padding is harmless)
+            if (p.flags & 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + 4 * NW * 32));
+        }
+        if (METRIC == KB2_METRIC_L2) {
+            st.t = __ldg(p.t1 + st.pos);
+            if ((p.flags & 2) && lane == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.t1 + st.pos + 4 * NW * 32));
+        } else {
+            st.t = 0.f;
+        }
+        it_ci += NW;
         if (it_ci >= it_nch) it_load();
     };
     auto process = [&](const PqStage<G>& st) {
-        float acc0 = st.t, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;   // four independent FADD chains
-        pq_group_sum<0>(st.w[0], lane4, acc0, acc1, acc2, acc3);
-        if (G > 1) pq_group_sum<1>(st.w[G > 1 ? 1 : 0], lane4, acc0, acc1, acc2, acc3);
-        if (G > 2) pq_group_sum<2>(st.w[G > 2 ? 2 : 0], lane4, acc0, acc1, acc2, acc3);
-        const float key = st.d0 + ((acc0 + acc1) + (acc2 + acc3));
-        tk.refresh();
-        bool pass = st.ok && key <= tk.thr_key;          // one float compare on the hot path
+        float key;
+        if (NACC == 4) {
+            float acc0 = st.t, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;   // four independent FADD chains
+            pq_group_sum<0>(st.w[0], lane4, acc0, acc1, acc2, acc3);
+            if (G > 1) pq_group_sum<1>(st.w[G > 1 ? 1 : 0], lane4, acc0, acc1, acc2, acc3);
+            if (G > 2) pq_group_sum<2>(st.w[G > 2 ? 2 : 0], lane4, acc0, acc1, acc2, acc3);
+            key = st.d0 + ((acc0 + acc1) + (acc2 + acc3));
+        } else {
+            float acc0 = st.t, acc1 = 0.f;                           // two chains
+            pq_group_sum<0>(st.w[0], lane4, acc0, acc1, acc0, acc1);
+            if (G > 1) pq_group_sum<1>(st.w[G > 1 ? 1 : 0], lane4, acc0, acc1, acc0, acc1);
+            if (G > 2) pq_group_sum<2>(st.w[G > 2 ? 2 : 0], lane4, acc0, acc1, acc0, acc1);
+            key = st.d0 + (acc0 + acc1);
+        }
+        // hot path: one shared load + min + compare; the exact (key,pos) test happens inside push()
+        bool pass = st.ok && key <= fminf(tk.thr_key, tk.shared_key());
         if (HAS_BITSET && pass) pass = !bit_is_set(p.bitset, p.rows[st.pos]);
         if (__any_sync(0xffffffffu, pass)) tk.push(pack_kp(key, st.pos), pass, lane);
     };
@@ -276,7 +298,7 @@ ivfpq_scan_kernel(IvfScanParams p) {
 
     uint64_t* out = p.partial + ((int64_t)q * p.nsplit + split) * p.kout;
     tk.finish(lane);
-    block_emit_topk(lists, p.K, out, p.kout);
+    block_emit_topk(lists, p.K, out, p.kout, NW);
 }
 
 // =====================================================================================

@@ -32,6 +32,8 @@ struct WarpTopK {
     // than a warp's own K-th best.  Published values only ever decrease, so stale reads stay valid.
     unsigned long long* sh_p;   // [nwarps] shared memory, or nullptr
     unsigned long long* sh_V;   // shared memory scalar
+    float* sh_Vkey;             // key part of *sh_V (hot-path pre-filter reads only this)
+    uint32_t sh_Vkey_addr;      // its shared-window address
     int nwarps, warp_id;
 
     __device__ __forceinline__ void
@@ -43,6 +45,7 @@ struct WarpTopK {
         thr_key = INFINITY;
         sh_p = nullptr;
         sh_V = nullptr;
+        sh_Vkey = nullptr;
         nwarps = 1;
         warp_id = 0;
         (void)lane;
@@ -53,16 +56,27 @@ struct WarpTopK {
         if (K / nw < 1) return;
         sh_p = p;
         sh_V = V;
+        sh_Vkey = reinterpret_cast<float*>(V + 1);
+        sh_Vkey_addr = (uint32_t)__cvta_generic_to_shared(sh_Vkey);
         nwarps = nw;
         warp_id = w;
         if (lane == 0) sh_p[w] = kEmpty;
-        if (w == 0 && lane == 0) *sh_V = kEmpty;
+        if (w == 0 && lane == 0) { *sh_V = kEmpty; *sh_Vkey = INFINITY; }
+    }
+    // hot path: pre-filter key of the CTA-wide bound (one LDS; thr_key = min(own, shared) by the caller)
+    // (requires share(); explicit shared-space load — a volatile generic load would compile to LD.E.STRONG.SYS)
+    __device__ __forceinline__ float
+    shared_key() const {
+        float v;
+        asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(v) : "r"(sh_Vkey_addr));
+        return v;
     }
     // adopt the CTA-wide bound if it is tighter (one LDS.64 + compare)
     __device__ __forceinline__ void
     refresh() {
         if (sh_V) {
-            const unsigned long long v = *(volatile unsigned long long*)sh_V;
+            unsigned long long v;
+            asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"((uint32_t)__cvta_generic_to_shared(sh_V)));
             if (v < thr) {
                 thr = v;
                 thr_key = unpack_key(v);
@@ -98,7 +112,9 @@ struct WarpTopK {
                     const unsigned long long pw = ((volatile unsigned long long*)sh_p)[w];
                     V = pw > V ? pw : V;
                 }
-                atomicMin(sh_V, V);
+                const unsigned long long old = atomicMin(sh_V, V);
+                if (V < old) *(volatile float*)sh_Vkey = unpack_key(V);   // racy but monotone enough: any published
+                                                                          // key belongs to a valid bound
             }
             __syncwarp();
             const unsigned long long v = *(volatile unsigned long long*)sh_V;
@@ -111,6 +127,7 @@ struct WarpTopK {
     // all 32 lanes must call; `valid` lanes offer `cand`
     __device__ __forceinline__ void
     push(uint64_t cand, bool valid, int lane) {
+        refresh();
         bool pass = valid && cand < thr;
         unsigned m = __ballot_sync(0xffffffffu, pass);
         if (m == 0) return;
@@ -157,9 +174,9 @@ block_bitonic_sort(uint64_t* s, int n) {
 // After every warp called WarpTopK::finish(): the kScanWarps buffers (2K entries each, contiguous in
 // `lists`) are sorted CTA-wide and the best `kout` written to out[0..kout).
 __device__ __forceinline__ void
-block_emit_topk(uint64_t* lists, int K, uint64_t* __restrict__ out, int kout) {
+block_emit_topk(uint64_t* lists, int K, uint64_t* __restrict__ out, int kout, int nwarps = kScanWarps) {
     __syncthreads();
-    block_bitonic_sort(lists, kScanWarps * 2 * K);
+    block_bitonic_sort(lists, nwarps * 2 * K);
     for (int i = threadIdx.x; i < kout; i += blockDim.x) out[i] = lists[i];
 }
 
