@@ -91,7 +91,8 @@ class ClockSampler:
 
 
 def ground_truth(kb, torch, xb, xq_sub, k, metric):
-    ids, _ = kb.brute_force_search(xb, xq_sub, k, metric, stream=torch.cuda.current_stream().cuda_stream)
+    ids, _ = kb.brute_force_search(xb, xq_sub, k, metric, device=xb.device.index or 0,
+                                   stream=torch.cuda.current_stream().cuda_stream)
     return ids.cpu().numpy()
 
 
@@ -106,7 +107,8 @@ def build_index(kb, torch, dist, wl, xb, rank, world, stream):
     """GPU build; for world>1 rank 0 trains and broadcasts centroids/codebooks so that every rank
     encodes against the same quantizers, then each rank keeps the lists l % world == rank."""
     d = wl["d"]
-    ix = kb.Index(wl["index"], wl["metric"], d, wl["build"])
+    dev_i = xb.device.index or 0
+    ix = kb.Index(wl["index"], wl["metric"], d, wl["build"], device=dev_i)
     ix.set_stream(stream)
     m = wl["build"].get("m", 0)
     if world == 1:
@@ -117,7 +119,7 @@ def build_index(kb, torch, dist, wl, xb, rank, world, stream):
         cent = torch.empty((nlist, d), dtype=torch.float32, device=xb.device)
         pq = torch.empty((max(m, 1), 256, d // max(m, 1)), dtype=torch.float32, device=xb.device)
         if rank == 0:
-            t = kb.Index(wl["index"], wl["metric"], d, wl["build"])
+            t = kb.Index(wl["index"], wl["metric"], d, wl["build"], device=dev_i)
             t.set_stream(stream)
             t.train(xb)
             c_h, pq_h = t.ivf_export_centroids(m)
@@ -230,6 +232,21 @@ def run_ours(args):
         ms_total = float(t.item())
     ctr = ix.last_counters()
     ix.enable_kernel_timing(False)
+    breakdown = None
+    if world > 1:
+        # where the N>1 step goes: local search vs all-gather + merge (device events, this rank)
+        ea, eb, ec = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        ts, tm = [], []
+        for _ in range(5):
+            ea.record()
+            ix.search(xq, k, cfg, out=(ids, dis))
+            eb.record()
+            sharding.gather_and_merge(torch, dist, ids, dis, merge_fn, world)
+            ec.record()
+            torch.cuda.synchronize()
+            ts.append(ea.elapsed_time(eb))
+            tm.append(eb.elapsed_time(ec))
+        breakdown = {"local_search_ms": statistics.median(ts), "allgather_merge_ms": statistics.median(tm)}
 
     # ---- end to end: pinned host queries in, host results out, through the same public call
     xq_h = torch.empty((nq, d), dtype=torch.float32).pin_memory()
@@ -299,6 +316,7 @@ def run_ours(args):
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": nq * d * 4,
                 "d2h_bytes_per_step": nq * k * 12, "results_equal_device_path": e2e_ok},
         "gpu_launches": launches,
+        "multi_gpu_breakdown": breakdown,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "ivfpq_scan_kernel" if wl["index"] == "IVF_PQ" else "ivfflat_scan_kernel",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -1,6 +1,7 @@
 // kb2_capi.cu — the extern "C" boundary declared in include/knowhere_b200.h.
 // Everything behind it is CUDA; there is no CPU fallback: without a usable sm_100 device every
 // entry point fails with KB2_CUDA_RUNTIME_ERROR.
+#include <atomic>
 #include <cstring>
 #include <memory>
 
@@ -52,6 +53,12 @@ usable_devices() {
 
 void
 require_device(int device) {
+    // validated devices are cached: cudaGetDeviceProperties costs milliseconds and this sits on per-call paths
+    static std::atomic<uint64_t> ok_mask{0};
+    if (device >= 0 && device < 64 && (ok_mask.load(std::memory_order_relaxed) >> device) & 1) {
+        KB2_CUDA_CHECK(cudaSetDevice(device));
+        return;
+    }
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n <= 0) {
@@ -64,6 +71,7 @@ require_device(int device) {
     KB2_REQUIRE(p.major == 10, KB2_CUDA_RUNTIME_ERROR,
                 "device is not sm_100 (this library ships sm_100a SASS only)");
     KB2_CUDA_CHECK(cudaSetDevice(device));
+    if (device < 64) ok_mask.fetch_or(1ull << device, std::memory_order_relaxed);
 }
 
 struct Handle {

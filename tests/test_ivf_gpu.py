@@ -200,3 +200,48 @@ def test_ivf_range_search(kb, ref):
         assert set(i4[l4[i]:l4[i + 1]].tolist()) == set(np.nonzero(ip[i] > 0.9)[0].tolist()) or \
             abs(len(i4[l4[i]:l4[i + 1]]) - (ip[i] > 0.9).sum()) <= 1   # fp32 boundary
         assert (np.diff(d4[l4[i]:l4[i + 1]]) <= 0).all()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_ivf_list_sharding_single_gpu(kb, world):
+    """kb2_index_set_shard + kb2_merge_topk on ONE GPU: `world` shard handles (lists l % world == rank) built
+    from the same quantizers; the merge of their local top-k must equal the unsharded search."""
+    nb, d, nlist, m, nq, k = 30000, 64, 64, 16, 400, 10
+    xb = datagen.clustered(nb, d, 42)
+    xq = datagen.clustered(nq, d, 43)
+    cfgb = {"nlist": nlist, "m": m, "refine": True, "refine_type": "flat"}
+    full = kb.Index("IVF_PQ", "L2", d, cfgb)
+    full.build(xb)
+    cent, pq = full.ivf_export_centroids(m)
+    # (a) pure ADC search: local top-k by ADC merged == global top-k by ADC, exactly
+    # (b) with refine each shard refines its own k*refine_k candidates, so the merged result considers a
+    #     superset of the unsharded candidates: it can only be better (pointwise smaller-or-equal distances)
+    cfg_adc, cfg_ref = {"nprobe": 16, "refine_k": 1}, {"nprobe": 16, "refine_k": 4}
+    full_adc = kb.Index("IVF_PQ", "L2", d, {"nlist": nlist, "m": m})
+    kb._check(kb.lib().kb2_ivf_import_begin(full_adc.h, nlist, cent.ctypes.data, pq.ctypes.data))
+    full_adc.add(xb)
+    I0, D0 = full_adc.search(xq, k, cfg_adc)
+    I1, D1 = full.search(xq, k, cfg_ref)
+    adc_ids, adc_dis, ref_ids, ref_dis, sizes = [], [], [], [], 0
+    for rank in range(world):
+        sh = kb.Index("IVF_PQ", "L2", d, cfgb)
+        sh.set_shard(rank, world)
+        kb._check(kb.lib().kb2_ivf_import_begin(sh.h, nlist, cent.ctypes.data, pq.ctypes.data))
+        sh.add(xb)
+        for l in range(nlist):
+            n_l = kb.lib().kb2_ivf_list_size(sh.h, l)
+            assert (n_l == kb.lib().kb2_ivf_list_size(full.h, l)) if l % world == rank else n_l == 0
+            sizes += n_l
+        a = sh.search(xq, k, cfg_ref)
+        ref_ids.append(a[0]); ref_dis.append(a[1])
+        sh2 = kb.Index("IVF_PQ", "L2", d, {"nlist": nlist, "m": m})
+        sh2.set_shard(rank, world)
+        kb._check(kb.lib().kb2_ivf_import_begin(sh2.h, nlist, cent.ctypes.data, pq.ctypes.data))
+        sh2.add(xb)
+        b = sh2.search(xq, k, cfg_adc)
+        adc_ids.append(b[0]); adc_dis.append(b[1])
+    assert sizes == nb
+    mi, md = kb.merge_topk(np.stack(adc_ids), np.stack(adc_dis), "L2")
+    assert_topk_parity(mi, md, I0, D0, rtol=1e-6, atol=1e-6, what="sharded ADC merge", max_tie_rows=nq // 10)
+    mi, md = kb.merge_topk(np.stack(ref_ids), np.stack(ref_dis), "L2")
+    assert (md <= D1 * (1 + 1e-6)).all()
