@@ -148,6 +148,7 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
     wl = WORKLOADS[args.workload]
     n, d, nq, k = wl["n"], wl["d"], wl["nq"], wl["k"]

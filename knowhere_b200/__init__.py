@@ -27,11 +27,12 @@ class KnowhereError(RuntimeError):
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB):
+        path = os.environ.get("KB2_LIB", LIB)   # development aid: A/B two builds on the same box
+        if not os.path.exists(path):
             raise ImportError(
                 f"{LIB} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(there is no CPU fallback)")
-        _lib = ctypes.CDLL(LIB)
+        _lib = ctypes.CDLL(path)
         _declare(_lib)
     return _lib
 

@@ -25,7 +25,7 @@ constexpr int kMaxDynSmem = 227 * 1024;
 #define KB2_DEFAULT_SCAN_NT 256
 #endif
 #ifndef KB2_DEFAULT_GEMM_MODE
-#define KB2_DEFAULT_GEMM_MODE 0
+#define KB2_DEFAULT_GEMM_MODE 1
 #endif
 
 inline void

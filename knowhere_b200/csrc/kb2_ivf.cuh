@@ -127,7 +127,7 @@ pq_group_sum(const uint4& w, uint32_t lane4, float& acc0, float& acc1, float& ac
 
 // =====================================================================================
 // IVF_PQ scan.  G = M/16 groups.  grid = nq * nsplit, block = 256.
-// dynamic smem: G*65536 (LUT, first) | kScanWarps*2K*8 (candidate buffers) | probes | query
+// dynamic smem: G*65536 (LUT, first) | NW*2K*8 (candidate buffers) | probes | query | CTA bound block
 // =====================================================================================
 // one in-flight 32-code chunk of the software pipeline (all warp-uniform except w/t/pos/ok)
 template <int G>
@@ -177,16 +177,44 @@ ivfpq_scan_kernel(IvfScanParams p) {
         atomicAdd(p.counters, tot);   // codes scanned by this CTA
     }
 
-    // ---- LUT build: value(m, j) = scale * <q_m, c_pq[m][j]>, replicated at words m%16 + 16t
+    // ---- LUT build: value(m, j) = scale * <q_m, c_pq[m][j]>, replicated at words m%16 + 16t.
+    // Thread mapping chosen for conflict-free stores: within a warp, lanes 0-15 take the 16 sub-quantizers of
+    // code value j, lanes 16-31 those of j+1 (same banks, one row = 64 words later), so the two half-warps
+    // write DIFFERENT replicas in each of the four store steps (banks m+16r vs m+16(r^1)).
     {
         const float scale = (METRIC == KB2_METRIC_L2) ? -2.f : -1.f;
         const int dsub = p.dsub;
+        const int half = lane >> 4;
+        const int mm = threadIdx.x & 15;   // blockDim % 16 == 0: a thread keeps its sub-quantizer-in-group
+        float qr[8];                       // its query sub-vector in registers when dsub <= 8 (no smem re-reads)
+        int g_loaded = -1;
         for (int e = threadIdx.x; e < p.M * 256; e += blockDim.x) {
-            const int m = e >> 8, j = e & 255;
-            const float* c = p.pq_centroids + (int64_t)e * dsub;
+            // e enumerates (group g, code value j, sub-quantizer-in-group mm): mm fastest, then j
+            const int j = (e >> 4) & 255;
+            const int g = e >> 12;
+            const int m = g * 16 + mm;
+            const float* c = p.pq_centroids + ((int64_t)m * 256 + j) * dsub;
             const float* qs = s_q + m * dsub;
             float acc = 0.f;
-            if ((dsub & 3) == 0) {
+            if (dsub <= 8) {
+                if (g != g_loaded) {
+#pragma unroll
+                    for (int t = 0; t < 8; t++) qr[t] = t < dsub ? qs[t] : 0.f;
+                    g_loaded = g;
+                }
+                if (dsub == 8) {
+                    const float4 c0 = *reinterpret_cast<const float4*>(c);
+                    const float4 c1 = *reinterpret_cast<const float4*>(c + 4);
+                    acc = fmaf(qr[0], c0.x, acc); acc = fmaf(qr[1], c0.y, acc);
+                    acc = fmaf(qr[2], c0.z, acc); acc = fmaf(qr[3], c0.w, acc);
+                    acc = fmaf(qr[4], c1.x, acc); acc = fmaf(qr[5], c1.y, acc);
+                    acc = fmaf(qr[6], c1.z, acc); acc = fmaf(qr[7], c1.w, acc);
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 8; t++)
+                        if (t < dsub) acc = fmaf(qr[t], c[t], acc);
+                }
+            } else if ((dsub & 3) == 0) {
                 for (int t = 0; t < dsub; t += 4) {
                     const float4 cv = *reinterpret_cast<const float4*>(c + t);
                     acc = fmaf(qs[t], cv.x, acc);
@@ -198,12 +226,9 @@ ivfpq_scan_kernel(IvfScanParams p) {
                 for (int t = 0; t < dsub; t++) acc = fmaf(qs[t], c[t], acc);
             }
             acc *= scale;
-            float* row = (float*)(lut + (size_t)(m >> 4) * 65536 + (size_t)j * 256);
-            const int w = m & 15;
-            row[w] = acc;
-            row[w + 16] = acc;
-            row[w + 32] = acc;
-            row[w + 48] = acc;
+            float* row = (float*)(lut + (size_t)g * 65536 + (size_t)j * 256);
+#pragma unroll
+            for (int r = 0; r < 4; r++) row[mm + 16 * (r ^ half)] = acc;
         }
     }
     WarpTopK tk;
@@ -238,6 +263,7 @@ ivfpq_scan_kernel(IvfScanParams p) {
 
     auto fetch = [&](PqStage<G>& st) {
         st.valid = it_j < np;
+        st.ok = false;
         if (!st.valid) return;
         const uint32_t rel = (uint32_t)it_ci * 32u + lane;
         st.pos = it_off + rel;
@@ -260,40 +286,51 @@ ivfpq_scan_kernel(IvfScanParams p) {
         it_ci += NW;
         if (it_ci >= it_nch) it_load();
     };
-    auto process = [&](const PqStage<G>& st) {
-        float key;
+    auto adc_key = [&](const PqStage<G>& st) -> float {
         if (NACC == 4) {
-            float acc0 = st.t, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;   // four independent FADD chains
+            float acc0 = st.t, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
             pq_group_sum<0>(st.w[0], lane4, acc0, acc1, acc2, acc3);
             if (G > 1) pq_group_sum<1>(st.w[G > 1 ? 1 : 0], lane4, acc0, acc1, acc2, acc3);
             if (G > 2) pq_group_sum<2>(st.w[G > 2 ? 2 : 0], lane4, acc0, acc1, acc2, acc3);
-            key = st.d0 + ((acc0 + acc1) + (acc2 + acc3));
+            return st.d0 + ((acc0 + acc1) + (acc2 + acc3));
         } else {
-            float acc0 = st.t, acc1 = 0.f;                           // two chains
+            float acc0 = st.t, acc1 = 0.f;
             pq_group_sum<0>(st.w[0], lane4, acc0, acc1, acc0, acc1);
             if (G > 1) pq_group_sum<1>(st.w[G > 1 ? 1 : 0], lane4, acc0, acc1, acc0, acc1);
             if (G > 2) pq_group_sum<2>(st.w[G > 2 ? 2 : 0], lane4, acc0, acc1, acc0, acc1);
-            key = st.d0 + (acc0 + acc1);
+            return st.d0 + (acc0 + acc1);
         }
-        // hot path: one shared load + min + compare; the exact (key,pos) test happens inside push()
-        bool pass = st.ok && key <= fminf(tk.thr_key, tk.shared_key());
+    };
+    auto admit = [&](const PqStage<G>& st, float key, float bound) {
+        bool pass = st.ok && key <= bound;            // one float compare on the hot path
         if (HAS_BITSET && pass) pass = !bit_is_set(p.bitset, p.rows[st.pos]);
         if (__any_sync(0xffffffffu, pass)) tk.push(pack_kp(key, st.pos), pass, lane);
     };
+    // two chunks are evaluated together: 2 x 16 independent PRMT/LDS/FADD chains per warp hide the
+    // shared-memory and ALU latencies that 24 resident warps alone cannot
+    auto process2 = [&](const PqStage<G>& a, const PqStage<G>& b) {
+        const float ka = adc_key(a);
+        const float kb = b.valid ? adc_key(b) : 0.f;
+        // hot path: one shared load + min; the exact (key,pos) test happens inside push()
+        const float bound = fminf(tk.thr_key, tk.shared_key());
+        admit(a, ka, bound);
+        if (b.valid) admit(b, kb, fminf(tk.thr_key, bound));
+    };
 
-    PqStage<G> s0, s1, s2;
+    PqStage<G> s0, s1, s2, s3;
     fetch(s0);
     fetch(s1);
+    fetch(s2);
+    fetch(s3);
     for (;;) {
-        fetch(s2);
         if (!s0.valid) break;
-        process(s0);
+        process2(s0, s1);
         fetch(s0);
-        if (!s1.valid) break;
-        process(s1);
         fetch(s1);
         if (!s2.valid) break;
-        process(s2);
+        process2(s2, s3);
+        fetch(s2);
+        fetch(s3);
     }
 
     uint64_t* out = p.partial + ((int64_t)q * p.nsplit + split) * p.kout;

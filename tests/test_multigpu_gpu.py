@@ -27,6 +27,7 @@ full.build(xb)                                   # each rank trains identically?
 cent, pq = full.ivf_export_centroids(m)
 ct, pt = torch.from_numpy(cent).to(dev), torch.from_numpy(pq).to(dev)
 dist.broadcast(ct, 0); dist.broadcast(pt, 0)
+torch.cuda.synchronize()   # the library copies on its own stream: the broadcast must have landed
 ref_ix = kb.Index("IVF_PQ", "L2", d, cfgb, device=rank)
 kb._check(kb.lib().kb2_ivf_import_begin(ref_ix.h, nlist, ct.data_ptr(), pt.data_ptr()))
 ref_ix.add(xb)
