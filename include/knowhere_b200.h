@@ -69,7 +69,8 @@ int kb2_device_count(void);
  * (reference: include/knowhere/index/index_factory.h:27-72, src/index/index_factory.cc:48-86).
  * index_type: "FLAT" | "IVF_FLAT" | "IVF_PQ" | "HNSW"    (index_param.h:27-46)
  * json_cfg  : build-time keys of the reference configs: metric_type, dim, nlist, m, nbits,
- *             refine, refine_type ("flat"|"fp32"), M, efConstruction
+ *             refine, refine_type ("flat"|"fp32"), M, efConstruction.  metric KB2_METRIC_COSINE: vectors are
+ *             L2-normalised on entry and queries at search (then inner product); HasRawData is false.
  *             (ivf_config.h:25-128, base_hnsw_config.h:36-62).  May be NULL/"" for defaults. */
 int kb2_index_create(const char* index_type, int metric, int dim, const char* json_cfg, int device,
                      kb2_index_t* out);

@@ -258,6 +258,7 @@ inline int kb2_metric_of(const Json& cfg, Status& st) {
     st = Status::success;
     if (m == "L2") return KB2_METRIC_L2;
     if (m == "IP") return KB2_METRIC_IP;
+    if (m == "COSINE") return KB2_METRIC_COSINE;
     st = Status::invalid_metric_type;
     return -1;
 }

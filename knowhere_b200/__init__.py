@@ -13,7 +13,7 @@ import numpy as np
 from ._build import LIB, build  # noqa: F401
 
 METRIC_L2, METRIC_IP = 0, 1
-_METRICS = {"L2": 0, "IP": 1, 0: 0, 1: 1}
+_METRICS = {"L2": 0, "IP": 1, "COSINE": 2, 0: 0, 1: 1, 2: 2}
 
 _lib = None
 

@@ -222,6 +222,19 @@ gather_f32_kernel(const float* __restrict__ src, const int32_t* __restrict__ row
     out[t] = (r >= 0) ? src[r] : fill;
 }
 
+// out[i] = x[i] / |x[i]|  (rows of norm 0 are copied unchanged), warp per row — COSINE support
+__global__ void __launch_bounds__(256)
+normalize_rows_kernel(const float* __restrict__ x, int64_t n, int d, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    float acc = 0.f;
+    for (int j = lane; j < d; j += kWarp) acc = fmaf(x[i * d + j], x[i * d + j], acc);
+    acc = warp_sum(acc);
+    const float inv = acc > 0.f ? 1.0f / sqrtf(acc) : 1.0f;
+    for (int j = lane; j < d; j += kWarp) out[i * d + j] = x[i * d + j] * inv;
+}
+
 // key = nearest list of each query (first entry of its probe row), value = query index
 __global__ void
 first_probe_kernel(const int64_t* __restrict__ probe_ids, int nprobe, int64_t nq, int32_t* __restrict__ key,

@@ -126,8 +126,13 @@ kb2_index_create(const char* index_type, int metric, int dim, const char* json_c
         JsonObj cfg = JsonObj::parse(json_cfg);
         KB2_REQUIRE(cfg.ok, KB2_INVALID_PARAM_IN_JSON, "malformed json");
         metric = parse_metric(metric, cfg);
-        KB2_REQUIRE(metric == KB2_METRIC_L2 || metric == KB2_METRIC_IP, KB2_INVALID_METRIC_TYPE,
-                    "metric must be L2 or IP (COSINE: normalise and use IP)");
+        KB2_REQUIRE(metric == KB2_METRIC_L2 || metric == KB2_METRIC_IP || metric == KB2_METRIC_COSINE,
+                    KB2_INVALID_METRIC_TYPE, "metric must be L2, IP or COSINE");
+        // COSINE = inner product of L2-normalised vectors: data is normalised when it enters the index and
+        // queries when they are searched (what the reference does for IVF_PQ, ivf.cc:557-565,1067-1071; for FLAT
+        // the reference keeps inverse norms instead, flat.cc:57-62 — same similarities)
+        const bool cosine = (metric == KB2_METRIC_COSINE);
+        if (cosine) metric = KB2_METRIC_IP;
         if (dim <= 0) dim = (int)cfg.get_int("dim", 0);
         KB2_REQUIRE(dim > 0, KB2_INVALID_ARGS, "dim must be positive");
         require_device(device);
@@ -165,6 +170,7 @@ kb2_index_create(const char* index_type, int metric, int dim, const char* json_c
         }
         ix->type = t;
         ix->metric = metric;
+        ix->cosine = cosine;
         ix->dim = dim;
         ix->device = device;
         ix->init_common();
@@ -209,7 +215,7 @@ kb2_index_train(kb2_index_t h, const float* x, int64_t n) {
         std::lock_guard<std::mutex> lk(ix->mu);
         KB2_CUDA_CHECK(cudaSetDevice(ix->device));
         KB2_REQUIRE(x != nullptr || n == 0, KB2_INVALID_ARGS, "null training data");
-        ix->train(x, n);
+        ix->train(ix->cosine ? ix->normalized(x, n) : x, n);
     });
 }
 
@@ -220,7 +226,7 @@ kb2_index_add(kb2_index_t h, const float* x, int64_t n, const int64_t* ids) {
         std::lock_guard<std::mutex> lk(ix->mu);
         KB2_CUDA_CHECK(cudaSetDevice(ix->device));
         KB2_REQUIRE(x != nullptr || n == 0, KB2_INVALID_ARGS, "null data");
-        ix->add(x, n, ids);
+        ix->add(ix->cosine ? ix->normalized(x, n) : x, n, ids);
     });
 }
 
@@ -239,7 +245,7 @@ kb2_index_search(kb2_index_t h, const float* queries, int64_t nq, int k, const c
         JsonObj cfg = JsonObj::parse(json);
         KB2_REQUIRE(cfg.ok, KB2_INVALID_PARAM_IN_JSON, "malformed json");
         ix->last = Counters{};
-        ix->search(queries, nq, k, cfg, bitset, bitset_nbits, out_ids, out_dist);
+        ix->search(ix->cosine ? ix->normalized(queries, nq) : queries, nq, k, cfg, bitset, bitset_nbits, out_ids, out_dist);
     });
 }
 
@@ -255,8 +261,8 @@ kb2_index_range_search(kb2_index_t h, const float* queries, int64_t nq, float ra
         JsonObj cfg = JsonObj::parse(json);
         KB2_REQUIRE(cfg.ok, KB2_INVALID_PARAM_IN_JSON, "malformed json");
         ix->last = Counters{};
-        range_search_index(*ix, queries, nq, radius, range_filter, has_range_filter != 0, cfg, bitset, bitset_nbits,
-                           out_lims, out_ids, out_dist);
+        range_search_index(*ix, ix->cosine ? ix->normalized(queries, nq) : queries, nq, radius, range_filter,
+                           has_range_filter != 0, cfg, bitset, bitset_nbits, out_lims, out_ids, out_dist);
     });
 }
 
@@ -283,7 +289,8 @@ kb2_index_is_trained(kb2_index_t h) {
 }
 int
 kb2_index_has_raw_data(kb2_index_t h) {
-    return h ? (int)reinterpret_cast<Handle*>(h)->ix->has_raw() : 0;
+    // COSINE stores the normalised vectors, not the caller's raw data
+    return h ? (int)(reinterpret_cast<Handle*>(h)->ix->has_raw() && !reinterpret_cast<Handle*>(h)->ix->cosine) : 0;
 }
 int
 kb2_index_get_vector_by_ids(kb2_index_t h, const int64_t* ids, int64_t n, float* out) {
@@ -291,6 +298,7 @@ kb2_index_get_vector_by_ids(kb2_index_t h, const int64_t* ids, int64_t n, float*
         IndexBase* ix = ix_of(h);
         std::lock_guard<std::mutex> lk(ix->mu);
         KB2_CUDA_CHECK(cudaSetDevice(ix->device));
+        KB2_REQUIRE(!ix->cosine, KB2_NOT_IMPLEMENTED, "GetVectorByIds: a COSINE index keeps normalised vectors only");
         ix->get_vectors(ids, n, out);
     });
 }
@@ -439,18 +447,20 @@ kb2_bruteforce_search(const float* base, int64_t nb, int dim, int metric, const 
                       void* cuda_stream) {
     return guarded([&] {
         KB2_REQUIRE(base && queries && out_ids && out_dist, KB2_INVALID_ARGS, "null buffer");
-        KB2_REQUIRE(metric == KB2_METRIC_L2 || metric == KB2_METRIC_IP, KB2_INVALID_METRIC_TYPE, "metric must be L2 or IP");
+        KB2_REQUIRE(metric == KB2_METRIC_L2 || metric == KB2_METRIC_IP || metric == KB2_METRIC_COSINE,
+                    KB2_INVALID_METRIC_TYPE, "metric must be L2, IP or COSINE");
         require_device(device);
         FlatIndex fi;
         fi.type = "FLAT";
-        fi.metric = metric;
+        fi.cosine = (metric == KB2_METRIC_COSINE);
+        fi.metric = fi.cosine ? KB2_METRIC_IP : metric;
         fi.dim = dim;
         fi.device = device;
         fi.init_common();
         if (cuda_stream) fi.set_stream((cudaStream_t)cuda_stream);
-        fi.add(base, nb, nullptr);
+        fi.add(fi.cosine ? fi.normalized(base, nb) : base, nb, nullptr);
         JsonObj cfg;
-        fi.search(queries, nq, k, cfg, bitset, bitset_nbits, out_ids, out_dist);
+        fi.search(fi.cosine ? fi.normalized(queries, nq) : queries, nq, k, cfg, bitset, bitset_nbits, out_ids, out_dist);
     });
 }
 int

@@ -140,6 +140,7 @@ dev_append(DevBuf<T>& buf, size_t& used, const T* src, size_t count, cudaStream_
 struct IndexBase {
     std::string type;
     int metric = KB2_METRIC_L2, dim = 0, device = 0;
+    bool cosine = false;   // COSINE: metric == IP over vectors normalised on entry (see kb2_index_create)
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int shard_rank = 0, shard_world = 1;
@@ -155,6 +156,18 @@ struct IndexBase {
     DevBuf<uint64_t> s_partial, s_partial2;
     DevBuf<int64_t> s_out_ids, s_probe_ids;
     DevBuf<uint8_t> s_bitset;
+    DevBuf<float> s_cos_in, s_cos_out;
+
+    // L2-normalised device copy of n rows (COSINE)
+    const float*
+    normalized(const float* x, int64_t n) {
+        if (n <= 0 || !x) return x;
+        const float* dx = to_device(x, (size_t)n * dim, s_cos_in);
+        s_cos_out.ensure((size_t)n * dim);
+        normalize_rows_kernel<<<grid1d(n * 32, 256), 256, 0, stream>>>(dx, n, dim, s_cos_out.p);
+        KB2_CUDA_CHECK(cudaGetLastError());
+        return s_cos_out.p;
+    }
 
     virtual ~IndexBase() {
         if (ev0) cudaEventDestroy(ev0);

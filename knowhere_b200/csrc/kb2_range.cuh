@@ -411,7 +411,7 @@ serialize_index(IndexBase& ix, std::vector<uint8_t>& blob) {
     w.put<uint32_t>(0x4932424b);  // "KB2I"
     w.put<uint32_t>(1);
     w.put_str(ix.type);
-    w.put<int32_t>(ix.metric);
+    w.put<int32_t>(ix.cosine ? KB2_METRIC_COSINE : ix.metric);
     w.put<int32_t>(ix.dim);
     if (auto* fi = dynamic_cast<FlatIndex*>(&ix)) {
         const int64_t n = fi->count();
@@ -471,7 +471,9 @@ deserialize_index(const uint8_t* blob, size_t size, int device) {
     KB2_REQUIRE(r.get<uint32_t>() == 0x4932424b, KB2_INVALID_BINARY_SET, "bad magic");
     KB2_REQUIRE(r.get<uint32_t>() == 1, KB2_INVALID_BINARY_SET, "unsupported version");
     const std::string type = r.get_str();
-    const int metric = r.get<int32_t>();
+    const int metric_raw = r.get<int32_t>();
+    const bool cosine = metric_raw == KB2_METRIC_COSINE;
+    const int metric = cosine ? KB2_METRIC_IP : metric_raw;
     const int dim = r.get<int32_t>();
     std::unique_ptr<IndexBase> ix;
     if (type == "FLAT") {
@@ -542,6 +544,7 @@ deserialize_index(const uint8_t* blob, size_t size, int device) {
     } else {
         throw Error(KB2_INVALID_BINARY_SET, "unknown index type in blob");
     }
+    ix->cosine = cosine;   // stored vectors are already normalised; queries will be
     return ix;
 }
 

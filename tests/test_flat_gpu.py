@@ -103,3 +103,23 @@ def test_flat_serialize_roundtrip(kb):
     b = ix2.search(xq, 5)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     np.testing.assert_array_equal(ix2.get_vector_by_ids([3, 1999]), xb[[3, 1999]])
+
+
+@pytest.mark.parametrize("kind,cfg,scfg", [("FLAT", {}, {}), ("IVF_FLAT", {"nlist": 16}, {"nprobe": 16}),
+                                           ("HNSW", {"M": 16, "efConstruction": 100}, {"ef": 64})])
+def test_cosine_metric(kb, kind, cfg, scfg):
+    # reference KAT (tests/ut/test_bruteforce.cc:57-77): self query under COSINE => first hit is itself, |dist-1| < 1e-5
+    xb = datagen.clustered(4000, 48, 21) + 1.0
+    ix = kb.Index(kind, "COSINE", 48, cfg)
+    ix.build(xb)
+    ids, dist = ix.search(xb[:50].copy(), 5, scfg)
+    assert (ids[:, 0] == np.arange(50)).all()
+    np.testing.assert_allclose(dist[:, 0], 1.0, atol=1e-5)
+    assert (dist <= 1.0 + 1e-5).all() and (dist >= -1.0 - 1e-5).all()
+    xn = xb / np.linalg.norm(xb, axis=1, keepdims=True)
+    if kind != "HNSW":
+        gt = np.argsort(-(xn[:50] @ xn.T), axis=1)[:, :5]
+        assert (ids == gt).mean() > 0.98
+    assert not ix.has_raw_data()
+    bi, bd = kb.brute_force_search(xb, xb[:50].copy(), 5, "COSINE")
+    assert (bi[:, 0] == np.arange(50)).all()
