@@ -800,7 +800,7 @@ struct IvfIndex : IndexBase {
         sp.counters = d_counter.p;
         sp.qperm = qperm;
         const size_t common_smem = (size_t)kScanWarps * 2 * Ksel * 8 + (size_t)(np_max + 1) * 4 + (size_t)np_max * 12 +
-                                   (size_t)dim * 4 + 64 + 8 * (kScanWarps + 2);
+                                   (size_t)dim * 4 + 64 + 8 * (2 * kScanWarps + 4) + (size_t)4 * Ksel * 8;   // + CTA bound block + merge buffer
         const unsigned grid = (unsigned)(nq * nsplit);
         if (timing) KB2_CUDA_CHECK(cudaEventRecord(ev0, st));
         if (is_pq) {
@@ -825,6 +825,7 @@ struct IvfIndex : IndexBase {
     if (scan_nt == 512) { KB2_LAUNCH_PQ_NT(GG, 512) } else { KB2_LAUNCH_PQ_NT(GG, 256) }
                 const char* e_pf = getenv("KB2_SCAN_PREFETCH");
                 sp.flags = (e_pf ? atoi(e_pf) : KB2_DEFAULT_SCAN_PREFETCH) ? 2 : 0;
+                if (const char* e_fm = getenv("KB2_SCAN_FULLMERGE")) sp.flags |= atoi(e_fm) ? 4 : 0;
                 if (G == 1) { KB2_LAUNCH_PQ(1) } else if (G == 2) { KB2_LAUNCH_PQ(2) } else { KB2_LAUNCH_PQ(3) }
 #undef KB2_LAUNCH_PQ
 #undef KB2_LAUNCH_PQ_NT

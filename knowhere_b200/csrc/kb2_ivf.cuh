@@ -60,7 +60,7 @@ struct IvfScanParams {
     const float* t1;           // [npad] or NULL
     unsigned long long* counters;  // [0] codes scanned (optional, NULL to skip)
     const int32_t* qperm;          // [nq] visiting order of the queries (NULL: identity)
-    int flags;                     // bit1: software L2 prefetch of upcoming chunks (A/B switch)
+    int flags;                     // bit1: software L2 prefetch of upcoming chunks; bit2: full-sort final merge (A/B switches)
 };
 
 // probe bookkeeping in shared memory
@@ -233,10 +233,16 @@ ivfpq_scan_kernel(IvfScanParams p) {
     }
     WarpTopK tk;
     tk.init(lists + warp * 2 * p.K, p.K, lane);
+    uint64_t* merge_tmp;
+    uint32_t* merge_ctr;
+    unsigned long long* sh_V_final;
     {
         // CTA-wide admission bound (see WarpTopK): 8-byte aligned block after the query
         unsigned long long* shb = (unsigned long long*)(((uintptr_t)(s_q + p.d) + 7) & ~(uintptr_t)7);
         tk.share(shb, shb + NW, NW, warp, lane);
+        merge_tmp = (uint64_t*)(shb + NW + 2);      // 4K-entry compaction buffer for the final merge
+        merge_ctr = (uint32_t*)(merge_tmp + 4 * p.K);
+        sh_V_final = shb + NW;
     }
     __syncthreads();
 
@@ -335,7 +341,12 @@ ivfpq_scan_kernel(IvfScanParams p) {
 
     uint64_t* out = p.partial + ((int64_t)q * p.nsplit + split) * p.kout;
     tk.finish(lane);
-    block_emit_topk(lists, p.K, out, p.kout, NW);
+    __syncthreads();
+    if (p.flags & 4) {
+        block_emit_topk(lists, p.K, out, p.kout, NW);   // A/B switch: plain full sort of all warp buffers
+    } else {
+        block_emit_topk_bounded(lists, p.K, NW, *sh_V_final, merge_tmp, 4 * p.K, merge_ctr, out, p.kout);
+    }
 }
 
 // =====================================================================================

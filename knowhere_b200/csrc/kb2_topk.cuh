@@ -180,6 +180,34 @@ block_emit_topk(uint64_t* lists, int K, uint64_t* __restrict__ out, int kout, in
     for (int i = threadIdx.x; i < kout; i += blockDim.x) out[i] = lists[i];
 }
 
+// Cheaper CTA merge when the warps exchanged a CTA-wide bound V (WarpTopK::share): every entry of the final
+// top-K is <= V and V is the max of the warps' (K/nwarps)-th best, so only the (typically K..2K) entries <= V
+// need sorting.  They are compacted into `tmp` (capacity cap, power of two, >= K) and sorted there; if more than
+// `cap` entries qualify the full sort is used.  `ctr` is one shared u32.  All threads of the CTA call this.
+__device__ __forceinline__ void
+block_emit_topk_bounded(uint64_t* lists, int K, int nwarps, unsigned long long V, uint64_t* tmp, int cap, uint32_t* ctr,
+                        uint64_t* __restrict__ out, int kout) {
+    __syncthreads();                      // every warp has finished (buffers sorted, [0,K) valid)
+    if (threadIdx.x == 0) *ctr = 0;
+    for (int i = threadIdx.x; i < cap; i += blockDim.x) tmp[i] = kEmpty;
+    __syncthreads();
+    for (int i = threadIdx.x; i < nwarps * K; i += blockDim.x) {
+        const uint64_t e = lists[(i / K) * 2 * K + (i % K)];
+        if (e != kEmpty && e <= V) {
+            const uint32_t slot = atomicAdd(ctr, 1u);
+            if (slot < (uint32_t)cap) tmp[slot] = e;
+        }
+    }
+    __syncthreads();
+    if (*ctr <= (uint32_t)cap) {          // CTA-uniform
+        block_bitonic_sort(tmp, cap);
+        for (int i = threadIdx.x; i < kout; i += blockDim.x) out[i] = i < cap ? tmp[i] : kEmpty;
+    } else {
+        block_bitonic_sort(lists, nwarps * 2 * K);
+        for (int i = threadIdx.x; i < kout; i += blockDim.x) out[i] = lists[i];
+    }
+}
+
 // --------------------------------------------------------------------------------------------
 // Finalize: one CTA per query.
 //   1. gather this query's partial candidate lists, CTA bitonic sort, keep the best k_sel

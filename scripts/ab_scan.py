@@ -16,7 +16,7 @@ ix.enable_kernel_timing(True)
 base = None
 for rep in range(2):
     for nt, acc, noshare in itertools.product((256,), (2,), (0, 1)):
-        os.environ["KB2_SCAN_NT"] = str(nt); os.environ["KB2_SCAN_ACC"] = str(acc); os.environ["KB2_SCAN_PREFETCH"] = str(noshare)
+        os.environ["KB2_SCAN_NT"] = str(nt); os.environ["KB2_SCAN_ACC"] = str(acc); os.environ["KB2_SCAN_FULLMERGE"] = str(noshare)
         for _ in range(3):
             ix.search(xq, k, cfg, out=(ids, dis))
         ks = []
@@ -26,4 +26,4 @@ for rep in range(2):
             ix.search(xq, k, cfg, out=(ids, dis)); ks.append(ix.last_kernel_ms())
         e1.record(); torch.cuda.synchronize()
         if base is None: base = ids.clone()
-        print(f"rep{rep} NT={nt} ACC={acc} prefetch={noshare}: step {e0.elapsed_time(e1)/8:.3f} ms  scan kernel {sum(ks)/len(ks):.3f} ms  same_ids={bool((ids==base).all())}", flush=True)
+        print(f"rep{rep} NT={nt} ACC={acc} fullmerge={noshare}: step {e0.elapsed_time(e1)/8:.3f} ms  scan kernel {sum(ks)/len(ks):.3f} ms  same_ids={bool((ids==base).all())}", flush=True)
