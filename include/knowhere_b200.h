@@ -176,7 +176,8 @@ int kb2_merge_topk(int metric, int world, int64_t nq, int k, const int64_t* in_i
 /* ---- introspection used by bench.py for the roofline figures --------------------------- */
 /* fills out[0..7] with counters of the last search on this handle:
  * [0] kernels launched, [1] codes (rows) scanned, [2] algorithmic code bytes scanned,
- * [3] (query,list) pairs, [4] H2D bytes, [5] D2H bytes, [6] reserved, [7] reserved */
+ * [3] (query,list) pairs, [4] H2D bytes, [5] D2H bytes, [6] IVF_PQ tensor-core engine: codes re-evaluated exactly (survivors of
+ * the bf16 filter), [7] queries redone by the LUT kernel (no bound / survivor-buffer overflow) */
 int kb2_index_last_search_counters(kb2_index_t h, int64_t* out8);
 /* device time in milliseconds of the dominant scan kernel of the last search, measured with
  * CUDA events on the handle's stream (valid only after kb2_index_enable_kernel_timing(h,1)) */

@@ -276,7 +276,7 @@ class Index:
         c = np.zeros(8, np.int64)
         _check(self.L.kb2_index_last_search_counters(self.h, _ptr(c)))
         return dict(launches=int(c[0]), codes=int(c[1]), code_bytes=int(c[2]), pairs=int(c[3]), h2d=int(c[4]),
-                    d2h=int(c[5]))
+                    d2h=int(c[5]), survivors=int(c[6]), flagged=int(c[7]))
 
     def enable_kernel_timing(self, on=True):
         _check(self.L.kb2_index_enable_kernel_timing(self.h, 1 if on else 0))

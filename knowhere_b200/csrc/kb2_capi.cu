@@ -532,8 +532,8 @@ kb2_index_last_search_counters(kb2_index_t h, int64_t* out8) {
         out8[3] = c.pairs;
         out8[4] = c.h2d;
         out8[5] = c.d2h;
-        out8[6] = 0;
-        out8[7] = 0;
+        out8[6] = c.survivors;
+        out8[7] = c.flagged;
     });
 }
 int

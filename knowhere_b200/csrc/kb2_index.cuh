@@ -11,6 +11,7 @@
 #include "kb2_build.cuh"
 #include "kb2_gemm_tc.cuh"
 #include "kb2_ivf.cuh"
+#include "kb2_ivfpq_tc.cuh"
 #include "kb2_json.h"
 
 namespace kb2 {
@@ -67,6 +68,10 @@ init_kernel_attributes() {
         set((const void*)ivfpq_scan_generic_kernel<KB2_METRIC_IP>);
         set((const void*)ivfflat_scan_kernel<KB2_METRIC_L2>);
         set((const void*)ivfflat_scan_kernel<KB2_METRIC_IP>);
+        set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_L2>);
+        set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_IP>);
+        set((const void*)pqtc::bound_kernel<KB2_METRIC_L2>);
+        set((const void*)pqtc::bound_kernel<KB2_METRIC_IP>);
         cudaGetLastError();
     });
 }
@@ -118,6 +123,7 @@ launch_gemm_keys(cudaStream_t st, int mode, int metric, const float* Q, const fl
 
 struct Counters {
     int64_t launches = 0, codes = 0, code_bytes = 0, pairs = 0, h2d = 0, d2h = 0;
+    int64_t survivors = 0, flagged = 0;   // tensor-core PQ engine: codes re-evaluated exactly / queries redone by the LUT kernel
 };
 
 // grow-by-doubling append of `count` elements (device->device or host->device)
@@ -182,7 +188,7 @@ struct IndexBase {
         own_stream = true;
         KB2_CUDA_CHECK(cudaEventCreate(&ev0));
         KB2_CUDA_CHECK(cudaEventCreate(&ev1));
-        d_counter.ensure(4);
+        d_counter.ensure(8);
     }
     void
     set_stream(cudaStream_t s) {
@@ -523,6 +529,7 @@ struct IvfIndex : IndexBase {
             AssignScratch sc;
             assign_nearest(xt, nt, dim, centroids.p, (int)nlist, metric, asg.p, nullptr, sc, stream);
             pqc.alloc_exact((size_t)M * 256 * dsub);
+            tc_ready = false;
             DevBuf<float> sub;
             sub.ensure((size_t)nt * dsub);
             for (int m = 0; m < M; m++) {
@@ -697,6 +704,255 @@ struct IvfIndex : IndexBase {
         sealed = false;
     }
 
+    // ---------------------------------------------------------------- query-major scan launch (all IVF kinds)
+    void
+    launch_scan(IvfScanParams sp, unsigned grid, int Ksel, int np_max, bool has_bits) {
+        cudaStream_t st = stream;
+        const uint8_t* dbits = has_bits ? sp.bitset : nullptr;
+        const size_t common_smem = (size_t)kScanWarps * 2 * Ksel * 8 + (size_t)(np_max + 1) * 4 + (size_t)np_max * 12 +
+                                   (size_t)dim * 4 + 64 + 8 * (2 * kScanWarps + 4) + (size_t)4 * Ksel * 8;   // + CTA bound block + merge buffer
+        if (is_pq) {
+            if (G > 0) {
+                const int scan_nt_env = [] { const char* e = getenv("KB2_SCAN_NT"); return e ? atoi(e) : 0; }();
+                int scan_nt = (scan_nt_env == 256 || scan_nt_env == 512) ? scan_nt_env : KB2_DEFAULT_SCAN_NT;
+                size_t smem = (size_t)G * 65536 + common_smem;
+                if (scan_nt == 512) {
+                    const size_t smem512 = smem + (size_t)kScanWarps * 2 * Ksel * 8 + 8 * kScanWarps;  // 16 warp buffers
+                    if (smem512 <= (size_t)kMaxDynSmem) smem = smem512; else scan_nt = 256;
+                }
+                KB2_REQUIRE(smem <= (size_t)kMaxDynSmem, KB2_INVALID_ARGS, "IVF_PQ: k too large for shared memory");
+#define KB2_LAUNCH_PQ_NT(GG, NTT)                                                                              \
+    if (metric == KB2_METRIC_L2) {                                                                             \
+        if (dbits) ivfpq_scan_kernel<GG, KB2_METRIC_L2, true, NTT><<<grid, NTT, smem, st>>>(sp);               \
+        else ivfpq_scan_kernel<GG, KB2_METRIC_L2, false, NTT><<<grid, NTT, smem, st>>>(sp);                    \
+    } else {                                                                                                   \
+        if (dbits) ivfpq_scan_kernel<GG, KB2_METRIC_IP, true, NTT><<<grid, NTT, smem, st>>>(sp);               \
+        else ivfpq_scan_kernel<GG, KB2_METRIC_IP, false, NTT><<<grid, NTT, smem, st>>>(sp);                    \
+    }
+#define KB2_LAUNCH_PQ(GG)                                     \
+    if (scan_nt == 512) { KB2_LAUNCH_PQ_NT(GG, 512) } else { KB2_LAUNCH_PQ_NT(GG, 256) }
+                const char* e_pf = getenv("KB2_SCAN_PREFETCH");
+                sp.flags = (e_pf ? atoi(e_pf) : KB2_DEFAULT_SCAN_PREFETCH) ? 2 : 0;
+                if (const char* e_fm = getenv("KB2_SCAN_FULLMERGE")) sp.flags |= atoi(e_fm) ? 4 : 0;
+                if (G == 1) { KB2_LAUNCH_PQ(1) } else if (G == 2) { KB2_LAUNCH_PQ(2) } else { KB2_LAUNCH_PQ(3) }
+#undef KB2_LAUNCH_PQ
+#undef KB2_LAUNCH_PQ_NT
+            } else {
+                const size_t smem = (size_t)M * 1024 + common_smem;
+                KB2_REQUIRE(smem <= (size_t)kMaxDynSmem, KB2_NOT_IMPLEMENTED, "IVF_PQ: m too large for the generic kernel");
+                if (metric == KB2_METRIC_L2)
+                    ivfpq_scan_generic_kernel<KB2_METRIC_L2><<<grid, kScanThreads, smem, st>>>(sp, codes.p);
+                else
+                    ivfpq_scan_generic_kernel<KB2_METRIC_IP><<<grid, kScanThreads, smem, st>>>(sp, codes.p);
+            }
+        } else {
+            KB2_REQUIRE(dim % 4 == 0, KB2_NOT_IMPLEMENTED, "IVF_FLAT: dim must be a multiple of 4 on the GPU path");
+            if (metric == KB2_METRIC_L2)
+                ivfflat_scan_kernel<KB2_METRIC_L2><<<grid, kScanThreads, common_smem, st>>>(sp);
+            else
+                ivfflat_scan_kernel<KB2_METRIC_IP><<<grid, kScanThreads, common_smem, st>>>(sp);
+        }
+        last.launches++;
+        KB2_CUDA_CHECK(cudaGetLastError());
+    }
+
+    // ---------------------------------------------------------------- list-major tensor-core engine (kb2_ivfpq_tc.cuh)
+    static constexpr int kTcCandCap = 512;      // survivor slots per query (overflow -> LUT kernel redoes the query)
+    DevBuf<uint16_t> tc_pqc16, s_qb16;
+    DevBuf<float> tc_maxn2, s_qnorm, s_pair_base, s_lut;
+    DevBuf<int32_t> s_lcount, s_lstart, s_items, s_pair_q, s_plan_out, s_flaglist;
+    DevBuf<uint64_t> s_cand, s_boundrows;
+    DevBuf<uint32_t> s_cand_cnt, s_logcnt;
+    DevBuf<uint4> s_log;
+    float tc_rmax = 0.f;
+    bool tc_ready = false;
+
+    bool
+    use_tc_engine(int64_t nq, int nprobe, int Ksel) const {
+        if (!is_pq || G != 1 || M != 16 || dsub != 8 || dim != 128) return false;
+        const char* e = getenv("KB2_PQ_ENGINE");
+        if (e && !strcmp(e, "lut")) return false;
+        if (nprobe < 8 || Ksel > kTcCandCap / 2) return false;
+        if (e && !strcmp(e, "tc")) return true;
+        // the decode of a list is amortised over the queries that probe it: needs a few dozen per list
+        return (double)nq * nprobe >= 32.0 * (double)nlist;
+    }
+
+    void
+    search_tc(IvfScanParams sp, int64_t nq, int nprobe, int Ksel, int k_base, bool has_bits) {
+        cudaStream_t st = stream;
+        if (!tc_ready) {
+            tc_pqc16.alloc_exact((size_t)16 * 256 * 8);
+            tc_maxn2.alloc_exact(16);
+            pqtc::prepare_tables_kernel<<<16, 256, 0, st>>>(pqc.p, (__nv_bfloat16*)tc_pqc16.p, tc_maxn2.p);
+            float h[16];
+            KB2_CUDA_CHECK(cudaMemcpyAsync(h, tc_maxn2.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+            KB2_CUDA_CHECK(cudaStreamSynchronize(st));
+            double acc = 0;
+            for (float v : h) acc += v;
+            tc_rmax = (float)std::sqrt(acc) * 1.0001f;
+            tc_ready = true;
+        }
+        const int64_t npairs = nq * nprobe;
+        // development aid: KB2_TC_VERBOSE=1 prints the device time of every stage of this engine
+        const bool verbose = getenv("KB2_TC_VERBOSE") != nullptr;
+        std::vector<std::pair<const char*, cudaEvent_t>> marks;
+        auto mark = [&](const char* name) {
+            if (!verbose) return;
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            cudaEventRecord(e, st);
+            marks.emplace_back(name, e);
+        };
+        mark("start");
+        // ---- phase A: LUT scan of the nearest lists -> per-query upper bound of the k_base-th best key
+        const char* e_p0 = getenv("KB2_TC_P0");
+        const char* e_ac = getenv("KB2_TC_A_CODES");
+        const int p0 = std::max(1, std::min((e_p0 ? atoi(e_p0) : 8) * std::max(1, shard_world), nprobe));   // at most this many lists
+        const int a_codes = e_ac ? atoi(e_ac) : 3000;                                                        // ... until this many codes
+        s_boundrows.ensure((size_t)nq * Ksel);
+        s_lut.ensure((size_t)nq * 4096);
+        {
+            const size_t smem = pqtc::BOUND_SMEM;
+            if (metric == KB2_METRIC_L2) {
+                pqtc::lut_build_kernel<KB2_METRIC_L2><<<kNumSMs, 256, 0, st>>>(sp.queries, nq, pqc.p, s_lut.p);
+                mark("lut");
+                pqtc::bound_kernel<KB2_METRIC_L2><<<(unsigned)nq, 128, smem, st>>>(
+                    s_lut.p, sp.probe_ids, sp.probe_dis, nprobe, p0, a_codes, k_base, list_off.p, list_len.p, (const uint4*)codes.p,
+                    t1.p, sp.bitset, rows.p, Ksel, s_boundrows.p, d_counter.p + 4);
+            } else {
+                pqtc::lut_build_kernel<KB2_METRIC_IP><<<kNumSMs, 256, 0, st>>>(sp.queries, nq, pqc.p, s_lut.p);
+                mark("lut");
+                pqtc::bound_kernel<KB2_METRIC_IP><<<(unsigned)nq, 128, smem, st>>>(
+                    s_lut.p, sp.probe_ids, sp.probe_dis, nprobe, p0, a_codes, k_base, list_off.p, list_len.p, (const uint4*)codes.p,
+                    t1.p, sp.bitset, rows.p, Ksel, s_boundrows.p, d_counter.p + 4);
+            }
+            KB2_CUDA_CHECK(cudaGetLastError());
+            last.launches += 2;
+        }
+        mark("phaseA");
+        // ---- plan: pairs grouped by list, work items
+        const int64_t max_items = nlist + npairs / pqtc::NQT + 2;
+        s_lcount.ensure((size_t)2 * nlist);
+        s_lstart.ensure((size_t)nlist);
+        s_items.ensure((size_t)3 * max_items);
+        s_plan_out.ensure(4);
+        s_pair_q.ensure((size_t)npairs);
+        s_pair_base.ensure((size_t)npairs);
+        s_qb16.ensure((size_t)nq * 128);
+        s_qnorm.ensure((size_t)nq);
+        s_cand.ensure((size_t)nq * kTcCandCap);
+        s_cand_cnt.ensure((size_t)2 * nq);
+        KB2_CUDA_CHECK(cudaMemsetAsync(s_lcount.p, 0, (size_t)2 * nlist * 4, st));
+        KB2_CUDA_CHECK(cudaMemsetAsync(s_cand_cnt.p, 0, (size_t)2 * nq * 4, st));
+        pqtc::count_pairs_kernel<<<grid1d(npairs, 256), 256, 0, st>>>(sp.probe_ids, npairs, list_len.p, s_lcount.p);
+        int32_t* item_list = s_items.p;
+        int32_t* item_q0 = s_items.p + max_items;
+        int32_t* item_nq = s_items.p + 2 * max_items;
+        pqtc::plan_kernel<<<1, 1024, 0, st>>>(s_lcount.p, (int)nlist, s_lstart.p, item_list, item_q0, item_nq, s_plan_out.p);
+        pqtc::fill_pairs_kernel<<<grid1d(npairs, 256), 256, 0, st>>>(sp.probe_ids, sp.probe_dis, npairs, nprobe, metric, list_len.p,
+                                                                     s_lstart.p, s_lcount.p + nlist, s_pair_q.p, s_pair_base.p);
+        pqtc::prepare_queries_kernel<<<grid1d(nq * 32, 256), 256, 0, st>>>(sp.queries, nq, (__nv_bfloat16*)s_qb16.p, s_qnorm.p);
+        mark("plan");
+        // ---- tensor-core filter + exact re-evaluation of the survivors
+        pqtc::Params tp{};
+        tp.metric = metric;
+        tp.nq = (int)nq;
+        tp.nprobe = nprobe;
+        tp.queries = sp.queries;
+        tp.qb16 = (const __nv_bfloat16*)s_qb16.p;
+        tp.qnorm = s_qnorm.p;
+        tp.n_items = s_plan_out.p;
+        tp.item_list = item_list;
+        tp.item_q0 = item_q0;
+        tp.item_nq = item_nq;
+        tp.pair_q = s_pair_q.p;
+        tp.pair_base = s_pair_base.p;
+        tp.bound_rows = s_boundrows.p;
+        tp.bound_stride = Ksel;
+        tp.k_need = k_base;
+        tp.margin_coef = (metric == KB2_METRIC_L2 ? 2.f : 1.f) * pqtc::kErrCoef * tc_rmax;
+        tp.list_off = list_off.p;
+        tp.list_len = list_len.p;
+        tp.codes = (const uint4*)codes.p;
+        tp.npad = npad;
+        tp.t1 = t1.p;
+        tp.pqc = pqc.p;
+        tp.pqc16 = (const uint4*)tc_pqc16.p;
+        tp.bitset = sp.bitset;
+        tp.rows = rows.p;
+        const int n_logs = 2 * kNumSMs;   // one per epilogue group, + 1 shared
+        const uint32_t log_cap = (uint32_t)std::min<int64_t>(std::max<int64_t>(nq * 1024 / n_logs, 16384), 1 << 19);
+        const uint32_t shared_cap = std::max<uint32_t>(1u << 20, 8 * log_cap);   // tiles that overflow the smem queue
+        s_log.ensure((size_t)n_logs * log_cap + shared_cap);
+        s_logcnt.ensure(n_logs + 8);
+        KB2_CUDA_CHECK(cudaMemsetAsync(s_logcnt.p, 0, (n_logs + 8) * 4, st));
+        tp.log = s_log.p;
+        tp.log_cnt = s_logcnt.p;
+        tp.log_cap = log_cap;
+        tp.shared_cap = shared_cap;
+        tp.qflag = s_cand_cnt.p + nq;
+        tp.counters = d_counter.p;
+        if (metric == KB2_METRIC_L2)
+            pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_L2><<<kNumSMs, pqtc::THREADS, pqtc::SMEM_BYTES, st>>>(tp);
+        else
+            pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_IP><<<kNumSMs, pqtc::THREADS, pqtc::SMEM_BYTES, st>>>(tp);
+        KB2_CUDA_CHECK(cudaGetLastError());
+        mark("tc_filter");
+        // ---- survivors: group by query, exact fp32 keys (bit-identical to the LUT engine's)
+        pqtc::scatter_survivors_kernel<<<dim3(16, n_logs + 1), 256, 0, st>>>(s_log.p, s_logcnt.p, log_cap, shared_cap, s_cand.p, s_cand_cnt.p,
+                                                                         kTcCandCap, tp.qflag, d_counter.p);
+        if (metric == KB2_METRIC_L2)
+            pqtc::exact_eval_kernel<KB2_METRIC_L2><<<(unsigned)nq, 128, 0, st>>>(
+                s_lut.p, s_boundrows.p, Ksel, k_base, (const uint4*)codes.p, t1.p, sp.bitset, rows.p, s_cand.p, s_cand_cnt.p,
+                kTcCandCap, tp.qflag, s_logcnt.p + n_logs + 1);
+        else
+            pqtc::exact_eval_kernel<KB2_METRIC_IP><<<(unsigned)nq, 128, 0, st>>>(
+                s_lut.p, s_boundrows.p, Ksel, k_base, (const uint4*)codes.p, t1.p, sp.bitset, rows.p, s_cand.p, s_cand_cnt.p,
+                kTcCandCap, tp.qflag, s_logcnt.p + n_logs + 1);
+        KB2_CUDA_CHECK(cudaGetLastError());
+        last.launches += 7;
+        mark("scatter+eval");
+        // ---- flagged queries (no bound / buffer overflow): complete LUT scan into their candidate rows
+        {
+            IvfScanParams f = sp;
+            f.nsplit = std::max(1, std::min(kTcCandCap / Ksel, nprobe));   // probe slices per flagged query: their lists fill the row
+            f.partial = s_cand.p;
+            f.partial_stride = kTcCandCap;
+            f.clear_to = kTcCandCap - (f.nsplit - 1) * Ksel;   // == Ksel (nothing to clear) when the slices fill the row
+            s_flaglist.ensure((size_t)nq + 1);
+            pqtc::compact_flags_kernel<<<1, 1024, 0, st>>>(tp.qflag, nq, s_flaglist.p + 1, (uint32_t*)s_flaglist.p);
+            last.launches++;
+            f.only_flagged = tp.qflag;
+            f.flag_list = s_flaglist.p + 1;
+            f.flag_count = (const uint32_t*)s_flaglist.p;
+            f.qperm = nullptr;
+            f.lut_global = s_lut.p;
+            f.counters = d_counter.p + 4;
+            launch_scan(f, (unsigned)std::min<int64_t>(nq * f.nsplit, 3 * kNumSMs), Ksel, (nprobe + f.nsplit - 1) / f.nsplit, has_bits);
+        }
+        mark("fallback");
+        if (verbose) {
+            KB2_CUDA_CHECK(cudaStreamSynchronize(st));
+            fprintf(stderr, "[kb2 tc]");
+            for (size_t i = 1; i < marks.size(); i++) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+                fprintf(stderr, " %s %.3f ms |", marks[i].first, ms);
+            }
+            uint32_t hn = 0;
+            cudaMemcpy(&hn, s_plan_out.p, 4, cudaMemcpyDeviceToHost);
+            unsigned long long hc2[8];
+            cudaMemcpy(hc2, d_counter.p, 64, cudaMemcpyDeviceToHost);
+            uint32_t hl[8];
+            cudaMemcpy(hl, s_logcnt.p + 2 * kNumSMs, 32, cudaMemcpyDeviceToHost);
+            fprintf(stderr, " [shared-log %u over %u | overflow tiles %u max pushes %u]", hl[0], hl[1], hl[2], hl[3]);
+            fprintf(stderr, " items %u survivors %llu flagged %llu (queue-overflow pushes %llu, row overflows %llu, no bound %llu)\n", hn,
+                    hc2[2], hc2[7], hc2[3], hc2[6] & 0xffffffffull, hc2[6] >> 32);
+            for (auto& m : marks) cudaEventDestroy(m.second);
+        }
+    }
+
     // ---------------------------------------------------------------- Search (ivf.cc:887-1168)
     void
     search(const float* q, int64_t nq, int k, const JsonObj& cfg, const uint8_t* bitset, int64_t nbits, int64_t* out_ids,
@@ -752,7 +1008,8 @@ struct IvfIndex : IndexBase {
         // ---- visiting order of the queries: sorted by nearest list, so that CTAs resident at the same
         //      time probe the same lists (L2 reuse of codes; results are order-independent)
         const int32_t* qperm = nullptr;
-        if (nq >= 2 * kNumSMs) {
+        const bool tc_engine = use_tc_engine(nq, nprobe, next_pow2(std::max(32, k_base)));
+        if (nq >= 2 * kNumSMs && !tc_engine) {
             s_qkey.ensure(nq); s_qkey2.ensure(nq); s_qidx.ensure(nq); s_qperm.ensure(nq);
             first_probe_kernel<<<grid1d(nq, 256), 256, 0, st>>>(s_probe_ids.p, nprobe, nq, s_qkey.p, s_qidx.p);
             size_t tmp_bytes = 0;
@@ -773,7 +1030,7 @@ struct IvfIndex : IndexBase {
         while ((int64_t)nsplit * Ksel > kMaxSortEntries) nsplit--;
         const int np_max = (nprobe + nsplit - 1) / nsplit;
         s_partial2.ensure((size_t)nq * nsplit * Ksel);
-        KB2_CUDA_CHECK(cudaMemsetAsync(d_counter.p, 0, 16, st));
+        KB2_CUDA_CHECK(cudaMemsetAsync(d_counter.p, 0, 64, st));
         IvfScanParams sp{};
         sp.queries = dq;
         sp.nq = (int)nq;
@@ -799,61 +1056,32 @@ struct IvfIndex : IndexBase {
         sp.t1 = t1.p;
         sp.counters = d_counter.p;
         sp.qperm = qperm;
-        const size_t common_smem = (size_t)kScanWarps * 2 * Ksel * 8 + (size_t)(np_max + 1) * 4 + (size_t)np_max * 12 +
-                                   (size_t)dim * 4 + 64 + 8 * (2 * kScanWarps + 4) + (size_t)4 * Ksel * 8;   // + CTA bound block + merge buffer
         const unsigned grid = (unsigned)(nq * nsplit);
         if (timing) KB2_CUDA_CHECK(cudaEventRecord(ev0, st));
-        if (is_pq) {
-            if (G > 0) {
-                const int scan_nt_env = [] { const char* e = getenv("KB2_SCAN_NT"); return e ? atoi(e) : 0; }();
-                int scan_nt = (scan_nt_env == 256 || scan_nt_env == 512) ? scan_nt_env : KB2_DEFAULT_SCAN_NT;
-                size_t smem = (size_t)G * 65536 + common_smem;
-                if (scan_nt == 512) {
-                    const size_t smem512 = smem + (size_t)kScanWarps * 2 * Ksel * 8 + 8 * kScanWarps;  // 16 warp buffers
-                    if (smem512 <= (size_t)kMaxDynSmem) smem = smem512; else scan_nt = 256;
-                }
-                KB2_REQUIRE(smem <= (size_t)kMaxDynSmem, KB2_INVALID_ARGS, "IVF_PQ: k too large for shared memory");
-#define KB2_LAUNCH_PQ_NT(GG, NTT)                                                                              \
-    if (metric == KB2_METRIC_L2) {                                                                             \
-        if (dbits) ivfpq_scan_kernel<GG, KB2_METRIC_L2, true, NTT><<<grid, NTT, smem, st>>>(sp);               \
-        else ivfpq_scan_kernel<GG, KB2_METRIC_L2, false, NTT><<<grid, NTT, smem, st>>>(sp);                    \
-    } else {                                                                                                   \
-        if (dbits) ivfpq_scan_kernel<GG, KB2_METRIC_IP, true, NTT><<<grid, NTT, smem, st>>>(sp);               \
-        else ivfpq_scan_kernel<GG, KB2_METRIC_IP, false, NTT><<<grid, NTT, smem, st>>>(sp);                    \
-    }
-#define KB2_LAUNCH_PQ(GG)                                     \
-    if (scan_nt == 512) { KB2_LAUNCH_PQ_NT(GG, 512) } else { KB2_LAUNCH_PQ_NT(GG, 256) }
-                const char* e_pf = getenv("KB2_SCAN_PREFETCH");
-                sp.flags = (e_pf ? atoi(e_pf) : KB2_DEFAULT_SCAN_PREFETCH) ? 2 : 0;
-                if (const char* e_fm = getenv("KB2_SCAN_FULLMERGE")) sp.flags |= atoi(e_fm) ? 4 : 0;
-                if (G == 1) { KB2_LAUNCH_PQ(1) } else if (G == 2) { KB2_LAUNCH_PQ(2) } else { KB2_LAUNCH_PQ(3) }
-#undef KB2_LAUNCH_PQ
-#undef KB2_LAUNCH_PQ_NT
-            } else {
-                const size_t smem = (size_t)M * 1024 + common_smem;
-                KB2_REQUIRE(smem <= (size_t)kMaxDynSmem, KB2_NOT_IMPLEMENTED, "IVF_PQ: m too large for the generic kernel");
-                if (metric == KB2_METRIC_L2)
-                    ivfpq_scan_generic_kernel<KB2_METRIC_L2><<<grid, kScanThreads, smem, st>>>(sp, codes.p);
-                else
-                    ivfpq_scan_generic_kernel<KB2_METRIC_IP><<<grid, kScanThreads, smem, st>>>(sp, codes.p);
-            }
+        const uint64_t* fin_partial = s_partial2.p;
+        int64_t fin_stride = (int64_t)nsplit * Ksel;
+        int fin_n = nsplit * Ksel;
+        const uint32_t *fin_counts = nullptr, *fin_flags = nullptr;
+        if (tc_engine) {
+            search_tc(sp, nq, nprobe, Ksel, k_base, dbits != nullptr);
+            fin_partial = s_cand.p;
+            fin_stride = kTcCandCap;
+            fin_n = kTcCandCap;
+            fin_counts = s_cand_cnt.p;
+            fin_flags = s_cand_cnt.p + nq;
         } else {
-            KB2_REQUIRE(dim % 4 == 0, KB2_NOT_IMPLEMENTED, "IVF_FLAT: dim must be a multiple of 4 on the GPU path");
-            if (metric == KB2_METRIC_L2)
-                ivfflat_scan_kernel<KB2_METRIC_L2><<<grid, kScanThreads, common_smem, st>>>(sp);
-            else
-                ivfflat_scan_kernel<KB2_METRIC_IP><<<grid, kScanThreads, common_smem, st>>>(sp);
+            launch_scan(sp, grid, Ksel, np_max, dbits != nullptr);
         }
         if (timing) KB2_CUDA_CHECK(cudaEventRecord(ev1, st));
-        last.launches++;
-        KB2_CUDA_CHECK(cudaGetLastError());
 
         // ---- finalize: merge CTA lists, optional exact refine, labels
         {
             FinalizeParams fp{};
-            fp.partial = s_partial2.p;
-            fp.partial_stride = (int64_t)nsplit * Ksel;
-            fp.n_partial = nsplit * Ksel;
+            fp.partial = fin_partial;
+            fp.partial_stride = fin_stride;
+            fp.n_partial = fin_n;
+            fp.counts = fin_counts;
+            fp.count_flags = fin_flags;
             fp.k_sel = k_base;
             fp.k_out = k;
             fp.rows = rows.p;
@@ -868,10 +1096,12 @@ struct IvfIndex : IndexBase {
             fp.out_dist = d_dist;
             launch_finalize(*this, fp, nq);
         }
-        unsigned long long hc[2] = {0, 0};
-        KB2_CUDA_CHECK(cudaMemcpyAsync(hc, d_counter.p, 16, cudaMemcpyDeviceToHost, st));
+        unsigned long long hc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        KB2_CUDA_CHECK(cudaMemcpyAsync(hc, d_counter.p, 64, cudaMemcpyDeviceToHost, st));
         results_out(nq, k, out_ids, out_dist, d_ids, d_dist);
-        KB2_REQUIRE(hc[1] == 0, KB2_INTERNAL_ERROR, "ivfpq_scan_kernel: unexpected shared-memory window base");
+        KB2_REQUIRE(hc[1] == 0 && hc[5] == 0, KB2_INTERNAL_ERROR, "ivfpq_scan_kernel: unexpected shared-memory window base");
+        last.survivors = (int64_t)hc[2];
+        last.flagged = (int64_t)hc[7];
         const unsigned long long scanned = hc[0];
         last.codes = (int64_t)scanned;
         last.code_bytes = (int64_t)scanned * (is_pq ? (int64_t)M : (int64_t)dim * 4);
@@ -916,6 +1146,7 @@ struct IvfIndex : IndexBase {
             KB2_REQUIRE(M > 0 && dim % M == 0 && nbits == 8, KB2_INVALID_ARGS, "IVF_PQ import: bad m / nbits");
             dsub = dim / M;
             pqc.alloc_exact((size_t)M * 256 * dsub);
+            tc_ready = false;
             KB2_CUDA_CHECK(cudaMemcpyAsync(pqc.p, pq_cent, (size_t)M * 256 * dsub * 4, cudaMemcpyDefault, stream));
         }
         KB2_CUDA_CHECK(cudaStreamSynchronize(stream));

@@ -60,6 +60,13 @@ struct IvfScanParams {
     const float* t1;           // [npad] or NULL
     unsigned long long* counters;  // [0] codes scanned (optional, NULL to skip)
     const int32_t* qperm;          // [nq] visiting order of the queries (NULL: identity)
+    int probe_stride;              // row stride of probe_ids/probe_dis (0: nprobe) — lets a pass scan only the first nprobe probes
+    int64_t partial_stride;        // entries between the output rows of consecutive queries (0: nsplit*kout)
+    const float* lut_global;       // [nq][G*4096] precomputed tables in the kernel's own enumeration ((g, j, m): m fastest), or NULL
+    const uint32_t* only_flagged;  // non-NULL selects the redo pass of the tensor-core engine: a small grid walks
+    const int32_t* flag_list;      //   the compacted list of flagged queries (flag_list[0..*flag_count)) x nsplit probe slices
+    const uint32_t* flag_count;
+    int clear_to;                  // the LAST probe slice fills its output with kEmpty from entry kout up to this entry count
     int flags;                     // bit1: software L2 prefetch of upcoming chunks; bit2: full-sort final merge (A/B switches)
 };
 
@@ -75,8 +82,9 @@ __device__ __forceinline__ int
 setup_probes(const IvfScanParams& p, int64_t q, int j0, int j1, ProbeSmem ps) {
     // serial prefix over <= a few hundred probes
     const int np = j1 - j0;
+    const int64_t pstride = p.probe_stride ? p.probe_stride : p.nprobe;
     for (int j = threadIdx.x; j < np; j += blockDim.x) {
-        const int64_t l = p.probe_ids[q * p.nprobe + j0 + j];
+        const int64_t l = p.probe_ids[q * pstride + j0 + j];
         int len = 0;
         uint32_t off = 0;
         if (l >= 0) {
@@ -85,7 +93,7 @@ setup_probes(const IvfScanParams& p, int64_t q, int j0, int j1, ProbeSmem ps) {
         }
         ps.len[j] = len;
         ps.off[j] = off;
-        const float dv = p.probe_dis[q * p.nprobe + j0 + j];
+        const float dv = p.probe_dis[q * pstride + j0 + j];
         ps.dis0[j] = (p.metric == KB2_METRIC_L2) ? dv : -dv;
     }
     __syncthreads();
@@ -140,9 +148,9 @@ struct PqStage {
     bool valid;     // stage holds a chunk (warp-uniform)
 };
 
-template <int G, int METRIC, bool HAS_BITSET, int NT, int NACC = 2>
-__global__ void __launch_bounds__(NT, G == 1 ? (NT == 512 ? 2 : 3) : 1)
-ivfpq_scan_kernel(IvfScanParams p) {
+template <int G, int METRIC, bool HAS_BITSET, int NT, int NACC>
+__device__ __forceinline__ void
+ivfpq_scan_body(const IvfScanParams& p, const int64_t bq, const int split) {
     constexpr int NW = NT / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char* lut = smem_raw;
@@ -158,9 +166,7 @@ ivfpq_scan_kernel(IvfScanParams p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // queries are visited in the order given by qperm (sorted by nearest list => CTAs that run
     // together probe the same lists and hit them in L2)
-    const int64_t bq = blockIdx.x / p.nsplit;
     const int64_t q = p.qperm ? (int64_t)p.qperm[bq] : bq;
-    const int split = blockIdx.x % p.nsplit;
     const int j0 = min(p.nprobe, split * np_max), j1 = min(p.nprobe, j0 + np_max);
     const int np = j1 - j0;
     if ((uint32_t)__cvta_generic_to_shared(smem_raw) != (uint32_t)KB2_SMEM_BASE) {
@@ -192,6 +198,14 @@ ivfpq_scan_kernel(IvfScanParams p) {
             // e enumerates (group g, code value j, sub-quantizer-in-group mm): mm fastest, then j
             const int j = (e >> 4) & 255;
             const int g = e >> 12;
+            if (p.lut_global) {
+                // tables of the whole batch were built by pqtc::lut_build_kernel (same fma chain): coalesced copy
+                const float v = __ldg(p.lut_global + (int64_t)q * (p.M * 256) + e);
+                float* row = (float*)(lut + (size_t)g * 65536 + (size_t)j * 256);
+#pragma unroll
+                for (int r = 0; r < 4; r++) row[mm + 16 * (r ^ half)] = v;
+                continue;
+            }
             const int m = g * 16 + mm;
             const float* c = p.pq_centroids + ((int64_t)m * 256 + j) * dsub;
             const float* qs = s_q + m * dsub;
@@ -339,7 +353,10 @@ ivfpq_scan_kernel(IvfScanParams p) {
         fetch(s3);
     }
 
-    uint64_t* out = p.partial + ((int64_t)q * p.nsplit + split) * p.kout;
+    uint64_t* out = p.partial_stride ? p.partial + (int64_t)q * p.partial_stride + (int64_t)split * p.kout
+                                     : p.partial + ((int64_t)q * p.nsplit + split) * p.kout;
+    if (split == p.nsplit - 1)   // only the last slice clears the rest of the row
+        for (int i = p.kout + threadIdx.x; i < p.clear_to; i += blockDim.x) out[i] = kEmpty;
     tk.finish(lane);
     __syncthreads();
     if (p.flags & 4) {
@@ -347,6 +364,25 @@ ivfpq_scan_kernel(IvfScanParams p) {
     } else {
         block_emit_topk_bounded(lists, p.K, NW, *sh_V_final, merge_tmp, 4 * p.K, merge_ctr, out, p.kout);
     }
+}
+
+template <int G, int METRIC, bool HAS_BITSET, int NT, int NACC = 2>
+__global__ void __launch_bounds__(NT, G == 1 ? (NT == 512 ? 2 : 3) : 1)
+ivfpq_scan_kernel(IvfScanParams p) {
+    if (p.only_flagged) {
+        // redo pass of the tensor-core engine: a small grid walks the (query, probe slice) units and scans only the
+        // flagged queries (every iteration is self-contained; the barrier keeps a fast warp out of the next unit's smem)
+        const int64_t units = (int64_t)(*p.flag_count) * p.nsplit;
+        for (int64_t w = blockIdx.x; w < units; w += gridDim.x) {
+            const int64_t bq = p.flag_list[w / p.nsplit];
+            const int split = (int)(w % p.nsplit);
+            if (threadIdx.x == 0 && split == 0 && p.counters) atomicAdd(p.counters + 3, 1ull);   // queries redone by this pass
+            ivfpq_scan_body<G, METRIC, HAS_BITSET, NT, NACC>(p, bq, split);
+            __syncthreads();
+        }
+        return;
+    }
+    ivfpq_scan_body<G, METRIC, HAS_BITSET, NT, NACC>(p, (int64_t)(blockIdx.x / p.nsplit), (int)(blockIdx.x % p.nsplit));
 }
 
 // =====================================================================================

@@ -1,0 +1,890 @@
+// kb2_ivfpq_tc.cuh — list-major tensor-core engine of the IVF_PQ scan (large batches).
+//
+// Reference path being replaced: IVFPQScanner::scan_list_with_table (one table look-up chain per
+// (query, code) pair; F/impl/pq_code_distance/IVFPQScanner_impl.h:110-185) under
+// IndexIVF::search_preassigned (F/IndexIVF.cpp:401-768).
+//
+// Why a second engine.  The query-major LUT kernel (kb2_ivf.cuh) is bound by the shared-memory gather pipe:
+// 16 wavefronts per 32 codes *per query* (profiles/r1_final_scan_kernel.md).  But the ADC inner term is a dot
+// product, <q, r^(code)>, and at batch 10^4 x nprobe 64 every list is probed by ~150 queries.  Decoding a
+// 128-code tile ONCE into bf16 and contracting it with all the queries of the list on tcgen05 replaces
+// 16 gathers per (query, code) by 16 gathers per code + 128 x N x 128 MACs on the tensor pipe.
+//
+// Exactness.  The tensor-core value S' is only a FILTER.  With u = 2^-8 (bf16 round-to-nearest),
+//     |S' - <q,r^>| <= (2u + u^2) |q| |r^| + (fp32 accumulation) <= 0.0085 |q| Rmax,   Rmax^2 = sum_m max_j |c_pq[m][j]|^2
+// so with a per-query upper bound B_q of the K-th best key (taken from a LUT scan of the query's nearest lists,
+// "phase A") every code with   key' <= B_q + |alpha| * 0.0085 |q| Rmax   is a *survivor*; survivors are
+// re-evaluated with exactly the fp32 operations (and summation order) of the LUT kernel and kept when
+// key <= B_q.  The final top-K is the same set with the same keys as the LUT engine returns
+// (tests/test_ivf_gpu.py::test_ivfpq_tc_engine_matches_lut_engine).  Queries whose bound is missing (fewer
+// than K codes in their nearest lists) or whose survivor buffer overflows are flagged and redone by the LUT kernel.
+//
+// sm_100a mapping (one persistent CTA per SM, 288 threads):
+//   warps 0-7  decoders : (two groups of 4 warps, one per A buffer, so two tiles are decoded concurrently)
+//                         code tile -> A operand [128 codes x 128 dims] bf16 in the no-swizzle K-major UMMA
+//                         layout (16-byte sub-vector of sub-quantizer m = one core-matrix row), via a 64 KB bf16
+//                         copy of the PQ codebooks in shared memory; also stage the B operand (bf16 queries of the
+//                         item, gathered by index) and the per-column thresholds.
+//   warp  16   MMA      : 8 x tcgen05.mma.kind::f16 (M=128, N=16..256, K=16) per tile into one of two 256-column
+//                         TMEM accumulators; tcgen05.commit releases the A buffer and publishes the accumulator.
+//   warps 8-15 epilogue : (two groups of 4 warps, one per accumulator) tcgen05.ld (32 lanes x 32 columns, double-buffered in registers), 2 instructions per
+//                         (code, query) pair (FADD threshold + FSETP), survivors -> one shared-memory slot
+//                         reservation per thread and tile -> CTA-private survivor log in global memory (plain
+//                         coalesced stores, nothing on the critical path waits for a global round trip).
+// Then: scatter_survivors_kernel groups the log by query, exact_eval_kernel recomputes the survivors' keys in fp32.
+// Work item = (list, chunk of <= 256 of the queries probing it); items are laid out by a single-CTA plan kernel
+// from the coarse result (count -> scan -> fill).
+#pragma once
+#include <cuda_bf16.h>
+
+#include <cub/block/block_scan.cuh>
+
+#include "kb2_gemm_tc.cuh"
+#include "kb2_ivf.cuh"
+
+namespace kb2 {
+namespace pqtc {
+
+constexpr int TM = 128;        // codes per tile (UMMA M)
+constexpr int NQT = 256;       // queries per item (UMMA N max)
+constexpr int KD = 128;        // dimensions (UMMA K total) — the engine is specialised to d=128, m=16, dsub=8
+constexpr int THREADS = 544;          // warps 0-7 decoders (2 groups), 8-15 epilogue (2 groups), 16 MMA
+constexpr int GROUP_THREADS = 128;
+constexpr int MMA_WARP = 16;
+constexpr int TAB_BYTES = 65536, A_BYTES = 32768, B_BYTES = 65536;
+constexpr int META_BYTES = 4 * NQT * 4;   // h | (unused) | base | qidx
+constexpr int QREG = 1024;                // survivor-queue entries per region (two regions)
+constexpr int OFF_TAB = 0;
+constexpr int OFF_A = TAB_BYTES;
+constexpr int OFF_B = OFF_A + 2 * A_BYTES;
+constexpr int OFF_META = OFF_B + B_BYTES;
+constexpr int OFF_QUEUE = OFF_META + 2 * META_BYTES;
+constexpr int OFF_BAR = OFF_QUEUE + 2 * QREG * 8;
+constexpr size_t SMEM_BYTES = OFF_BAR + 256 + 128 /*alignment slack*/;
+constexpr float kErrCoef = 0.0085f;       // (2u + u^2) for bf16 operands + fp32 accumulation slack
+
+struct Params {
+    int metric;
+    int nq, nprobe;
+    const float* queries;          // [nq][128] fp32
+    const __nv_bfloat16* qb16;     // [nq][128]
+    const float* qnorm;            // [nq]
+    // plan
+    const int32_t* n_items;        // device scalar
+    const int32_t* item_list;      // [items]
+    const int32_t* item_q0;        // [items] first pair of the chunk
+    const int32_t* item_nq;        // [items]
+    const int32_t* pair_q;         // [pairs] query index, grouped by list
+    const float* pair_base;        // [pairs] key base: L2 |q-c|^2, IP -<q,c>
+    // per-query bound from phase A
+    const uint64_t* bound_rows;    // [nq][bound_stride] sorted packed (key,pos) rows
+    int64_t bound_stride;
+    int k_need;
+    float margin_coef;             // |alpha| * kErrCoef * Rmax  (multiplied by |q|)
+    // index
+    const int64_t* list_off;
+    const int32_t* list_len;
+    const uint4* codes;            // [npad]
+    int64_t npad;
+    const float* t1;               // [npad] (L2)
+    const float* pqc;              // [16][256][8] fp32
+    const uint4* pqc16;            // [16][256] x 8 bf16
+    const uint8_t* bitset;
+    const int32_t* rows;
+    // output
+    uint4* log;                    // [2*gridDim.x + 1][log_cap] survivors {query, position, key base bits, 0}: one log per
+                                   // epilogue group, the last one shared by all for tiles that overflow the smem queue
+    uint32_t* log_cnt;             // [2*gridDim.x] entries per private log; [2G] cursor of the shared log;
+                                   // [2G + 1] = 1 when any log overflowed; [2G + 2..3] diagnostics
+    uint32_t log_cap;              // entries per private log
+    uint32_t shared_cap;           // entries of the shared log
+    uint32_t* qflag;               // [nq] 1: redo this query with the LUT kernel
+    unsigned long long* counters;  // [0] codes scanned (pairs x codes), [2] survivors re-evaluated, [3] flagged
+};
+
+__device__ __forceinline__ bool
+mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug must end the launch with an error, never hang the GPU
+__device__ __forceinline__ void
+mbar_wait_g(uint32_t bar, uint32_t parity) {
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try(bar, parity)) {
+        if (clock64() - t0 > 6000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void
+bar_sync_epi() {
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+}
+// UMMA shared-memory descriptor, K-major, no swizzle: core matrix = 8 rows x 16 B (128 B contiguous);
+// LBO = distance between the two core matrices of one K=16 step (128 B), SBO = distance between 8-row groups (2048 B)
+__device__ __forceinline__ uint64_t
+make_desc_ns(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(128 >> 4) << 16;
+    d |= (uint64_t)(2048 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// instruction descriptor: D=f32, A=B=bf16, K-major, M=128, N=n
+__device__ __forceinline__ uint32_t
+make_idesc_bf16(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+__device__ __forceinline__ void
+mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(THREADS, 1)
+ivfpq_tc_filter_kernel(Params p) {
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t raw = tc::smem_u32(smem_dyn);
+    const uint32_t base = (raw + 127u) & ~127u;
+    unsigned char* sm = smem_dyn + (base - raw);
+    const uint32_t bars = base + OFF_BAR;
+    // barriers: a_full[2] a_empty[2] acc_full[2] acc_empty[2] b_full b_free meta_full[2] meta_free[2]
+    auto bar_a_full = [&](int i) { return bars + 8u * i; };
+    auto bar_a_empty = [&](int i) { return bars + 8u * (2 + i); };
+    auto bar_acc_full = [&](int i) { return bars + 8u * (4 + i); };
+    auto bar_acc_empty = [&](int i) { return bars + 8u * (6 + i); };
+    const uint32_t bar_b_full = bars + 8u * 8, bar_b_free = bars + 8u * 9;
+    auto bar_meta_full = [&](int i) { return bars + 8u * (10 + i); };
+    auto bar_meta_free = [&](int i) { return bars + 8u * (12 + i); };
+    const uint32_t tmem_slot = bars + 8u * 14;
+    volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(sm + OFF_BAR + 8 * 14);
+    uint32_t* qcnt = (uint32_t*)(sm + OFF_BAR + 8 * 15);   // survivor counters: [epilogue group][own tile parity]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_items = *p.n_items;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; i++) {
+            tc::mbar_init(bar_a_full(i), GROUP_THREADS);
+            tc::mbar_init(bar_a_empty(i), 1);
+            tc::mbar_init(bar_acc_full(i), 1);
+            tc::mbar_init(bar_acc_empty(i), GROUP_THREADS);
+            tc::mbar_init(bar_meta_full(i), 2 * GROUP_THREADS);
+            tc::mbar_init(bar_meta_free(i), 2 * GROUP_THREADS);
+        }
+        tc::mbar_init(bar_b_full, 2 * GROUP_THREADS);
+        tc::mbar_init(bar_b_free, 1);
+        qcnt[0] = qcnt[1] = qcnt[2] = qcnt[3] = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // bf16 codebooks -> shared memory
+    {
+        uint4* tab = (uint4*)(sm + OFF_TAB);
+        for (int i = threadIdx.x; i < TAB_BYTES / 16; i += THREADS) tab[i] = __ldg(p.pqc16 + i);
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    const float inv_alpha = (METRIC == KB2_METRIC_L2) ? 0.5f : 1.f;
+
+    if (warp < 8) {
+        // =========================== decoders: two groups of 4 warps, group d owns A buffer d (tiles g % 2 == d) =========
+        const int dt = threadIdx.x;    // 0..255
+        const int dg = dt >> 7;        // group
+        const int tid = dt & 127;      // code row inside the tile
+        const uint4* tab = (const uint4*)(sm + OFF_TAB);
+        // per-column thresholds of one item -> meta buffer (it & 1), one column per decoder thread; written one item
+        // AHEAD of its use so that the dependent global loads (pair -> bound row, norm) stay off the critical path
+        auto write_meta = [&](int item, int it) {
+            const int par = it & 1;
+            mbar_wait_g(bar_meta_free(par), (((uint32_t)it >> 1) & 1u) ^ 1u);
+            const int q0 = p.item_q0[item];
+            const int nqi = p.item_nq[item];
+            float* m_h = (float*)(sm + OFF_META + par * META_BYTES);
+            float* m_base = m_h + 2 * NQT;
+            int* m_q = (int*)(m_base + NQT);
+            const int j = dt;
+            float h = -INFINITY, bs = 0.f;
+            int q = -1;
+            if (j < nqi) {
+                q = p.pair_q[q0 + j];
+                bs = p.pair_base[q0 + j];
+                const uint64_t e = p.bound_rows[(int64_t)q * p.bound_stride + p.k_need - 1];
+                if (e == kEmpty) {
+                    p.qflag[q] = 1u;   // no bound: the LUT kernel redoes this query
+                    if (p.counters) atomicAdd(p.counters + 6, 1ull << 32);
+                } else {
+                    const float bnd = unpack_key(e);
+                    const float margin = p.margin_coef * p.qnorm[q] * 1.01f + 1e-30f;
+                    h = (bnd + margin - bs) * inv_alpha;
+                }
+            }
+            m_h[j] = h;
+            m_base[j] = bs;
+            m_q[j] = q;
+            tc::mbar_arrive(bar_meta_full(par));
+        };
+        uint32_t g0 = 0;   // global tile counter at the start of the item
+        int it = 0;
+        if ((int)blockIdx.x < n_items) write_meta(blockIdx.x, 0);
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
+            const int l = p.item_list[item];
+            const int nqi = p.item_nq[item];
+            const int nmma = (nqi + 15) & ~15;
+            const int len = p.list_len[l];
+            const int64_t off = p.list_off[l];
+            const int ntiles = (len + TM - 1) / TM;
+            const int par = it & 1;
+            const int t_first = (int)((dg - (int)(g0 & 1u)) & 1);   // this group's first tile of the item
+            uint4 w_next = make_uint4(0, 0, 0, 0);
+            if (t_first < ntiles && off + (int64_t)t_first * TM + tid < p.npad)
+                w_next = ldg_stream_u4(p.codes + off + (int64_t)t_first * TM + tid);
+            auto decode_tile = [&](int t) {
+                const uint32_t g = g0 + (uint32_t)t;      // g & 1 == dg
+                const uint4 w = w_next;
+                {
+                    const int64_t pn = off + (int64_t)(t + 2) * TM + tid;
+                    if (t + 2 < ntiles && pn < p.npad) w_next = ldg_stream_u4(p.codes + pn);
+                }
+                mbar_wait_g(bar_a_empty(dg), ((g >> 1) & 1u) ^ 1u);
+                unsigned char* A = sm + OFF_A + dg * A_BYTES + (tid >> 3) * 2048 + (tid & 7) * 16;
+                const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+                uint4 v[16];
+#pragma unroll
+                for (int s = 0; s < 16; s++) {           // all 16 gathers in flight before the first store
+                    const uint32_t byte = (ww[s >> 2] >> (8 * (s & 3))) & 255u;
+                    v[s] = tab[((s + tid) & 15) * 256 + byte];   // pos % 16 == tid % 16 (list_off, tile starts: multiples of 16)
+                }
+#pragma unroll
+                for (int s = 0; s < 16; s++) *reinterpret_cast<uint4*>(A + ((s + tid) & 15) * 128) = v[s];
+                tc::fence_proxy_async();
+                tc::mbar_arrive(bar_a_full(dg));
+            };
+            // the first tile of each group only needs a free A buffer: decode it while the tensor pipe still works on
+            // the previous item, then stage the B operand (which must wait for that item's last MMA)
+            if (t_first < ntiles) decode_tile(t_first);
+            // ---- B operand: the item's queries (bf16) gathered by index with cp.async, K-major no-swizzle layout
+            asm volatile("bar.sync 2, 256;" ::: "memory");          // meta[par] (query indices) written by all decoders
+            mbar_wait_g(bar_b_free, ((uint32_t)it & 1u) ^ 1u);
+            {
+                const int* m_q = (const int*)(sm + OFF_META + par * META_BYTES) + 3 * NQT;
+                const uint32_t Bs = base + OFF_B;
+                unsigned char* B = sm + OFF_B;
+                const int kc = tid >> 3;        // 16-byte chunk along K (0..15)
+                const int rsub = tid & 7;
+                for (int blk = dg; blk < nmma / 8; blk += 2) {
+                    const int row = blk * 8 + rsub;
+                    const int q = m_q[row];
+                    const uint32_t dst = (uint32_t)(blk * 2048 + kc * 128 + rsub * 16);
+                    if (q >= 0) {
+                        const void* src = reinterpret_cast<const uint4*>(p.qb16 + (int64_t)q * KD) + kc;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(Bs + dst), "l"(src) : "memory");
+                    } else {
+                        *reinterpret_cast<uint4*>(B + dst) = make_uint4(0, 0, 0, 0);
+                    }
+                }
+                asm volatile("cp.async.wait_all;" ::: "memory");
+            }
+            tc::fence_proxy_async();
+            tc::mbar_arrive(bar_b_full);
+            // thresholds of the NEXT item (other meta buffer)
+            if (item + (int)gridDim.x < n_items) write_meta(item + gridDim.x, it + 1);
+            // ---- this group's remaining tiles
+            for (int t = t_first + 2; t < ntiles; t += 2) decode_tile(t);
+            g0 += (uint32_t)ntiles;
+        }
+    } else if (warp == MMA_WARP) {
+        // =========================== MMA issuer ===========================
+        uint32_t g = 0;
+        int it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
+            const int l = p.item_list[item];
+            const int nqi = p.item_nq[item];
+            const int nmma = (nqi + 15) & ~15;
+            const int ntiles = (p.list_len[l] + TM - 1) / TM;
+            const uint32_t idesc = make_idesc_bf16(nmma);
+            mbar_wait_g(bar_b_full, (uint32_t)it & 1u);
+            for (int t = 0; t < ntiles; t++, g++) {
+                const int buf = g & 1;
+                mbar_wait_g(bar_a_full(buf), (g >> 1) & 1u);
+                mbar_wait_g(bar_acc_empty(buf), ((g >> 1) & 1u) ^ 1u);
+                tc::tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a0 = base + OFF_A + buf * A_BYTES;
+                    const uint32_t b0 = base + OFF_B;
+                    const uint32_t d = tmem_base + (uint32_t)buf * 256u;
+#pragma unroll
+                    for (int ks = 0; ks < KD / 16; ks++)
+                        mma_bf16(d, make_desc_ns(a0 + ks * 256), make_desc_ns(b0 + ks * 256), idesc, ks > 0 ? 1u : 0u);
+                    tc::tc_commit(bar_a_empty(buf));
+                    tc::tc_commit(bar_acc_full(buf));
+                }
+                __syncwarp();
+            }
+            if (lane == 0) tc::tc_commit(bar_b_free);
+            __syncwarp();
+        }
+    } else {
+        // =========================== epilogue: two groups of 4 warps, group e owns accumulator e (tiles g % 2 == e) ======
+        const int et = threadIdx.x - 256;        // 0..255
+        const int eg = et >> 7;                  // group
+        const int e = et & 127;                  // thread inside the group
+        const int we = warp & 3;                 // TMEM lane quarter (== warp % 4)
+        const int row = we * 32 + lane;          // code row inside the tile
+        uint64_t* my_q = (uint64_t*)(sm + OFF_QUEUE) + eg * QREG;
+        const uint32_t n_logs = 2u * gridDim.x;  // private logs; log n_logs is the shared one
+        uint4* my_log = p.log + (size_t)(2 * blockIdx.x + eg) * p.log_cap;
+        uint4* shared_log = p.log + (size_t)n_logs * p.log_cap;
+        uint32_t log_off = 0;
+        bool log_over = false;
+        unsigned long long n_codes = 0;
+        uint32_t g0 = 0, k_own = 0;
+        int it = 0;
+#define KB2_TMEM_LD32(V, TADDR)                                                                                          \
+    asm volatile(                                                                                                        \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                        \
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"                                                        \
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"                                       \
+        : "=r"(V[0]), "=r"(V[1]), "=r"(V[2]), "=r"(V[3]), "=r"(V[4]), "=r"(V[5]), "=r"(V[6]), "=r"(V[7]), "=r"(V[8]),    \
+          "=r"(V[9]), "=r"(V[10]), "=r"(V[11]), "=r"(V[12]), "=r"(V[13]), "=r"(V[14]), "=r"(V[15]), "=r"(V[16]),         \
+          "=r"(V[17]), "=r"(V[18]), "=r"(V[19]), "=r"(V[20]), "=r"(V[21]), "=r"(V[22]), "=r"(V[23]), "=r"(V[24]),        \
+          "=r"(V[25]), "=r"(V[26]), "=r"(V[27]), "=r"(V[28]), "=r"(V[29]), "=r"(V[30]), "=r"(V[31])                      \
+        : "r"(TADDR))
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
+            const int l = p.item_list[item];
+            const int nqi = p.item_nq[item];
+            const int nmma = (nqi + 15) & ~15;
+            const int nch = (nmma + 31) >> 5;    // 32-column chunks (a 16-column tail reads columns whose h is -inf)
+            const int len = p.list_len[l];
+            const int64_t off = p.list_off[l];
+            const int ntiles = (len + TM - 1) / TM;
+            const int par = it & 1;
+            mbar_wait_g(bar_meta_full(par), ((uint32_t)it >> 1) & 1u);
+            const float* m_h = (const float*)(sm + OFF_META + par * META_BYTES);
+            const float* m_base = m_h + 2 * NQT;
+            const int* m_q = (const int*)(m_base + NQT);
+            if (et == 0) n_codes += (unsigned long long)len * (unsigned long long)nqi;
+            const int t_first = (int)((eg - (int)(g0 & 1u)) & 1);
+            float t1_next = 0.f;
+            if (METRIC == KB2_METRIC_L2 && t_first * TM + row < len) t1_next = __ldg(p.t1 + off + t_first * TM + row);
+            for (int t = t_first; t < ntiles; t += 2, k_own++) {
+                const uint32_t g = g0 + (uint32_t)t;   // g & 1 == eg
+                uint32_t* my_cnt = qcnt + eg * 2 + (k_own & 1u);
+                mbar_wait_g(bar_acc_full(eg), (g >> 1) & 1u);
+                tc::tc_fence_after();
+                const int rel = t * TM + row;
+                float r = INFINITY;
+                if (rel < len) r = (METRIC == KB2_METRIC_L2) ? 0.5f * t1_next : 0.f;
+                if (METRIC == KB2_METRIC_L2 && rel + 2 * TM < len) t1_next = __ldg(p.t1 + off + rel + 2 * TM);   // next own tile
+                const uint32_t taddr0 = tmem_base + ((uint32_t)(we * 32) << 16) + (uint32_t)(eg * 256);
+                uint32_t masks[8];
+                uint32_t va[32];
+                // pass  <=>  S' + h_col >= r_row
+                auto scan_chunk = [&](const uint32_t (&v)[32], int ci) -> uint32_t {
+                    const float4* h4 = reinterpret_cast<const float4*>(m_h + ci * 32);
+                    bool any = false;
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const float4 hv = h4[u];
+                        any |= (__uint_as_float(v[4 * u + 0]) + hv.x >= r);
+                        any |= (__uint_as_float(v[4 * u + 1]) + hv.y >= r);
+                        any |= (__uint_as_float(v[4 * u + 2]) + hv.z >= r);
+                        any |= (__uint_as_float(v[4 * u + 3]) + hv.w >= r);
+                    }
+                    uint32_t m = 0;
+                    if (any) {
+#pragma unroll
+                        for (int u = 0; u < 32; u++) m |= (__uint_as_float(v[u]) + m_h[ci * 32 + u] >= r) ? (1u << u) : 0u;
+                    }
+                    return m;
+                };
+#pragma unroll
+                for (int ci = 0; ci < 8; ci++) {
+                    masks[ci] = 0;
+                    if (ci < nch) {   // (the other epilogue group works on the other accumulator meanwhile)
+                        KB2_TMEM_LD32(va, taddr0 + (uint32_t)(ci * 32));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        masks[ci] = scan_chunk(va, ci);
+                    }
+                }
+                tc::tc_fence_before();
+                tc::mbar_arrive(bar_acc_empty(eg));
+                // ---- survivors of this thread's row: one slot reservation in the group's queue (and one in the shared
+                //      global log for what does not fit), then plain stores
+                uint32_t total = 0;
+#pragma unroll
+                for (int ci = 0; ci < 8; ci++) total += __popc(masks[ci]);
+                if (total) {
+                    const uint32_t slot = atomicAdd(my_cnt, total);
+                    const uint32_t n_in = slot < (uint32_t)QREG ? min(total, (uint32_t)QREG - slot) : 0u;
+                    uint32_t gslot = 0;
+                    if (n_in < total) {
+                        gslot = atomicAdd(p.log_cnt + n_logs, total - n_in);
+                        if (p.counters) atomicAdd(p.counters + 3, (unsigned long long)(total - n_in));
+                    }
+                    uint32_t i = 0;
+#pragma unroll
+                    for (int ci = 0; ci < 8; ci++) {
+                        uint32_t m = masks[ci];
+                        while (m) {
+                            const int u = __ffs(m) - 1;
+                            m &= m - 1;
+                            const int col = ci * 32 + u;
+                            if (i < n_in) {
+                                my_q[slot + i] = ((uint64_t)col << 32) | (uint32_t)rel;
+                            } else {
+                                const uint32_t s2 = gslot + (i - n_in);
+                                if (s2 < p.shared_cap) {
+                                    uint4 o;
+                                    o.x = (uint32_t)m_q[col];
+                                    o.y = (uint32_t)(off + rel);
+                                    o.z = __float_as_uint(m_base[col]);
+                                    o.w = 0u;
+                                    shared_log[s2] = o;
+                                } else {
+                                    p.log_cnt[n_logs + 1] = 1u;
+                                }
+                            }
+                            i++;
+                        }
+                    }
+                }
+                // ---- flush the group's queue to its survivor log (fire-and-forget stores)
+                if (eg == 0) asm volatile("bar.sync 3, 128;" ::: "memory"); else asm volatile("bar.sync 4, 128;" ::: "memory");
+                const uint32_t n_raw = *my_cnt;
+                const uint32_t n = min(n_raw, (uint32_t)QREG);
+                if (e == 0 && n_raw > (uint32_t)QREG) {   // diagnostics: overflowing tiles, their largest push count
+                    atomicAdd(p.log_cnt + n_logs + 2, 1u);
+                    atomicMax(p.log_cnt + n_logs + 3, n_raw);
+                }
+                if (log_off + n > p.log_cap) {
+                    log_over = true;
+                } else {
+                    for (uint32_t i = e; i < n; i += GROUP_THREADS) {
+                        const uint64_t ent = my_q[i];
+                        const int col = (int)(ent >> 32);
+                        uint4 o;
+                        o.x = (uint32_t)m_q[col];
+                        o.y = (uint32_t)(off + (int64_t)(uint32_t)ent);
+                        o.z = __float_as_uint(m_base[col]);
+                        o.w = 0u;
+                        my_log[log_off + i] = o;
+                    }
+                    log_off += n;
+                }
+                if (eg == 0) asm volatile("bar.sync 3, 128;" ::: "memory"); else asm volatile("bar.sync 4, 128;" ::: "memory");
+                if (e == 0) *my_cnt = 0;   // next used two own tiles later, i.e. after the next pair of barriers
+            }
+            tc::mbar_arrive(bar_meta_free(par));
+            g0 += (uint32_t)ntiles;
+        }
+#undef KB2_TMEM_LD32
+        if (e == 0) {
+            p.log_cnt[2 * blockIdx.x + eg] = log_off;
+            if (log_over) p.log_cnt[n_logs + 1] = 1u;
+            if (p.counters) atomicAdd(p.counters + 2, (unsigned long long)log_off);
+        }
+        if (et == 0 && p.counters) atomicAdd(p.counters, n_codes);
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        tc::tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------- plan: (query, probe) pairs grouped by list
+__global__ void
+count_pairs_kernel(const int64_t* __restrict__ probe_ids, int64_t npairs, const int32_t* __restrict__ list_len,
+                   int32_t* __restrict__ lcount) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npairs) return;
+    const int64_t l = probe_ids[i];
+    if (l >= 0 && list_len[l] > 0) atomicAdd(lcount + l, 1);
+}
+
+// one CTA: exclusive scans over the lists -> first pair of each list, item table (list, query chunk)
+__global__ void __launch_bounds__(1024)
+plan_kernel(const int32_t* __restrict__ lcount, int nlist, int32_t* __restrict__ lstart, int32_t* __restrict__ item_list,
+            int32_t* __restrict__ item_q0, int32_t* __restrict__ item_nq, int32_t* __restrict__ n_items) {
+    typedef cub::BlockScan<int, 1024> Scan;
+    __shared__ typename Scan::TempStorage tmp_a, tmp_b;
+    __shared__ int carry_a, carry_b;
+    if (threadIdx.x == 0) carry_a = carry_b = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < nlist; b0 += 1024) {
+        const int l = b0 + threadIdx.x;
+        const int c = l < nlist ? lcount[l] : 0;
+        const int nch = (c + NQT - 1) / NQT;
+        int ex_a, ex_b, tot_a, tot_b;
+        Scan(tmp_a).ExclusiveSum(c, ex_a, tot_a);
+        Scan(tmp_b).ExclusiveSum(nch, ex_b, tot_b);
+        const int ca = carry_a, cb = carry_b;
+        if (l < nlist) {
+            lstart[l] = ca + ex_a;
+            if (nch > 0) {
+                // even chunks, multiples of 16 queries (the UMMA N granularity)
+                const int per = ((c + nch - 1) / nch + 15) & ~15;
+                for (int ch = 0; ch < nch; ch++) {
+                    const int i = cb + ex_b + ch;
+                    item_list[i] = l;
+                    item_q0[i] = ca + ex_a + ch * per;
+                    item_nq[i] = max(0, min(per, c - ch * per));
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            carry_a = ca + tot_a;
+            carry_b = cb + tot_b;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_items = carry_b;
+}
+
+__global__ void
+fill_pairs_kernel(const int64_t* __restrict__ probe_ids, const float* __restrict__ probe_dis, int64_t npairs, int nprobe,
+                  int metric, const int32_t* __restrict__ list_len, const int32_t* __restrict__ lstart,
+                  int32_t* __restrict__ lcursor, int32_t* __restrict__ pair_q, float* __restrict__ pair_base) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npairs) return;
+    const int64_t l = probe_ids[i];
+    if (l < 0 || list_len[l] <= 0) return;
+    const int slot = lstart[l] + atomicAdd(lcursor + l, 1);
+    pair_q[slot] = (int32_t)(i / nprobe);
+    const float dv = probe_dis[i];
+    pair_base[slot] = (metric == KB2_METRIC_L2) ? dv : -dv;
+}
+
+// bf16 copy + norm of the queries (warp per query, d = 128)
+__global__ void
+prepare_queries_kernel(const float* __restrict__ q, int64_t nq, __nv_bfloat16* __restrict__ qb16, float* __restrict__ qnorm) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= nq) return;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(q + w * KD) + lane);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&lo);
+    o.y = *reinterpret_cast<uint32_t*>(&hi);
+    reinterpret_cast<uint2*>(qb16 + w * KD)[lane] = o;
+    float s = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    s = warp_sum(s);
+    if (lane == 0) qnorm[w] = sqrtf(s) * 1.0001f;
+}
+
+// bf16 copy of the PQ codebooks [16][256][8] + max_j |c[m][j]|^2 per sub-quantizer (grid = 16, block = 256)
+__global__ void __launch_bounds__(256)
+prepare_tables_kernel(const float* __restrict__ pqc, __nv_bfloat16* __restrict__ pqc16, float* __restrict__ maxn2) {
+    const int m = blockIdx.x, j = threadIdx.x;
+    const float* c = pqc + ((size_t)m * 256 + j) * 8;
+    float n2 = 0.f;
+    __nv_bfloat16* o = pqc16 + ((size_t)m * 256 + j) * 8;
+    for (int t = 0; t < 8; t++) {
+        n2 = fmaf(c[t], c[t], n2);
+        o[t] = __float2bfloat16_rn(c[t]);
+    }
+    __shared__ float red[256];
+    red[j] = n2;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (j < s) red[j] = fmaxf(red[j], red[j + s]);
+        __syncthreads();
+    }
+    if (j == 0) maxn2[m] = red[0];
+}
+
+// survivors of all CTA logs -> per-query rows (thread per log entry; grid = (x, number of logs))
+__global__ void
+scatter_survivors_kernel(const uint4* __restrict__ log, const uint32_t* __restrict__ log_cnt, uint32_t log_cap,
+                         uint32_t shared_cap, uint64_t* __restrict__ cand, uint32_t* __restrict__ cand_cnt, int cap, uint32_t* __restrict__ qflag,
+                         unsigned long long* __restrict__ counters) {
+    const uint32_t n = min(log_cnt[blockIdx.y], blockIdx.y + 1 == gridDim.y ? shared_cap : log_cap);   // last log = shared one
+    const uint4* src = log + (size_t)blockIdx.y * log_cap;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint4 e = src[i];
+        const uint32_t slot = atomicAdd(cand_cnt + e.x, 1u);
+        if (slot < (uint32_t)cap) cand[(int64_t)e.x * cap + slot] = ((uint64_t)e.z << 32) | e.y;   // (key base bits, position)
+        else {
+            qflag[e.x] = 1u;
+            if (counters) atomicAdd(counters + 6, 1ull);
+        }
+    }
+}
+
+// Per-query ADC tables for the whole batch:  lut[q][j*16 + m] = scale * <q_m, c_pq[m][j]>  (scale -2 for L2, -1 for IP),
+// each entry the same 8-term fma chain the LUT kernel uses when it builds its table itself, so every consumer
+// (phase A, the exact re-evaluation, the LUT kernel's copy-in mode) sees bit-identical values.
+// grid = number of SMs, block = 256 (thread = code value j, its 16 sub-vectors live in registers).
+template <int METRIC>
+__global__ void __launch_bounds__(256, 1)
+lut_build_kernel(const float* __restrict__ queries, int64_t nq, const float* __restrict__ pqc, float* __restrict__ lut) {
+    __shared__ __align__(16) float s_q[2][KD];
+    const int j = threadIdx.x;
+    const float scale = (METRIC == KB2_METRIC_L2) ? -2.f : -1.f;
+    // thread j keeps the 16 sub-vectors c_pq[.][j] (128 floats) in registers for all the queries of this CTA
+    float4 c[32];
+#pragma unroll
+    for (int m = 0; m < 16; m++) {
+        const float* cp = pqc + ((size_t)m * 256 + j) * 8;
+        c[2 * m] = __ldg(reinterpret_cast<const float4*>(cp));
+        c[2 * m + 1] = __ldg(reinterpret_cast<const float4*>(cp + 4));
+    }
+    const int64_t per = (nq + gridDim.x - 1) / gridDim.x;
+    const int64_t q_beg = (int64_t)blockIdx.x * per, q_end = min(nq, q_beg + per);
+    if (q_beg < q_end && threadIdx.x < KD) s_q[0][threadIdx.x] = queries[q_beg * KD + threadIdx.x];
+    __syncthreads();
+    for (int64_t q = q_beg; q < q_end; q++) {
+        const int cur = (int)((q - q_beg) & 1);
+        if (q + 1 < q_end && threadIdx.x < KD) s_q[cur ^ 1][threadIdx.x] = queries[(q + 1) * KD + threadIdx.x];
+        float* dst = lut + q * 4096 + j * 16;
+#pragma unroll
+        for (int m4 = 0; m4 < 16; m4 += 4) {
+            float o[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int m = m4 + u;
+                const float4 qa = *reinterpret_cast<const float4*>(&s_q[cur][m * 8]);
+                const float4 qb = *reinterpret_cast<const float4*>(&s_q[cur][m * 8 + 4]);
+                float a = 0.f;
+                a = fmaf(qa.x, c[2 * m].x, a); a = fmaf(qa.y, c[2 * m].y, a); a = fmaf(qa.z, c[2 * m].z, a); a = fmaf(qa.w, c[2 * m].w, a);
+                a = fmaf(qb.x, c[2 * m + 1].x, a); a = fmaf(qb.y, c[2 * m + 1].y, a); a = fmaf(qb.z, c[2 * m + 1].z, a); a = fmaf(qb.w, c[2 * m + 1].w, a);
+                o[u] = a * scale;
+            }
+            *reinterpret_cast<float4*>(dst + m4) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+        __syncthreads();
+    }
+}
+
+// exact fp32 keys of the survivors: the LUT kernel's own values in its own order (two interleaved accumulators over
+// the stored byte order; key = base + (acc0 + acc1)), so both engines produce bit-identical keys.
+// grid = nq, block = 128.  Survivors above the bound become kEmpty.
+template <int METRIC>
+__global__ void __launch_bounds__(128)
+exact_eval_kernel(const float* __restrict__ lut, const uint64_t* __restrict__ bound_rows, int64_t bound_stride, int k_need,
+                  const uint4* __restrict__ codes, const float* __restrict__ t1, const uint8_t* __restrict__ bitset,
+                  const int32_t* __restrict__ rows, uint64_t* __restrict__ cand, const uint32_t* __restrict__ cand_cnt, int cap,
+                  uint32_t* __restrict__ qflag, const uint32_t* __restrict__ log_over) {
+    const int64_t q = blockIdx.x;
+    if (*log_over) {
+        if (threadIdx.x == 0) qflag[q] = 1u;
+        return;
+    }
+    if (qflag[q]) return;
+    const uint64_t be = bound_rows[q * bound_stride + k_need - 1];
+    const float bound = unpack_key(be);
+    const uint32_t n = min(cand_cnt[q], (uint32_t)cap);
+    const float* lq = lut + q * 4096;
+    uint64_t* row = cand + q * cap;
+    for (uint32_t i = threadIdx.x; i < n; i += 128) {
+        const uint64_t ent = row[i];
+        const uint32_t pos = (uint32_t)ent;
+        const float base = __uint_as_float((uint32_t)(ent >> 32));
+        const uint4 w = __ldg(codes + pos);
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+        float acc0 = (METRIC == KB2_METRIC_L2) ? __ldg(t1 + pos) : 0.f, acc1 = 0.f;
+#pragma unroll
+        for (int s = 0; s < 16; s++) {
+            const uint32_t byte = (ww[s >> 2] >> (8 * (s & 3))) & 255u;
+            const float a = __ldg(lq + byte * 16 + ((pos + s) & 15u));
+            if (s & 1) acc1 += a; else acc0 += a;
+        }
+        const float key = base + (acc0 + acc1);
+        bool keep = key <= bound;
+        if (keep && bitset) keep = !bit_is_set(bitset, rows[pos]);
+        row[i] = keep ? pack_kp(key, pos) : kEmpty;
+    }
+}
+
+// flagged queries -> compact list (one CTA; order is irrelevant)
+__global__ void __launch_bounds__(1024)
+compact_flags_kernel(const uint32_t* __restrict__ qflag, int64_t nq, int32_t* __restrict__ list, uint32_t* __restrict__ count) {
+    __shared__ uint32_t s_n;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for (int64_t q = threadIdx.x; q < nq; q += 1024)
+        if (qflag[q]) list[atomicAdd(&s_n, 1u)] = (int32_t)q;
+    __syncthreads();
+    if (threadIdx.x == 0) *count = s_n;
+}
+
+// Phase A: exact keys of the codes in the nearest probed lists of every query — lists are taken in probe order until
+// `min_codes` codes were seen (at most `p0_max` lists; lists of other shards have length 0 and cost nothing) —
+// the k_need-th smallest key (rounded up to a histogram bin edge) -> entry k_need-1 of the query's row = the admission
+// bound of the filter pass.  When the lists did not
+// hold 4*k_need codes the bound would be loose (a large share of every probed list would survive): the row is left
+// without a bound and the LUT kernel redoes that query.
+// The query's table is copied from `lut` into a skewed shared layout: code value j owns a row of 32 words,
+// row[w] = LUT[w % 16][j]; lane i reads word (i % 16) + s at step s, i.e. sub-quantizer (pos + s) % 16 — the address
+// is one byte-permute plus an immediate (PRMT + LDS + FADD per look-up, like the LUT kernel), lanes i and i+16 share
+// a bank (2 wavefronts per gather).  The keys go to shared memory and the bound is read off a 1024-bin histogram
+// (no top-k structure at all).  grid = nq, block = 128 (4 warps); dynamic smem = BOUND_SMEM (61 KB).
+#define KB2_BOUND_STEP(WORD, KB, S, ACC)                                                      \
+    {                                                                                         \
+        const uint32_t _x = __byte_perm((WORD), lane4, 0x6504u | ((KB) << 4));                \
+        float _v;                                                                             \
+        asm("ld.shared.f32 %0, [%1+%2];" : "=f"(_v) : "r"(_x >> 1), "n"(KB2_SMEM_BASE + 4 * (S))); \
+        ACC += _v;                                                                            \
+    }
+constexpr int BOUND_KMAX = 6144;    // keys held per query (phase A looks at no more codes than this)
+constexpr int BOUND_BINS = 1024;
+constexpr size_t BOUND_SMEM = 32768 + BOUND_KMAX * 4 + BOUND_BINS * 4 + 64;
+
+template <int METRIC>
+__global__ void __launch_bounds__(128)
+bound_kernel(const float* __restrict__ lut, const int64_t* __restrict__ probe_ids, const float* __restrict__ probe_dis,
+             int probe_stride, int p0_max, int min_codes, int k_need, const int64_t* __restrict__ list_off,
+             const int32_t* __restrict__ list_len, const uint4* __restrict__ codes, const float* __restrict__ t1,
+             const uint8_t* __restrict__ bitset, const int32_t* __restrict__ rows, int K, uint64_t* __restrict__ out,
+             unsigned long long* __restrict__ counters) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* s_lut = (float*)smem_raw;                              // [256][32]
+    float* s_keys = (float*)(smem_raw + 32768);                   // [BOUND_KMAX]
+    uint32_t* s_hist = (uint32_t*)(s_keys + BOUND_KMAX);          // [BOUND_BINS]
+    float* s_red = (float*)(s_hist + BOUND_BINS);                 // [16]
+    const int64_t q = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if ((uint32_t)__cvta_generic_to_shared(smem_raw) != (uint32_t)KB2_SMEM_BASE) {
+        if (threadIdx.x == 0 && counters) atomicExch(counters + 1, 0xBAD5ull);   // layout assumption violated: host raises an error
+        return;
+    }
+    {
+        // lut[q][j*16 + m] -> s_lut[j*32 + m] and s_lut[j*32 + 16 + m]
+        const float4* src = reinterpret_cast<const float4*>(lut + q * 4096);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int idx = threadIdx.x + i * 128;       // float4 index: j = idx / 4, m4 = (idx % 4) * 4
+            const float4 v = __ldg(src + idx);
+            float4* dst = reinterpret_cast<float4*>(s_lut + (idx >> 2) * 32 + (idx & 3) * 4);
+            dst[0] = v;
+            dst[4] = v;
+        }
+    }
+    for (int i = threadIdx.x; i < BOUND_BINS; i += 128) s_hist[i] = 0;
+    __syncthreads();
+    // PRMT builds (byte << 8) | (lane16 << 3) ; >> 1 = byte * 128 + lane16 * 4 (row pitch 128 B)
+    const uint32_t lane4 = (uint32_t)(lane & 15) << 3;
+    int seen = 0, n_tot = 0;
+    float kmin = INFINITY, kmax = -INFINITY;
+    for (int j = 0; j < p0_max && seen < min_codes && n_tot < BOUND_KMAX; j++) {
+        const int64_t l = probe_ids[q * probe_stride + j];
+        if (l < 0) continue;
+        const int len_all = list_len[l];
+        if (len_all == 0) continue;
+        seen += len_all;
+        const int len = min(len_all, BOUND_KMAX - n_tot);   // any subset of the codes still yields a valid upper bound
+        const int64_t off = list_off[l];
+        const float dv = probe_dis[q * probe_stride + j];
+        const float base = (METRIC == KB2_METRIC_L2) ? dv : -dv;
+        // two chunks per iteration: both code words are in flight before the first gather chain starts
+        for (int c0 = warp * 64; c0 < len; c0 += 256) {
+            const int relA = c0 + lane, relB = c0 + 32 + lane;
+            const bool okA = relA < len, okB = relB < len;
+            const uint32_t posA = (uint32_t)(off + relA), posB = (uint32_t)(off + relB);
+            const bool hasB = c0 + 32 < len;
+            const uint4 wA = ldg_stream_u4(codes + posA);       // inside the padded position space even when !ok
+            uint4 wB = wA;
+            if (hasB) wB = ldg_stream_u4(codes + posB);
+            float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+            if (METRIC == KB2_METRIC_L2) {
+                a0 = __ldg(t1 + posA);
+                if (hasB) b0 = __ldg(t1 + posB);
+            }
+            KB2_BOUND_STEP(wA.x, 0, 0, a0)  KB2_BOUND_STEP(wB.x, 0, 0, b0)  KB2_BOUND_STEP(wA.x, 1, 1, a1)  KB2_BOUND_STEP(wB.x, 1, 1, b1)
+            KB2_BOUND_STEP(wA.x, 2, 2, a0)  KB2_BOUND_STEP(wB.x, 2, 2, b0)  KB2_BOUND_STEP(wA.x, 3, 3, a1)  KB2_BOUND_STEP(wB.x, 3, 3, b1)
+            KB2_BOUND_STEP(wA.y, 0, 4, a0)  KB2_BOUND_STEP(wB.y, 0, 4, b0)  KB2_BOUND_STEP(wA.y, 1, 5, a1)  KB2_BOUND_STEP(wB.y, 1, 5, b1)
+            KB2_BOUND_STEP(wA.y, 2, 6, a0)  KB2_BOUND_STEP(wB.y, 2, 6, b0)  KB2_BOUND_STEP(wA.y, 3, 7, a1)  KB2_BOUND_STEP(wB.y, 3, 7, b1)
+            KB2_BOUND_STEP(wA.z, 0, 8, a0)  KB2_BOUND_STEP(wB.z, 0, 8, b0)  KB2_BOUND_STEP(wA.z, 1, 9, a1)  KB2_BOUND_STEP(wB.z, 1, 9, b1)
+            KB2_BOUND_STEP(wA.z, 2, 10, a0) KB2_BOUND_STEP(wB.z, 2, 10, b0) KB2_BOUND_STEP(wA.z, 3, 11, a1) KB2_BOUND_STEP(wB.z, 3, 11, b1)
+            KB2_BOUND_STEP(wA.w, 0, 12, a0) KB2_BOUND_STEP(wB.w, 0, 12, b0) KB2_BOUND_STEP(wA.w, 1, 13, a1) KB2_BOUND_STEP(wB.w, 1, 13, b1)
+            KB2_BOUND_STEP(wA.w, 2, 14, a0) KB2_BOUND_STEP(wB.w, 2, 14, b0) KB2_BOUND_STEP(wA.w, 3, 15, a1) KB2_BOUND_STEP(wB.w, 3, 15, b1)
+            float keyA = base + (a0 + a1), keyB = base + (b0 + b1);
+            if (okA) {
+                if (bitset && bit_is_set(bitset, rows[posA])) keyA = INFINITY;
+                s_keys[n_tot + relA] = keyA;
+                if (keyA < INFINITY) { kmin = fminf(kmin, keyA); kmax = fmaxf(kmax, keyA); }
+            }
+            if (hasB && okB) {
+                if (bitset && bit_is_set(bitset, rows[posB])) keyB = INFINITY;
+                s_keys[n_tot + relB] = keyB;
+                if (keyB < INFINITY) { kmin = fminf(kmin, keyB); kmax = fmaxf(kmax, keyB); }
+            }
+        }
+        n_tot += len;
+    }
+    // ---- K-th smallest key, rounded UP to the edge of one of 1024 linear bins over [min, max]: any value >= the
+    //      k_need-th best is a valid admission bound, and a bin is far narrower than the filter's error margin
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        kmin = fminf(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+        kmax = fmaxf(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    }
+    if (lane == 0) { s_red[warp] = kmin; s_red[4 + warp] = kmax; }
+    __syncthreads();
+    const float lo = fminf(fminf(s_red[0], s_red[1]), fminf(s_red[2], s_red[3]));
+    const float hi = fmaxf(fmaxf(s_red[4], s_red[5]), fmaxf(s_red[6], s_red[7]));
+    const float scale = (hi > lo) ? (float)BOUND_BINS / (hi - lo) : 0.f;
+    for (int i = threadIdx.x; i < n_tot; i += 128) {
+        const float kv = s_keys[i];
+        if (kv < INFINITY) atomicAdd(&s_hist[min(BOUND_BINS - 1, (int)((kv - lo) * scale))], 1u);
+    }
+    __syncthreads();
+    // thread t owns bins [8t, 8t+8): exclusive prefix over threads, then the owner of the crossing writes the bound
+    uint32_t mine[8], tsum = 0;
+#pragma unroll
+    for (int b = 0; b < 8; b++) { mine[b] = s_hist[threadIdx.x * 8 + b]; tsum += mine[b]; }
+    uint32_t incl = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    uint32_t* s_wsum = (uint32_t*)(s_red + 8);
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    uint32_t before = incl - tsum;
+    for (int w = 0; w < warp; w++) before += s_wsum[w];
+    const uint32_t total = s_wsum[0] + s_wsum[1] + s_wsum[2] + s_wsum[3];
+    const uint32_t need = (uint32_t)k_need;
+    if (total < need || seen < 4 * k_need) {
+        if (threadIdx.x == 0) out[q * K + k_need - 1] = kEmpty;   // no (or only a loose) bound: the LUT kernel redoes the query
+    } else if (before < need && before + tsum >= need) {
+        uint32_t cum = before;
+        int b = 0;
+#pragma unroll
+        for (int bb = 0; bb < 8; bb++) {
+            if (cum < need) { cum += mine[bb]; b = bb; }
+        }
+        const float bound = (scale > 0.f) ? lo + ((float)(threadIdx.x * 8 + b) + 1.01f) / scale : hi;
+        out[q * K + k_need - 1] = pack_kp(fmaxf(bound, lo) + 4e-7f * fmaxf(fabsf(lo), fabsf(hi)), 0u);
+    }
+}
+#undef KB2_BOUND_STEP
+
+}  // namespace pqtc
+}  // namespace kb2

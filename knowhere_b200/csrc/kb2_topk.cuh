@@ -233,6 +233,8 @@ struct FinalizeParams {
     int64_t* out_ids;          // [nq][k_out]
     float* out_dist;           // [nq][k_out]
     int32_t* out_pos;          // optional [nq][k_out] positions (NULL: skip)
+    const uint32_t* counts;    // optional [nq]: only the first min(counts[q], n_partial) entries of a row are valid ...
+    const uint32_t* count_flags;   // ... unless count_flags[q] != 0 (then all n_partial are)
 };
 
 // dynamic smem: n_sort*8 + k_sel*(4+8+4) + d*4
@@ -247,6 +249,12 @@ finalize_kernel(FinalizeParams p) {
 
     const int64_t q = blockIdx.x;
     const uint64_t* src = p.partial + q * p.partial_stride;
+    if (p.counts && !(p.count_flags && p.count_flags[q])) {
+        // variable-length row (tensor-core PQ engine): sort only what is there
+        const int c = (int)min(p.counts[q], (uint32_t)p.n_partial);
+        p.n_partial = c;
+        p.n_sort = c <= 2 ? 2 : (1 << (32 - __clz(c - 1)));
+    }
     for (int i = threadIdx.x; i < p.n_sort; i += blockDim.x) s_sort[i] = (i < p.n_partial) ? src[i] : kEmpty;
     if (p.rerank)
         for (int i = threadIdx.x; i < p.d; i += blockDim.x) s_q[i] = p.queries[q * p.d + i];

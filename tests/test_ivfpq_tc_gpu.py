@@ -1,0 +1,90 @@
+"""List-major tensor-core engine of the IVF_PQ scan (kb2_ivfpq_tc.cuh) against the query-major LUT engine.
+
+The tensor-core contraction is only a filter: survivors are re-evaluated with the LUT kernel's own fp32 operations,
+so both engines must return the same (id, distance) rows bit for bit; the LUT engine itself is pinned to the
+compiled reference in test_ivf_gpu.py, and here the tc engine is compared with the reference directly as well."""
+import os
+
+import numpy as np
+import pytest
+
+from knowhere_b200 import datagen
+from tests.util import assert_topk_parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _search(ix, xq, k, cfg, engine, bitset=None):
+    old = os.environ.get("KB2_PQ_ENGINE")
+    os.environ["KB2_PQ_ENGINE"] = engine
+    try:
+        return ix.search(xq, k, cfg, bitset=bitset) if bitset is not None else ix.search(xq, k, cfg)
+    finally:
+        if old is None:
+            os.environ.pop("KB2_PQ_ENGINE", None)
+        else:
+            os.environ["KB2_PQ_ENGINE"] = old
+
+
+def _build(kb, metric, nb, nlist, refine=False, seed=42):
+    xb = datagen.clustered(nb, 128, seed)
+    ix = kb.Index("IVF_PQ", metric, 128, {"nlist": nlist, "m": 16, "nbits": 8, "refine": refine, "refine_type": "flat"})
+    ix.train(xb[: min(nb, 40000)])
+    ix.add(xb)
+    return ix, xb
+
+
+@pytest.mark.parametrize("metric", ["L2", "IP"])
+@pytest.mark.parametrize("nb,nlist,nprobe,nq,k", [(60000, 64, 16, 3000, 10), (30000, 32, 32, 1000, 40), (8000, 128, 64, 700, 10)])
+def test_ivfpq_tc_engine_matches_lut_engine(kb, metric, nb, nlist, nprobe, nq, k):
+    ix, xb = _build(kb, metric, nb, nlist)
+    xq = datagen.clustered(nq, 128, 43)
+    cfg = {"nprobe": nprobe}
+    i0, d0 = _search(ix, xq, k, cfg, "lut")
+    i1, d1 = _search(ix, xq, k, cfg, "tc")
+    c = ix.last_counters()
+    assert np.array_equal(d0.view(np.uint32), d1.view(np.uint32)), f"distances differ in {(d0 != d1).any(axis=1).sum()} rows"
+    assert np.array_equal(i0, i1), f"ids differ in {(i0 != i1).any(axis=1).sum()} rows"
+    # the tc pass really ran: it reports the (query, code) pairs it filtered
+    assert c["codes"] > 0
+
+
+def test_ivfpq_tc_engine_refine_bitset_and_reference(kb, ref):
+    nb, nlist, nprobe, nq, k = 40000, 64, 16, 2000, 10
+    xb = datagen.clustered(nb, 128, 7)
+    xq = datagen.clustered(nq, 128, 8)
+    r = ref.RefIvf("IVF_PQ", 128, 0, nlist, 16, 8, refine=True)
+    r.train(xb)
+    r.add(xb)
+    ix = kb.Index("IVF_PQ", "L2", 128, {"nlist": nlist, "m": 16, "nbits": 8, "refine": True, "refine_type": "flat"})
+    ix.ivf_import(r.centroids(), r.pq_centroids(), list(r.lists()), raw=xb)
+    cfg = {"nprobe": nprobe, "refine_k": 4.0}
+    I0, D0 = r.search(xq, k, nprobe, refine_k=4.0)
+    i1, d1 = _search(ix, xq, k, cfg, "tc")
+    assert_topk_parity(i1, d1, I0, D0, rtol=1e-4, atol=1e-3, what="IVF_PQ tc engine + refine", max_tie_rows=nq // 20)
+    # bitset on a GPU-built index (labels == insertion rows): every third row filtered out
+    ix2, _ = _build(kb, "L2", nb, nlist, refine=True, seed=7)
+    mask = np.zeros(nb, bool)
+    mask[::3] = True
+    bits = np.packbits(mask, bitorder="little")
+    a = _search(ix2, xq, k, cfg, "lut", bitset=bits)
+    b = _search(ix2, xq, k, cfg, "tc", bitset=bits)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+    assert not mask[b[0][b[0] >= 0]].any()
+
+
+def test_ivfpq_tc_engine_flagged_queries_fall_back(kb):
+    # tiny lists: the two nearest lists hold fewer than k codes for many queries -> no bound -> those queries are
+    # redone by the LUT kernel inside the same call; results must still be identical
+    ix, xb = _build(kb, "L2", 6000, 512, seed=5)
+    xq = datagen.clustered(600, 128, 6)
+    cfg = {"nprobe": 64}
+    i0, d0 = _search(ix, xq, 40, cfg, "lut")
+    os.environ["KB2_TC_P0"] = "1"     # phase A may only look at the nearest list (~12 codes): no bound for most queries
+    try:
+        i1, d1 = _search(ix, xq, 40, cfg, "tc")
+    finally:
+        os.environ.pop("KB2_TC_P0", None)
+    c = ix.last_counters()
+    assert np.array_equal(i0, i1) and np.array_equal(d0.view(np.uint32), d1.view(np.uint32))
+    assert c["flagged"] > 0
