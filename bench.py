@@ -51,6 +51,16 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def peaks_tensor():
+    """dense bf16 tensor peak: the burst figure (the filter kernel is timed alone with CUDA events)."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        if "bf16_tflops" in j:
+            return float(j["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst)"
+    return 1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s dense bf16)"
+
+
 class ClockSampler:
     """nvidia-smi clock / throttle sampling DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -209,7 +219,7 @@ def run_ours(args):
     for _ in range(args.warmup):
         search_dev(cfg)
     ix.enable_kernel_timing(True)
-    kernel_ms = []
+    kernel_ms, stage_ms, stage_info = [], [], None
     sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
     if os.environ.get("KB2_PROFILE"):       # ncu --profile-from-start off: capture only the timed steps
@@ -220,6 +230,8 @@ def run_ours(args):
     for _ in range(args.steps):
         search_dev(cfg)
         kernel_ms.append(ix.last_kernel_ms())
+        stage_info = ix.last_stage_info()
+        stage_ms.append(stage_info["stage_ms"])
         launches += ix.last_counters()["launches"] + (5 if world > 1 else 0)
     e1.record()
     barrier()
@@ -289,18 +301,41 @@ def run_ours(args):
     qps = nq * args.steps / (ms_total / 1e3)
     e2e_qps = nq * args.steps / e2e_s
     peak, peak_src = peaks()
-    # roofline of the dominant kernel (ivfpq_scan / ivfflat_scan): algorithmic bytes per launch =
-    # codes scanned x code_size (16 B per PQ code, ids excluded) / live CUDA-event duration
+    # roofline of the dominant kernel, live CUDA-event duration (kb2_index_last_kernel_ms):
+    #  * query-major scan kernels (ivfpq_scan / ivfflat_scan): HBM view, algorithmic bytes per launch = codes scanned x
+    #    code_size (16 B per PQ code, ids excluded);
+    #  * list-major tensor-core engine (ivfpq_tc_filter_kernel): tensor view, algorithmic flops per launch =
+    #    (query, code) pairs x 2 x d — the bf16 contraction the kernel issues on tcgen05 — against the measured dense
+    #    bf16 peak; the HBM view of the same launch is reported beside it.
     k_ms = statistics.mean(kernel_ms)
+    st_ms = statistics.mean(stage_ms)
+    engine = stage_info["engine"] if stage_info else "scan"
     alg_bytes = ctr["code_bytes"]
-    achieved = alg_bytes / (k_ms / 1e3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "scan_kernel_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(args.workload)
+            traffic = json.load(open(tp)).get(args.workload + ("_tc" if engine == "tc" else ""))
         except Exception:
             traffic = None
+    if engine == "tc":
+        alg_flops = ctr["codes"] * 2.0 * d
+        achieved = alg_flops / (k_ms / 1e3) / 1e12
+        tpeak, tsrc = peaks_tensor()
+        roofline = {"bound": "tensor", "kernel": "ivfpq_tc_filter_kernel", "achieved": achieved, "peak": tpeak,
+                    "unit": "TFLOP/s", "frac": achieved / tpeak, "peak_source": tsrc, "traffic": traffic,
+                    "kernel_ms": k_ms, "algorithmic_flops_per_launch": alg_flops,
+                    "codes_scanned_per_launch": ctr["codes"], "kernel_share_of_step": k_ms / (ms_total / args.steps),
+                    "scan_stage_ms": st_ms, "survivors_re_evaluated": ctr["survivors"], "queries_redone": ctr["flagged"],
+                    "hbm_view": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (k_ms / 1e3) / 1e9,
+                                 "achieved_gbs_whole_scan_stage": alg_bytes / (st_ms / 1e3) / 1e9, "peak_gbs": peak}}
+    else:
+        achieved = alg_bytes / (k_ms / 1e3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "ivfpq_scan_kernel" if wl["index"] == "IVF_PQ" else "ivfflat_scan_kernel",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "peak_source": peak_src, "traffic": traffic, "kernel_ms": k_ms,
+                    "algorithmic_bytes_per_launch": alg_bytes, "codes_scanned_per_launch": ctr["codes"],
+                    "kernel_share_of_step": k_ms / (ms_total / args.steps)}
     out = {
         "metric": METRIC_NAME if args.workload == "ivf_pq_10m" else f"queries/sec, {args.workload}",
         "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -319,11 +354,7 @@ def run_ours(args):
         "gpu_launches": launches,
         "multi_gpu_breakdown": breakdown,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "ivfpq_scan_kernel" if wl["index"] == "IVF_PQ" else "ivfflat_scan_kernel",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "peak_source": peak_src, "traffic": traffic, "kernel_ms": k_ms,
-                     "algorithmic_bytes_per_launch": alg_bytes, "codes_scanned_per_launch": ctr["codes"],
-                     "kernel_share_of_step": k_ms / (ms_total / args.steps)},
+        "roofline": roofline,
     }
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the reference's own CPU code on the host cores

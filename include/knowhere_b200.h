@@ -183,6 +183,10 @@ int kb2_index_last_search_counters(kb2_index_t h, int64_t* out8);
  * CUDA events on the handle's stream (valid only after kb2_index_enable_kernel_timing(h,1)) */
 int kb2_index_enable_kernel_timing(kb2_index_t h, int on);
 int kb2_index_last_kernel_ms(kb2_index_t h, float* out_ms);
+/* out4: [0] device ms of the whole list-scan stage of the last search, [1] device ms of its dominant kernel
+ * (== kb2_index_last_kernel_ms), [2] engine that served it: 0 = query-major scan kernels, 1 = list-major
+ * tensor-core engine (IVF_PQ m=16 d=128 with large batches; kb2_ivfpq_tc.cuh), [3] reserved */
+int kb2_index_last_stage_info(kb2_index_t h, float* out4);
 
 /* validation hook: writes the full key matrix [nq][round_up(nb,4)] of the dense contraction
  * (|q|^2+|x|^2-2qx for L2, -qx for IP) computed by the fp32 CUDA-core kernel (use_tc=0) or by the

@@ -85,6 +85,7 @@ def _declare(L):
     L.kb2_index_last_search_counters.argtypes = [vp, vp]
     L.kb2_index_enable_kernel_timing.argtypes = [vp, i32]
     L.kb2_index_last_kernel_ms.argtypes = [vp, c.POINTER(f32)]
+    L.kb2_index_last_stage_info.argtypes = [vp, vp]
 
 
 def _check(status):
@@ -280,6 +281,11 @@ class Index:
 
     def enable_kernel_timing(self, on=True):
         _check(self.L.kb2_index_enable_kernel_timing(self.h, 1 if on else 0))
+
+    def last_stage_info(self):
+        v = np.zeros(4, np.float32)
+        _check(self.L.kb2_index_last_stage_info(self.h, _ptr(v)))
+        return dict(stage_ms=float(v[0]), kernel_ms=float(v[1]), engine="tc" if v[2] > 0.5 else "scan")
 
     def last_kernel_ms(self):
         v = ctypes.c_float()

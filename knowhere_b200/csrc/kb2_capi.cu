@@ -544,5 +544,15 @@ int
 kb2_index_last_kernel_ms(kb2_index_t h, float* out_ms) {
     return guarded([&] { *out_ms = ix_of(h)->last_kernel_ms; });
 }
+int
+kb2_index_last_stage_info(kb2_index_t h, float* out4) {
+    return guarded([&] {
+        IndexBase* ix = ix_of(h);
+        out4[0] = ix->last_stage_ms;
+        out4[1] = ix->last_kernel_ms;
+        out4[2] = (float)ix->last_engine;
+        out4[3] = 0.f;
+    });
+}
 
 }  // extern "C"

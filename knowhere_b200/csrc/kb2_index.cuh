@@ -153,8 +153,10 @@ struct IndexBase {
     std::mutex mu;
     Counters last;
     bool timing = false;
-    float last_kernel_ms = 0.f;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_kernel_ms = 0.f;      // dominant kernel of the last search (IVF_PQ tensor-core engine: the filter kernel)
+    float last_stage_ms = 0.f;       // whole list-scan stage of the last search (all engines)
+    int last_engine = 0;             // 0: query-major scan kernels, 1: list-major tensor-core engine
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     DevBuf<unsigned long long> d_counter;
 
     // per-search scratch (grow-only, reused across calls)
@@ -188,6 +190,8 @@ struct IndexBase {
         own_stream = true;
         KB2_CUDA_CHECK(cudaEventCreate(&ev0));
         KB2_CUDA_CHECK(cudaEventCreate(&ev1));
+        KB2_CUDA_CHECK(cudaEventCreate(&ev2));
+        KB2_CUDA_CHECK(cudaEventCreate(&ev3));
         d_counter.ensure(8);
     }
     void
@@ -420,7 +424,11 @@ struct FlatIndex : IndexBase {
         last.code_bytes = n * (int64_t)dim * 4;  // list-major contraction reads the base once per batch
         last.pairs = nq;
         results_out(nq, k, out_ids, out_dist, d_ids, d_dist);
-        if (timing) KB2_CUDA_CHECK(cudaEventElapsedTime(&last_kernel_ms, ev0, ev1));
+        last_engine = 0;
+        if (timing) {
+            KB2_CUDA_CHECK(cudaEventElapsedTime(&last_stage_ms, ev0, ev1));
+            last_kernel_ms = last_stage_ms;
+        }
     }
 
     void
@@ -757,7 +765,7 @@ struct IvfIndex : IndexBase {
     }
 
     // ---------------------------------------------------------------- list-major tensor-core engine (kb2_ivfpq_tc.cuh)
-    static constexpr int kTcCandCap = 512;      // survivor slots per query (overflow -> LUT kernel redoes the query)
+    static constexpr int kTcCandCap = 1024;     // survivor slots per query (overflow -> LUT kernel redoes the query)
     DevBuf<uint16_t> tc_pqc16, s_qb16;
     DevBuf<float> tc_maxn2, s_qnorm, s_pair_base, s_lut;
     DevBuf<int32_t> s_lcount, s_lstart, s_items, s_pair_q, s_plan_out, s_flaglist;
@@ -893,10 +901,12 @@ struct IvfIndex : IndexBase {
         tp.shared_cap = shared_cap;
         tp.qflag = s_cand_cnt.p + nq;
         tp.counters = d_counter.p;
+        if (timing) KB2_CUDA_CHECK(cudaEventRecord(ev2, st));
         if (metric == KB2_METRIC_L2)
             pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_L2><<<kNumSMs, pqtc::THREADS, pqtc::SMEM_BYTES, st>>>(tp);
         else
             pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_IP><<<kNumSMs, pqtc::THREADS, pqtc::SMEM_BYTES, st>>>(tp);
+        if (timing) KB2_CUDA_CHECK(cudaEventRecord(ev3, st));
         KB2_CUDA_CHECK(cudaGetLastError());
         mark("tc_filter");
         // ---- survivors: group by query, exact fp32 keys (bit-identical to the LUT engine's)
@@ -1106,7 +1116,12 @@ struct IvfIndex : IndexBase {
         last.codes = (int64_t)scanned;
         last.code_bytes = (int64_t)scanned * (is_pq ? (int64_t)M : (int64_t)dim * 4);
         last.pairs = nq * nprobe;
-        if (timing) KB2_CUDA_CHECK(cudaEventElapsedTime(&last_kernel_ms, ev0, ev1));
+        last_engine = tc_engine ? 1 : 0;
+        if (timing) {
+            KB2_CUDA_CHECK(cudaEventElapsedTime(&last_stage_ms, ev0, ev1));
+            last_kernel_ms = last_stage_ms;
+            if (tc_engine) KB2_CUDA_CHECK(cudaEventElapsedTime(&last_kernel_ms, ev2, ev3));
+        }
     }
 
     void
