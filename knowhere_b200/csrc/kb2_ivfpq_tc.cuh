@@ -801,20 +801,30 @@ bound_kernel(const float* __restrict__ lut, const int64_t* __restrict__ probe_id
         const int64_t off = list_off[l];
         const float dv = probe_dis[q * probe_stride + j];
         const float base = (METRIC == KB2_METRIC_L2) ? dv : -dv;
-        // two chunks per iteration: both code words are in flight before the first gather chain starts
+        // two chunks per iteration, software-pipelined: the code words / row terms of the NEXT iteration are in
+        // flight while the gather chains of this one run (the kernel was latency bound on these loads)
+        uint4 nA = make_uint4(0, 0, 0, 0), nB = nA;
+        float ntA = 0.f, ntB = 0.f;
+        auto load_iter = [&](int c0) {
+            if (c0 < len) {
+                nA = ldg_stream_u4(codes + off + c0 + lane);        // inside the padded position space even past len
+                if (METRIC == KB2_METRIC_L2) ntA = __ldg(t1 + off + c0 + lane);
+                if (c0 + 32 < len) {
+                    nB = ldg_stream_u4(codes + off + c0 + 32 + lane);
+                    if (METRIC == KB2_METRIC_L2) ntB = __ldg(t1 + off + c0 + 32 + lane);
+                }
+            }
+        };
+        load_iter(warp * 64);
         for (int c0 = warp * 64; c0 < len; c0 += 256) {
             const int relA = c0 + lane, relB = c0 + 32 + lane;
             const bool okA = relA < len, okB = relB < len;
             const uint32_t posA = (uint32_t)(off + relA), posB = (uint32_t)(off + relB);
             const bool hasB = c0 + 32 < len;
-            const uint4 wA = ldg_stream_u4(codes + posA);       // inside the padded position space even when !ok
-            uint4 wB = wA;
-            if (hasB) wB = ldg_stream_u4(codes + posB);
-            float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-            if (METRIC == KB2_METRIC_L2) {
-                a0 = __ldg(t1 + posA);
-                if (hasB) b0 = __ldg(t1 + posB);
-            }
+            const uint4 wA = nA;
+            const uint4 wB = hasB ? nB : nA;
+            float a0 = ntA, a1 = 0.f, b0 = hasB ? ntB : 0.f, b1 = 0.f;
+            load_iter(c0 + 256);
             KB2_BOUND_STEP(wA.x, 0, 0, a0)  KB2_BOUND_STEP(wB.x, 0, 0, b0)  KB2_BOUND_STEP(wA.x, 1, 1, a1)  KB2_BOUND_STEP(wB.x, 1, 1, b1)
             KB2_BOUND_STEP(wA.x, 2, 2, a0)  KB2_BOUND_STEP(wB.x, 2, 2, b0)  KB2_BOUND_STEP(wA.x, 3, 3, a1)  KB2_BOUND_STEP(wB.x, 3, 3, b1)
             KB2_BOUND_STEP(wA.y, 0, 4, a0)  KB2_BOUND_STEP(wB.y, 0, 4, b0)  KB2_BOUND_STEP(wA.y, 1, 5, a1)  KB2_BOUND_STEP(wB.y, 1, 5, b1)
