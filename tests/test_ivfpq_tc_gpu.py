@@ -88,3 +88,29 @@ def test_ivfpq_tc_engine_flagged_queries_fall_back(kb):
     c = ix.last_counters()
     assert np.array_equal(i0, i1) and np.array_equal(d0.view(np.uint32), d1.view(np.uint32))
     assert c["flagged"] > 0
+
+
+def test_ivfpq_tc_engine_on_shards(kb):
+    """List sharding (kb2_index_set_shard): lists of the other shard have length 0 — no work items, phase A walks further
+    down the probe list.  Each shard must answer identically through both engines, and the merged shards must equal the
+    unsharded search."""
+    nb, nlist, nq, k, world = 40000, 64, 2000, 10, 2
+    xb = datagen.clustered(nb, 128, 21)
+    xq = datagen.clustered(nq, 128, 22)
+    full, _ = _build(kb, "L2", nb, nlist, seed=21)
+    cent, pq = full.ivf_export_centroids(16)
+    cfg = {"nprobe": 16}
+    I0, D0 = _search(full, xq, k, cfg, "tc")
+    ids, dis = [], []
+    for rank in range(world):
+        sh = kb.Index("IVF_PQ", "L2", 128, {"nlist": nlist, "m": 16, "nbits": 8})
+        sh.set_shard(rank, world)
+        kb._check(kb.lib().kb2_ivf_import_begin(sh.h, nlist, cent.ctypes.data, pq.ctypes.data))
+        sh.add(xb)
+        a = _search(sh, xq, k, cfg, "lut")
+        b = _search(sh, xq, k, cfg, "tc")
+        assert sh.last_counters()["codes"] > 0
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32)), f"shard {rank}"
+        ids.append(b[0]); dis.append(b[1])
+    mi, md = kb.merge_topk(np.stack(ids), np.stack(dis), "L2")
+    assert_topk_parity(mi, md, I0, D0, rtol=1e-6, atol=1e-6, what="sharded tc merge", max_tie_rows=nq // 10)
