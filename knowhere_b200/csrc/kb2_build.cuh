@@ -74,23 +74,30 @@ argmin_rows_kernel(const float* __restrict__ keys, int64_t ldk, int64_t n, int k
         if (out_val) out_val[i] = best;
     }
 }
+// Deterministic centroid update: the points are sorted by (centroid, index) beforehand; one warp per centroid sums its
+// points in a fixed order (lane group g takes points g, g+groups, ...; groups are combined by a fixed shuffle tree), so two
+// builds of the same data give bit-identical centroids (no float atomics).
 __global__ void __launch_bounds__(256)
-kmeans_accumulate_kernel(const float* __restrict__ x, const int32_t* __restrict__ assign, int64_t n, int d,
-                         float* __restrict__ sums, int32_t* __restrict__ counts) {
+kmeans_reduce_kernel(const float* __restrict__ x, const int32_t* __restrict__ sorted_idx, const int32_t* __restrict__ seg_off,
+                     const int32_t* __restrict__ counts, int k, int d, float* __restrict__ cent) {
     const int lane = threadIdx.x & 31;
-    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (i >= n) return;
-    const int c = assign[i];
-    for (int j = lane; j < d; j += kWarp) atomicAdd(&sums[(int64_t)c * d + j], x[i * d + j]);
-    if (lane == 0) atomicAdd(&counts[c], 1);
-}
-__global__ void
-kmeans_divide_kernel(float* __restrict__ cent, const float* __restrict__ sums, const int32_t* __restrict__ counts,
-                     int k, int d) {
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (int64_t)k * d) return;
-    const int c = (int)(t / d);
-    if (counts[c] > 0) cent[t] = sums[t] / (float)counts[c];
+    const int c = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (c >= k) return;
+    const int cnt = counts[c];
+    if (cnt <= 0) return;
+    const int32_t* idx = sorted_idx + seg_off[c];
+    int dp = 1;
+    while (dp < d && dp < 32) dp <<= 1;          // lanes per point (power of two <= 32)
+    const int groups = 32 / dp, g = lane / dp, jl = lane % dp;
+    const float inv = 1.f / (float)cnt;
+    for (int j0 = 0; j0 < d; j0 += dp) {
+        const int j = j0 + jl;
+        float acc = 0.f;
+        if (j < d)
+            for (int p = g; p < cnt; p += groups) acc += x[(int64_t)idx[p] * d + j];
+        for (int o = dp; o < 32; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (g == 0 && j < d) cent[(int64_t)c * d + j] = acc * inv;
+    }
 }
 // sequentially applied (ci <- perturbed copy of cj) pairs; faiss split_clusters semantics
 __global__ void
@@ -213,6 +220,26 @@ layout_codes_plain_kernel(const uint8_t* __restrict__ codes_flat, const int32_t*
     const int32_t r = rows[pos];
     out[t] = (r >= 0) ? codes_flat[(int64_t)r * M + m] : 0;
 }
+// inverse of the two layout kernels: codes_flat[row*M + m] from the list-order layout (add() after a search)
+__global__ void
+unlayout_codes_kernel(const uint8_t* __restrict__ laid, const int32_t* __restrict__ pos_of_row, int64_t n, int64_t npad, int M,
+                      int G, uint8_t* __restrict__ codes_flat) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * M) return;
+    const int64_t r = t / M;
+    const int m = (int)(t % M);
+    const int64_t pos = pos_of_row[r];
+    uint8_t v = 0;
+    if (pos >= 0) {
+        if (G > 0) {
+            const int g = m >> 4, s = (m - (int)(pos & 15)) & 15;
+            v = laid[((int64_t)g * npad + pos) * 16 + s];
+        } else {
+            v = laid[pos * M + m];
+        }
+    }
+    codes_flat[t] = v;
+}
 __global__ void
 gather_f32_kernel(const float* __restrict__ src, const int32_t* __restrict__ rows, int64_t npad, float* __restrict__ out,
                   float fill) {
@@ -326,21 +353,35 @@ kmeans_train(const float* x, int64_t n, int d, int k, int metric, int niter, uin
         gather_rows_kernel<<<grid1d((int64_t)k * 32, 256), 256, 0, st>>>(xt, didx.p, k, d, d, centroids);
         KB2_CUDA_CHECK(cudaStreamSynchronize(st));
     }
-    DevBuf<int32_t> assign, counts, pairs;
-    DevBuf<float> sums;
+    DevBuf<int32_t> assign, counts, pairs, idx_in, idx_out, key_out, seg_off;
+    DevBuf<uint8_t> sort_tmp;
     assign.ensure(nt);
     counts.ensure(k);
-    sums.ensure((size_t)k * d);
+    idx_in.ensure(nt);
+    idx_out.ensure(nt);
+    key_out.ensure(nt);
+    seg_off.ensure(k);
+    iota_kernel<<<dim3((unsigned)((nt + 255) / 256)), 256, 0, st>>>(idx_in.p, nt);
+    int end_bit = 1;
+    while ((1ll << end_bit) < k) end_bit++;
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, assign.p, key_out.p, idx_in.p, idx_out.p, (int)nt, 0, end_bit, st);
+    sort_tmp.ensure(tmp_bytes);
     AssignScratch sc;
-    std::vector<int32_t> hcounts(k);
+    std::vector<int32_t> hcounts(k), hoff(k);
     for (int it = 0; it < niter; it++) {
         assign_nearest(xt, nt, d, centroids, k, metric, assign.p, nullptr, sc, st);
         KB2_CUDA_CHECK(cudaMemsetAsync(counts.p, 0, (size_t)k * 4, st));
-        KB2_CUDA_CHECK(cudaMemsetAsync(sums.p, 0, (size_t)k * d * 4, st));
-        kmeans_accumulate_kernel<<<grid1d(nt * 32, 256), 256, 0, st>>>(xt, assign.p, nt, d, sums.p, counts.p);
-        kmeans_divide_kernel<<<grid1d((int64_t)k * d, 256), 256, 0, st>>>(centroids, sums.p, counts.p, k, d);
+        histogram_kernel<<<dim3((unsigned)((nt + 255) / 256)), 256, 0, st>>>(assign.p, nt, counts.p);
+        cub::DeviceRadixSort::SortPairs(sort_tmp.p, tmp_bytes, assign.p, key_out.p, idx_in.p, idx_out.p, (int)nt, 0, end_bit, st);
         KB2_CUDA_CHECK(cudaMemcpyAsync(hcounts.data(), counts.p, (size_t)k * 4, cudaMemcpyDeviceToHost, st));
         KB2_CUDA_CHECK(cudaStreamSynchronize(st));
+        int32_t run = 0;
+        for (int c = 0; c < k; c++) { hoff[c] = run; run += hcounts[c]; }
+        KB2_CUDA_CHECK(cudaMemcpyAsync(seg_off.p, hoff.data(), (size_t)k * 4, cudaMemcpyHostToDevice, st));
+        kmeans_reduce_kernel<<<dim3((unsigned)(((int64_t)k * 32 + 255) / 256)), 256, 0, st>>>(xt, idx_out.p, seg_off.p, counts.p, k, d,
+                                                                                         centroids);
+        KB2_CUDA_CHECK(cudaStreamSynchronize(st));   // hoff is reused next iteration
         // empty clusters: split a populated one (probability ~ size), like faiss split_clusters
         std::vector<int32_t> hp;
         for (int ci = 0; ci < k; ci++) {

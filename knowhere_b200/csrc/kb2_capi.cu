@@ -215,6 +215,7 @@ kb2_index_train(kb2_index_t h, const float* x, int64_t n) {
         std::lock_guard<std::mutex> lk(ix->mu);
         KB2_CUDA_CHECK(cudaSetDevice(ix->device));
         KB2_REQUIRE(x != nullptr || n == 0, KB2_INVALID_ARGS, "null training data");
+        ix->wait_caller_work();
         ix->train(ix->cosine ? ix->normalized(x, n) : x, n);
     });
 }
@@ -226,6 +227,7 @@ kb2_index_add(kb2_index_t h, const float* x, int64_t n, const int64_t* ids) {
         std::lock_guard<std::mutex> lk(ix->mu);
         KB2_CUDA_CHECK(cudaSetDevice(ix->device));
         KB2_REQUIRE(x != nullptr || n == 0, KB2_INVALID_ARGS, "null data");
+        ix->wait_caller_work();
         ix->add(ix->cosine ? ix->normalized(x, n) : x, n, ids);
     });
 }
@@ -245,6 +247,7 @@ kb2_index_search(kb2_index_t h, const float* queries, int64_t nq, int k, const c
         JsonObj cfg = JsonObj::parse(json);
         KB2_REQUIRE(cfg.ok, KB2_INVALID_PARAM_IN_JSON, "malformed json");
         ix->last = Counters{};
+        ix->wait_caller_work();
         ix->search(ix->cosine ? ix->normalized(queries, nq) : queries, nq, k, cfg, bitset, bitset_nbits, out_ids, out_dist);
     });
 }
@@ -261,6 +264,7 @@ kb2_index_range_search(kb2_index_t h, const float* queries, int64_t nq, float ra
         JsonObj cfg = JsonObj::parse(json);
         KB2_REQUIRE(cfg.ok, KB2_INVALID_PARAM_IN_JSON, "malformed json");
         ix->last = Counters{};
+        ix->wait_caller_work();
         range_search_index(*ix, ix->cosine ? ix->normalized(queries, nq) : queries, nq, radius, range_filter,
                            has_range_filter != 0, cfg, bitset, bitset_nbits, out_lims, out_ids, out_dist);
     });
@@ -441,26 +445,72 @@ kb2_index_deserialize(const uint8_t* blob, size_t size, int device, kb2_index_t*
 }
 
 // ---------------------------------------------------------------- BruteForce
+// One scratch FLAT object per device, reused across calls (stream, events, selection scratch); a device-resident base is
+// viewed in place (no copy), a host base is staged into the scratch buffer.
+namespace {
+struct BfSlot {
+    std::mutex mu;
+    std::unique_ptr<FlatIndex> fi;
+};
+BfSlot g_bf[64];
+
+FlatIndex&
+bf_prepare(BfSlot& slot, int device, int metric, int dim, void* cuda_stream, const float* base, int64_t nb) {
+    if (!slot.fi) {
+        slot.fi.reset(new FlatIndex());
+        slot.fi->type = "FLAT";
+        slot.fi->device = device;
+        slot.fi->init_common();
+    }
+    FlatIndex& fi = *slot.fi;
+    fi.cosine = (metric == KB2_METRIC_COSINE);
+    fi.metric = fi.cosine ? KB2_METRIC_IP : metric;
+    fi.dim = dim;
+    if (cuda_stream) fi.set_stream((cudaStream_t)cuda_stream); else fi.use_own_stream();
+    fi.wait_caller_work();
+    fi.last = Counters{};
+    const size_t cnt = (size_t)nb * dim;
+    if (fi.cosine) {
+        const float* dx = fi.to_device(base, cnt, fi.s_cos_in);
+        fi.base.ensure(cnt);
+        normalize_rows_kernel<<<grid1d(nb * 32, 256), 256, 0, fi.stream>>>(dx, nb, dim, fi.base.p);
+    } else if (is_device_ptr(base)) {
+        fi.base.borrow(base, cnt);
+    } else {
+        fi.base.ensure(cnt);
+        KB2_CUDA_CHECK(cudaMemcpyAsync(fi.base.p, base, cnt * 4, cudaMemcpyHostToDevice, fi.stream));
+        fi.last.h2d += (int64_t)cnt * 4;
+    }
+    fi.n_used = cnt;
+    fi.norms.ensure(nb);
+    row_norms_kernel<<<grid1d(nb * 32, 256), 256, 0, fi.stream>>>(fi.base.p, nb, dim, fi.norms.p);
+    fi.norms_used = (size_t)nb;
+    fi.custom_labels = false;
+    fi.n_global_added = nb;
+    KB2_CUDA_CHECK(cudaGetLastError());
+    return fi;
+}
+}  // namespace
+
 int
 kb2_bruteforce_search(const float* base, int64_t nb, int dim, int metric, const float* queries, int64_t nq, int k,
                       const uint8_t* bitset, int64_t bitset_nbits, int64_t* out_ids, float* out_dist, int device,
                       void* cuda_stream) {
     return guarded([&] {
         KB2_REQUIRE(base && queries && out_ids && out_dist, KB2_INVALID_ARGS, "null buffer");
+        KB2_REQUIRE(nb > 0 && dim > 0 && nq >= 0 && k > 0, KB2_INVALID_ARGS, "bad sizes");
         KB2_REQUIRE(metric == KB2_METRIC_L2 || metric == KB2_METRIC_IP || metric == KB2_METRIC_COSINE,
                     KB2_INVALID_METRIC_TYPE, "metric must be L2, IP or COSINE");
         require_device(device);
-        FlatIndex fi;
-        fi.type = "FLAT";
-        fi.cosine = (metric == KB2_METRIC_COSINE);
-        fi.metric = fi.cosine ? KB2_METRIC_IP : metric;
-        fi.dim = dim;
-        fi.device = device;
-        fi.init_common();
-        if (cuda_stream) fi.set_stream((cudaStream_t)cuda_stream);
-        fi.add(fi.cosine ? fi.normalized(base, nb) : base, nb, nullptr);
+        KB2_REQUIRE(device < 64, KB2_INVALID_ARGS, "bad device ordinal");
+        if (nq == 0) return;
+        BfSlot& slot = g_bf[device];
+        std::lock_guard<std::mutex> lk(slot.mu);
+        FlatIndex& fi = bf_prepare(slot, device, metric, dim, cuda_stream, base, nb);
         JsonObj cfg;
         fi.search(fi.cosine ? fi.normalized(queries, nq) : queries, nq, k, cfg, bitset, bitset_nbits, out_ids, out_dist);
+        fi.base.release();   // never keep a view of caller memory (or a stale copy) between calls
+        fi.n_used = 0;
     });
 }
 int
@@ -470,19 +520,19 @@ kb2_bruteforce_range_search(const float* base, int64_t nb, int dim, int metric, 
                             void* cuda_stream) {
     return guarded([&] {
         KB2_REQUIRE(base && queries, KB2_INVALID_ARGS, "null buffer");
-        KB2_REQUIRE(metric == KB2_METRIC_L2 || metric == KB2_METRIC_IP, KB2_INVALID_METRIC_TYPE, "metric must be L2 or IP");
+        KB2_REQUIRE(nb > 0 && dim > 0 && nq >= 0, KB2_INVALID_ARGS, "bad sizes");
+        KB2_REQUIRE(metric == KB2_METRIC_L2 || metric == KB2_METRIC_IP || metric == KB2_METRIC_COSINE,
+                    KB2_INVALID_METRIC_TYPE, "metric must be L2, IP or COSINE");
         require_device(device);
-        FlatIndex fi;
-        fi.type = "FLAT";
-        fi.metric = metric;
-        fi.dim = dim;
-        fi.device = device;
-        fi.init_common();
-        if (cuda_stream) fi.set_stream((cudaStream_t)cuda_stream);
-        fi.add(base, nb, nullptr);
+        KB2_REQUIRE(device < 64, KB2_INVALID_ARGS, "bad device ordinal");
+        BfSlot& slot = g_bf[device];
+        std::lock_guard<std::mutex> lk(slot.mu);
+        FlatIndex& fi = bf_prepare(slot, device, metric, dim, cuda_stream, base, nb);
         JsonObj cfg;
-        range_search_index(fi, queries, nq, radius, range_filter, has_range_filter != 0, cfg, bitset, bitset_nbits,
-                           out_lims, out_ids, out_dist);
+        range_search_index(fi, fi.cosine ? fi.normalized(queries, nq) : queries, nq, radius, range_filter,
+                           has_range_filter != 0, cfg, bitset, bitset_nbits, out_lims, out_ids, out_dist);
+        fi.base.release();
+        fi.n_used = 0;
     });
 }
 

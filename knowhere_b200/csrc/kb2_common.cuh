@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <mutex>
 #include <stdexcept>
 #include <string>
 
@@ -128,23 +129,32 @@ template <typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    bool owned = true;   // false: p is a caller-owned device buffer viewed in place (borrow())
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), owned(o.owned) { o.p = nullptr; o.n = 0; o.owned = true; }
     DevBuf& operator=(DevBuf&& o) noexcept {
-        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        if (this != &o) { release(); p = o.p; n = o.n; owned = o.owned; o.p = nullptr; o.n = 0; o.owned = true; }
         return *this;
     }
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFree(p);
+        if (p && owned) cudaFree(p);
         p = nullptr;
         n = 0;
+        owned = true;
+    }
+    // view `count` elements of a caller-owned device buffer (never freed, never grown in place)
+    void borrow(const T* ptr, size_t count) {
+        release();
+        p = const_cast<T*>(ptr);
+        n = count;
+        owned = false;
     }
     // grow-only allocation (contents are NOT preserved)
     void ensure(size_t count) {
-        if (count <= n && p) return;
+        if (count <= n && p && owned) return;
         release();
         if (count == 0) count = 1;
         cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
@@ -179,6 +189,19 @@ struct PinnedBuf {
         }
         n = bytes;
         return p;
+    }
+};
+
+// Run `f` once per CUDA device (cudaFuncSetAttribute & friends apply to the current device only; one process may hold
+// indexes on several GPUs — the C ABI takes a device ordinal per handle).
+struct PerDeviceOnce {
+    std::once_flag flags[64];
+    template <typename F>
+    void run(F&& f) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+        if (dev < 0 || dev >= 64) { f(); return; }
+        std::call_once(flags[dev], f);
     }
 };
 

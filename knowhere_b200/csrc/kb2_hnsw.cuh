@@ -571,7 +571,27 @@ struct HnswIndex : IndexBase {
         entry_point = ep;
         max_level = ml;
         KB2_REQUIRE(max_level + 1 < n_cum, KB2_INVALID_ARGS, "cum_nneighbor_per_level shorter than max_level");
+        validate_graph();
         uploaded = false;
+    }
+
+    // structural checks of an externally supplied graph (the search kernel trusts these arrays)
+    void
+    validate_graph() const {
+        const int ncum = (int)h_cum.size();
+        KB2_REQUIRE(n > 0 && ncum >= 2 && h_cum[0] == 0, KB2_INVALID_BINARY_SET, "HNSW: bad graph header");
+        for (int l = 0; l + 1 < ncum; l++) KB2_REQUIRE(h_cum[l + 1] > h_cum[l], KB2_INVALID_BINARY_SET, "HNSW: cum_nneighbor not increasing");
+        KB2_REQUIRE(max_level >= 0 && max_level + 1 < ncum, KB2_INVALID_BINARY_SET, "HNSW: max_level outside cum_nneighbor");
+        KB2_REQUIRE(entry_point >= 0 && entry_point < n, KB2_INVALID_BINARY_SET, "HNSW: entry point out of range");
+        KB2_REQUIRE((int64_t)h_offsets.size() == n + 1 && h_offsets[0] == 0, KB2_INVALID_BINARY_SET, "HNSW: bad offsets");
+        for (int64_t i = 0; i < n; i++) {
+            const int lv = h_levels[i];
+            KB2_REQUIRE(lv >= 1 && lv < ncum && h_offsets[i + 1] - h_offsets[i] == h_cum[lv], KB2_INVALID_BINARY_SET,
+                        "HNSW: offsets do not match the levels");
+        }
+        KB2_REQUIRE((int64_t)h_neighbors.size() == h_offsets[n], KB2_INVALID_BINARY_SET, "HNSW: neighbor array size");
+        KB2_REQUIRE(h_levels[entry_point] - 1 >= max_level, KB2_INVALID_BINARY_SET, "HNSW: entry point below max_level");
+        for (int32_t v : h_neighbors) KB2_REQUIRE(v >= -1 && v < n, KB2_INVALID_BINARY_SET, "HNSW: neighbor id out of range");
     }
 
     void
@@ -600,8 +620,8 @@ struct HnswIndex : IndexBase {
         KB2_REQUIRE(n > 0 && entry_point >= 0, KB2_EMPTY_INDEX, "index is empty");
         KB2_REQUIRE(bitset == nullptr, KB2_NOT_IMPLEMENTED, "HNSW: bitset-filtered search is not implemented yet");
         upload();
-        static std::once_flag once;
-        std::call_once(once, [] {
+        static PerDeviceOnce once;
+        once.run([] {
             cudaFuncSetAttribute((const void*)hnsw_search_kernel<KB2_METRIC_L2>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
             cudaFuncSetAttribute((const void*)hnsw_search_kernel<KB2_METRIC_IP>,
@@ -715,12 +735,15 @@ struct HnswIndex : IndexBase {
         max_level = r.get<int32_t>();
         const int ncum = r.get<int32_t>();
         custom_labels = r.get<int32_t>() != 0;
+        KB2_REQUIRE(n > 0 && n < (1ll << 31) && ncum >= 2 && ncum < 64 && (uint64_t)n <= r.n / 4, KB2_INVALID_BINARY_SET,
+                    "HNSW: bad header in blob");
         h_cum.resize(ncum);
         memcpy(h_cum.data(), r.get_bytes((size_t)ncum * 4), (size_t)ncum * 4);
         h_levels.resize(n);
         memcpy(h_levels.data(), r.get_bytes((size_t)n * 4), (size_t)n * 4);
         h_offsets.resize(n + 1);
         memcpy(h_offsets.data(), r.get_bytes((size_t)(n + 1) * 8), (size_t)(n + 1) * 8);
+        KB2_REQUIRE(h_offsets[n] >= 0 && (uint64_t)h_offsets[n] <= r.n / 4, KB2_INVALID_BINARY_SET, "HNSW: bad offsets in blob");
         h_neighbors.resize(h_offsets[n]);
         memcpy(h_neighbors.data(), r.get_bytes(h_neighbors.size() * 4), h_neighbors.size() * 4);
         h_vecs.resize((size_t)n * dim);
@@ -729,6 +752,7 @@ struct HnswIndex : IndexBase {
             h_labels.resize(n);
             memcpy(h_labels.data(), r.get_bytes((size_t)n * 8), (size_t)n * 8);
         }
+        validate_graph();
         uploaded = false;
     }
 };

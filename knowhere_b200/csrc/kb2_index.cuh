@@ -31,8 +31,8 @@ constexpr int kMaxDynSmem = 227 * 1024;
 
 inline void
 init_kernel_attributes() {
-    static std::once_flag once;
-    std::call_once(once, [] {
+    static PerDeviceOnce once;
+    once.run([] {
         auto set = [](const void* f) {
             cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
         };
@@ -96,8 +96,8 @@ launch_gemm_keys(cudaStream_t st, int mode, int metric, const float* Q, const fl
     if (mode == 1 && (ldk & 3) == 0) {
         CUtensorMap tq, tx;
         if (tc::make_tmap(&tq, Q, nq, d) && tc::make_tmap(&tx, X, cols, d)) {
-            static std::once_flag once;
-            std::call_once(once, [] {
+            static PerDeviceOnce once;
+            once.run([] {
                 cudaFuncSetAttribute((const void*)tc::gemm_keys_tc_kernel<KB2_METRIC_L2>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
                 cudaFuncSetAttribute((const void*)tc::gemm_keys_tc_kernel<KB2_METRIC_IP>,
@@ -156,8 +156,9 @@ struct IndexBase {
     float last_kernel_ms = 0.f;      // dominant kernel of the last search (IVF_PQ tensor-core engine: the filter kernel)
     float last_stage_ms = 0.f;       // whole list-scan stage of the last search (all engines)
     int last_engine = 0;             // 0: query-major scan kernels, 1: list-major tensor-core engine
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev_in = nullptr;
     DevBuf<unsigned long long> d_counter;
+    PinnedBuf h_counter;   // pinned landing zone of the per-search device counters (no pageable async copy)
 
     // per-search scratch (grow-only, reused across calls)
     DevBuf<float> s_q, s_keys, s_qn, s_out_dist, s_probe_dis;
@@ -178,9 +179,19 @@ struct IndexBase {
     }
 
     virtual ~IndexBase() {
-        if (ev0) cudaEventDestroy(ev0);
-        if (ev1) cudaEventDestroy(ev1);
+        for (cudaEvent_t e : {ev0, ev1, ev2, ev3, ev_in})
+            if (e) cudaEventDestroy(e);
         if (own_stream && stream) cudaStreamDestroy(stream);
+    }
+    // Stream contract: work runs on the handle's stream.  With the library-owned (non-blocking) stream, device buffers
+    // handed in by the caller may still be in flight on the caller's side: order our stream after everything already
+    // queued on the legacy default stream (which itself waits for all blocking streams, e.g. torch's default stream).
+    // Callers that produce inputs on their own NON-blocking stream pass it through kb2_index_set_stream instead.
+    void
+    wait_caller_work() {
+        if (!own_stream || !ev_in) return;
+        KB2_CUDA_CHECK(cudaEventRecord(ev_in, cudaStreamLegacy));
+        KB2_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_in, 0));
     }
     void
     init_common() {
@@ -192,13 +203,21 @@ struct IndexBase {
         KB2_CUDA_CHECK(cudaEventCreate(&ev1));
         KB2_CUDA_CHECK(cudaEventCreate(&ev2));
         KB2_CUDA_CHECK(cudaEventCreate(&ev3));
+        KB2_CUDA_CHECK(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
         d_counter.ensure(8);
+        h_counter.ensure(64);
     }
     void
     set_stream(cudaStream_t s) {
         if (own_stream && stream) cudaStreamDestroy(stream);
         stream = s;
         own_stream = false;
+    }
+    void
+    use_own_stream() {
+        if (own_stream) return;
+        KB2_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        own_stream = true;
     }
 
     // returns a device pointer to `count` floats of `src` (copying H2D on the stream if needed)
@@ -213,6 +232,8 @@ struct IndexBase {
     const uint8_t*
     bitset_to_device(const uint8_t* bits, int64_t nbits) {
         if (!bits || nbits <= 0) return nullptr;
+        // the kernels index the bitmap by any stored row: a shorter bitmap would be read out of bounds
+        KB2_REQUIRE(nbits >= bitset_rows(), KB2_INVALID_ARGS, "bitset has fewer bits than the index has rows");
         if (is_device_ptr(bits)) return bits;
         const size_t nbytes = (size_t)((nbits + 7) / 8);
         s_bitset.ensure(nbytes);
@@ -236,6 +257,7 @@ struct IndexBase {
     virtual void search(const float* q, int64_t nq, int k, const JsonObj& cfg, const uint8_t* bitset, int64_t nbits,
                         int64_t* out_ids, float* out_dist) = 0;
     virtual int64_t count() const = 0;
+    virtual int64_t bitset_rows() const { return count(); }   // rows a BitsetView must cover (whole index, also on a shard)
     virtual int64_t size_bytes() const = 0;
     virtual bool is_trained() const = 0;
     virtual bool has_raw() const = 0;
@@ -700,8 +722,10 @@ struct IvfIndex : IndexBase {
         const int64_t n = n_total;
         cudaStream_t st = stream;
         if (is_pq) {
-            // gather codes back: launch one thread per (row, m)
-            KB2_REQUIRE(false, KB2_NOT_IMPLEMENTED, "IVF_PQ add() after the first search is not supported yet");
+            // gather the codes back into insertion order: one thread per (row, m)
+            f_codes.alloc_exact((size_t)std::max<int64_t>(n, 1) * M);
+            if (n) unlayout_codes_kernel<<<grid1d(n * M, 256), 256, 0, st>>>(codes.p, pos_of_row.p, n, npad, M, G, f_codes.p);
+            f_codes_used = (size_t)n * M;
         }
         if (keeps_vecs()) {
             f_vecs.alloc_exact((size_t)std::max<int64_t>(n, 1) * dim);
@@ -1106,7 +1130,7 @@ struct IvfIndex : IndexBase {
             fp.out_dist = d_dist;
             launch_finalize(*this, fp, nq);
         }
-        unsigned long long hc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        unsigned long long* hc = (unsigned long long*)h_counter.p;
         KB2_CUDA_CHECK(cudaMemcpyAsync(hc, d_counter.p, 64, cudaMemcpyDeviceToHost, st));
         results_out(nq, k, out_ids, out_dist, d_ids, d_dist);
         KB2_REQUIRE(hc[1] == 0 && hc[5] == 0, KB2_INTERNAL_ERROR, "ivfpq_scan_kernel: unexpected shared-memory window base");
@@ -1178,24 +1202,54 @@ struct IvfIndex : IndexBase {
         imp_labels.insert(imp_labels.end(), ids, ids + sz);
         imp_codes.insert(imp_codes.end(), cds, cds + (size_t)sz * cs);
     }
+    // raw (refine=true): [n_raw][dim] rows addressed by label, or — raw_in_import_order — by the order of the import_list calls
     void
-    import_finish(const float* raw, int64_t n_raw) {
+    import_finish(const float* raw, int64_t n_raw, bool raw_in_import_order = false) {
         const int64_t n = (int64_t)imp_assign.size();
+        std::vector<int32_t> orig_of_row;   // row -> position in the import stream (only when raw_in_import_order)
+        // Rows were numbered in import (list) order.  The reference's ids are segment offsets 0..n-1 and a BitsetView /
+        // GetVectorByIds address vectors by that id (bitsetview.h:131-175), so when the labels are a permutation of
+        // 0..n-1 renumber the rows so that row == label: bitset tests, GetVectorByIds and add() then behave exactly as
+        // on an index built here.  Within a list the scan order becomes ascending id (the reference's insertion order).
+        {
+            bool perm = n > 0;
+            std::vector<uint8_t> seen((size_t)n, 0);
+            for (int64_t i = 0; i < n && perm; i++) {
+                const int64_t l = imp_labels[i];
+                if (l < 0 || l >= n || seen[l]) perm = false; else seen[l] = 1;
+            }
+            if (perm) {
+                const size_t cs = is_pq ? (size_t)M : (size_t)dim * 4;
+                std::vector<int32_t> a2((size_t)n);
+                std::vector<uint8_t> c2((size_t)n * cs);
+                if (raw_in_import_order) orig_of_row.resize((size_t)n);
+                for (int64_t i = 0; i < n; i++) {
+                    const int64_t l = imp_labels[i];
+                    if (raw_in_import_order) orig_of_row[l] = (int32_t)i;
+                    a2[l] = imp_assign[i];
+                    memcpy(c2.data() + (size_t)l * cs, imp_codes.data() + (size_t)i * cs, cs);
+                }
+                imp_assign.swap(a2);
+                imp_codes.swap(c2);
+                for (int64_t i = 0; i < n; i++) imp_labels[i] = i;
+            }
+            custom_labels = !perm;
+        }
         f_assign_used = 0;
         dev_append(f_assign, f_assign_used, imp_assign.data(), (size_t)n, stream);
-        custom_labels = true;
         f_labels_used = 0;
-        dev_append(f_labels, f_labels_used, imp_labels.data(), (size_t)n, stream);
+        if (custom_labels) dev_append(f_labels, f_labels_used, imp_labels.data(), (size_t)n, stream);
         if (is_pq) {
             f_codes_used = 0;
             dev_append(f_codes, f_codes_used, imp_codes.data(), imp_codes.size(), stream);
             if (refine) {
                 KB2_REQUIRE(raw != nullptr, KB2_INVALID_ARGS, "refine=true import needs the raw vectors");
-                // raw is in label order; our rows are import-order: gather raw[label[row]]
+                // gather the raw vector of every row: raw[label[row]], or raw[import position of row]
                 std::vector<int32_t> lab32(n);
                 for (int64_t i = 0; i < n; i++) {
-                    KB2_REQUIRE(imp_labels[i] >= 0 && imp_labels[i] < n_raw, KB2_INVALID_ARGS, "label outside raw data");
-                    lab32[i] = (int32_t)imp_labels[i];
+                    const int64_t src = raw_in_import_order ? (orig_of_row.empty() ? i : (int64_t)orig_of_row[i]) : imp_labels[i];
+                    KB2_REQUIRE(src >= 0 && src < n_raw, KB2_INVALID_ARGS, "label outside raw data");
+                    lab32[i] = (int32_t)src;
                 }
                 DevBuf<float> rbuf;
                 const float* draw = to_device(raw, (size_t)n_raw * dim, rbuf, false);

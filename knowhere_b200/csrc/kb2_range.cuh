@@ -152,8 +152,8 @@ inline void
 range_search_index(IndexBase& ix, const float* queries, int64_t nq, float radius, float range_filter, bool has_filter,
                    const JsonObj& cfg, const uint8_t* bitset, int64_t nbits, int64_t** out_lims, int64_t** out_ids,
                    float** out_dist) {
-    static std::once_flag once;
-    std::call_once(once, [] {
+    static PerDeviceOnce once;
+    once.run([] {
         cudaFuncSetAttribute((const void*)range_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
     });
     cudaStream_t st = ix.stream;
@@ -387,8 +387,8 @@ merge_topk_device(int metric, int world, int64_t nq, int k, const int64_t* in_id
         d_odist = b_odist.p;
     }
     const size_t smem = (size_t)world * k * 12 + 16;
-    static std::once_flag once;
-    std::call_once(once, [] {
+    static PerDeviceOnce once;
+    once.run([] {
         cudaFuncSetAttribute((const void*)merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
     });
     merge_topk_kernel<<<(unsigned)nq, 256, smem, st>>>(metric, world, nq, k, d_in_ids, d_in_dist, d_oids, d_odist);
@@ -475,6 +475,8 @@ deserialize_index(const uint8_t* blob, size_t size, int device) {
     const bool cosine = metric_raw == KB2_METRIC_COSINE;
     const int metric = cosine ? KB2_METRIC_IP : metric_raw;
     const int dim = r.get<int32_t>();
+    KB2_REQUIRE(dim > 0 && dim <= (1 << 20), KB2_INVALID_BINARY_SET, "bad dim in blob");
+    KB2_REQUIRE(metric == KB2_METRIC_L2 || metric == KB2_METRIC_IP, KB2_INVALID_BINARY_SET, "bad metric in blob");
     std::unique_ptr<IndexBase> ix;
     if (type == "FLAT") {
         auto* fi = new FlatIndex();
@@ -482,6 +484,7 @@ deserialize_index(const uint8_t* blob, size_t size, int device) {
         fi->type = type; fi->metric = metric; fi->dim = dim; fi->device = device;
         fi->init_common();
         const int64_t n = r.get<int64_t>();
+        KB2_REQUIRE(n >= 0 && (uint64_t)n <= size / ((size_t)dim * 4), KB2_INVALID_BINARY_SET, "bad row count in blob");
         const int custom = r.get<int32_t>();
         const float* data = (const float*)r.get_bytes((size_t)n * dim * 4);
         const int64_t* labels = custom ? (const int64_t*)r.get_bytes((size_t)n * 8) : nullptr;
@@ -501,6 +504,9 @@ deserialize_index(const uint8_t* blob, size_t size, int device) {
         iv->M = r.get<int32_t>();
         iv->nbits = r.get<int32_t>();
         iv->refine = r.get<int32_t>() != 0;
+        KB2_REQUIRE(nlist >= 1 && (uint64_t)nlist <= size / ((size_t)dim * 4), KB2_INVALID_BINARY_SET, "bad nlist in blob");
+        if (iv->is_pq)
+            KB2_REQUIRE(iv->M > 0 && dim % iv->M == 0 && iv->nbits == 8, KB2_INVALID_BINARY_SET, "bad m / nbits in blob");
         std::vector<float> c((size_t)nlist * dim);
         memcpy(c.data(), r.get_bytes(c.size() * 4), c.size() * 4);
         std::vector<float> pc;
@@ -513,6 +519,7 @@ deserialize_index(const uint8_t* blob, size_t size, int device) {
         std::vector<float> raw_rows;  // import order
         for (int64_t l = 0; l < nlist; l++) {
             const int64_t len = r.get<int64_t>();
+            KB2_REQUIRE(len >= 0 && (uint64_t)len <= size / 8, KB2_INVALID_BINARY_SET, "bad list length in blob");
             if (!len) continue;
             std::vector<int64_t> ids(len);
             memcpy(ids.data(), r.get_bytes(len * 8), len * 8);
@@ -526,15 +533,7 @@ deserialize_index(const uint8_t* blob, size_t size, int device) {
             }
         }
         const bool with_raw = iv->is_pq && iv->refine;
-        const bool saved_refine = iv->refine;
-        iv->refine = false;  // import_finish(label-ordered raw) is not what we have; set rows directly below
-        iv->import_finish(nullptr, 0);
-        iv->refine = saved_refine;
-        if (with_raw) {
-            iv->f_vecs_used = 0;
-            dev_append(iv->f_vecs, iv->f_vecs_used, raw_rows.data(), raw_rows.size(), iv->stream);
-            KB2_CUDA_CHECK(cudaStreamSynchronize(iv->stream));
-        }
+        iv->import_finish(with_raw ? raw_rows.data() : nullptr, with_raw ? (int64_t)(raw_rows.size() / dim) : 0, true);
     } else if (type == "HNSW") {
         auto* hn = new HnswIndex();
         ix.reset(hn);
