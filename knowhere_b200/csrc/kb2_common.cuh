@@ -124,6 +124,14 @@ round_up(int64_t v, int64_t a) {
     return (v + a - 1) / a * a;
 }
 
+// one RangeSearch hit as the device kernels emit it (kb2_range.cuh, kb2_hnsw.cuh)
+struct RangeHit {
+    int32_t q;
+    int32_t probe;   // IVF: rank of the probed list (max_empty_result_buckets); otherwise 0
+    uint32_t pos;    // position / internal row
+    float dist;
+};
+
 // ------------------------------------------------------------------ RAII device buffer
 template <typename T>
 struct DevBuf {

@@ -46,6 +46,18 @@ struct HnswSearchParams {
     int64_t* out_ids;
     float* out_dist;
     unsigned long long* stats;  // [0] ndis, [1] nhops
+    // filtered search / range search (hnsw_filtered_kernel)
+    const uint8_t* bitset;      // bit set => node filtered out (internal ids), or NULL
+    float k_alpha;              // filter_ratio * 0.7 (faiss_hnsw.cc:1425)
+    int range_mode;             // 0: top-k, 1: range search
+    float radius_key;           // range: keep key < radius_key (key = L2 distance, or -ip)
+    RangeHit* hits;             // range: global append buffer
+    unsigned long long* hit_count;
+    unsigned long long hit_cap;
+    int32_t* bfs_queue;         // range: [total_warps][queue_cap]
+    int queue_cap;
+    uint32_t* q_overflow;       // range: [nq] 1 = the BFS queue overflowed (host reruns that query with a larger queue)
+    const int32_t* q_list;      // optional: indices of the queries to run (second pass), nq = its length
 };
 
 constexpr int kHnswWarps = 4;  // warps (queries in flight) per CTA
@@ -122,6 +134,56 @@ hnsw_key2(const float* __restrict__ vecs, int d, const float* s_q, int32_t v0, i
     k1 = (METRIC == KB2_METRIC_L2) ? a1 : -a1;
 }
 
+// greedy descent from max_level to level 1 (HnswSearcher.h:116-170,334-356): first strict minimum over the link slots
+template <int METRIC>
+__device__ __forceinline__ void
+hnsw_descend(const HnswSearchParams& p, const float* s_q, int lane, int32_t& nearest, float& d_nearest,
+             unsigned long long& ndis_tot, unsigned long long& nhops_tot) {
+    for (int level = p.max_level; level >= 1; level--) {
+        for (;;) {
+            const int32_t prev = nearest;
+            const int64_t begin = p.offsets[prev] + p.cum[level];
+            const int64_t end = p.offsets[prev] + p.cum[level + 1];
+            bool done = false;
+            for (int64_t b = begin; b < end && !done; b += kWarp) {
+                const int32_t v = (b + lane < end) ? p.neighbors[b + lane] : -1;
+                const unsigned neg = __ballot_sync(0xffffffffu, v < 0);
+                const int cnt = neg ? (__ffs(neg) - 1) : kWarp;
+                float myk = INFINITY;
+                for (int j = 0; j < cnt; j += 2) {
+                    const int32_t va = __shfl_sync(0xffffffffu, v, j);
+                    float ka, kb = INFINITY;
+                    if (j + 1 < cnt) {
+                        const int32_t vb = __shfl_sync(0xffffffffu, v, j + 1);
+                        hnsw_key2<METRIC>(p.vecs, p.d, s_q, va, vb, lane, ka, kb);
+                    } else {
+                        ka = hnsw_key<METRIC>(p.vecs, p.d, s_q, va, lane);
+                    }
+                    if (lane == j) myk = ka;
+                    if (lane == j + 1) myk = kb;
+                }
+                ndis_tot += cnt;
+                // sequential "if (dis < d_nearest)" over the slots == first strict minimum
+                float bk = myk;
+                int bl = lane;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ok = __shfl_xor_sync(0xffffffffu, bk, o);
+                    const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+                    if (ok < bk || (ok == bk && ol < bl)) { bk = ok; bl = ol; }
+                }
+                if (bk < d_nearest) {
+                    d_nearest = bk;
+                    nearest = __shfl_sync(0xffffffffu, v, bl);
+                }
+                if (cnt < kWarp) done = true;
+            }
+            nhops_tot++;
+            if (nearest == prev) break;
+        }
+    }
+}
+
 // dynamic smem per warp: d floats (query, 16B aligned) + ef_cap * (4 + 4)
 template <int METRIC>
 __global__ void __launch_bounds__(kHnswWarps * 32)
@@ -151,49 +213,7 @@ hnsw_search_kernel(HnswSearchParams p) {
         // ---- greedy descent on the upper levels (HnswSearcher.h:116-170,334-356)
         int32_t nearest = p.entry_point;
         float d_nearest = hnsw_key<METRIC>(p.vecs, p.d, s_q, nearest, lane);
-        for (int level = p.max_level; level >= 1; level--) {
-            for (;;) {
-                const int32_t prev = nearest;
-                const int64_t begin = p.offsets[prev] + p.cum[level];
-                const int64_t end = p.offsets[prev] + p.cum[level + 1];
-                bool done = false;
-                for (int64_t b = begin; b < end && !done; b += kWarp) {
-                    const int32_t v = (b + lane < end) ? p.neighbors[b + lane] : -1;
-                    const unsigned neg = __ballot_sync(0xffffffffu, v < 0);
-                    const int cnt = neg ? (__ffs(neg) - 1) : kWarp;
-                    float myk = INFINITY;
-                    for (int j = 0; j < cnt; j += 2) {
-                        const int32_t va = __shfl_sync(0xffffffffu, v, j);
-                        float ka, kb = INFINITY;
-                        if (j + 1 < cnt) {
-                            const int32_t vb = __shfl_sync(0xffffffffu, v, j + 1);
-                            hnsw_key2<METRIC>(p.vecs, p.d, s_q, va, vb, lane, ka, kb);
-                        } else {
-                            ka = hnsw_key<METRIC>(p.vecs, p.d, s_q, va, lane);
-                        }
-                        if (lane == j) myk = ka;
-                        if (lane == j + 1) myk = kb;
-                    }
-                    ndis_tot += cnt;
-                    // sequential "if (dis < d_nearest)" over the slots == first strict minimum
-                    float bk = myk;
-                    int bl = lane;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const float ok = __shfl_xor_sync(0xffffffffu, bk, o);
-                        const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
-                        if (ok < bk || (ok == bk && ol < bl)) { bk = ok; bl = ol; }
-                    }
-                    if (bk < d_nearest) {
-                        d_nearest = bk;
-                        nearest = __shfl_sync(0xffffffffu, v, bl);
-                    }
-                    if (cnt < kWarp) done = true;
-                }
-                nhops_tot++;
-                if (nearest == prev) break;
-            }
-        }
+        hnsw_descend<METRIC>(p, s_q, lane, nearest, d_nearest, ndis_tot, nhops_tot);
 
         // ---- level 0 beam (HnswSearcher.h:296-332,390-432; Neighbor.h:46-150)
         const int cap = p.ef_cap;
@@ -331,6 +351,376 @@ hnsw_search_kernel(HnswSearchParams p) {
     }
 }
 
+
+// ============================================================================================
+// Filtered top-k search and range search (the reference always runs the two-pool searcher; the plain kernel above is
+// its all-members special case).
+//   NeighborSetDoublePopList                      K/impl/Neighbor.h:155-210
+//   evaluate_single_node with kAlpha              K/impl/HnswSearcher.h:173-293 (:213-225 accumulated_alpha)
+//   search / range_search                         K/impl/HnswSearcher.h:358-432, 435-553
+// Valid pool: sorted array with a cursor and "checked" flags (capacity cap).  Invalid pool (filtered-out nodes that
+// are still traversed): sorted array of capacity cap, popped from the front; a filtered node is admitted only while
+// it is closer than the valid pool's back.  A filtered fresh neighbour costs a distance only every 1/kAlpha-th time
+// (accumulated_alpha), evaluated in link-slot order like the reference.
+// dynamic smem per warp: d floats + 2 * cap * 8
+// ============================================================================================
+__device__ __forceinline__ int
+hnsw_upper_bound(const float* dist, int size, float key, int lane) {
+    int pos = 0;
+    for (int base = 0; base < size; base += kWarp) {
+        const int i = base + lane;
+        const bool le = (i < size) && (dist[i] <= key);
+        pos += __popc(__ballot_sync(0xffffffffu, le));
+    }
+    return pos;
+}
+// insert (key, idv) at pos < cap, dropping the last entry when full; returns the new size
+__device__ __forceinline__ int
+hnsw_shift_insert(float* dist, uint32_t* id, int size, int cap, int pos, float key, uint32_t idv, int lane) {
+    const int newsize = min(size + 1, cap);
+    for (int hi = newsize - 1; hi > pos; hi -= kWarp) {
+        const int i = hi - lane;
+        float td = 0.f;
+        uint32_t ti = 0;
+        if (i > pos) { td = dist[i - 1]; ti = id[i - 1]; }
+        __syncwarp();
+        if (i > pos) { dist[i] = td; id[i] = ti; }
+        __syncwarp();
+    }
+    if (lane == 0) { dist[pos] = key; id[pos] = idv; }
+    __syncwarp();
+    return newsize;
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(kHnswWarps * 32)
+hnsw_filtered_kernel(HnswSearchParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int dpad = (p.d + 3) & ~3;
+    const int cap = p.ef_cap;
+    const size_t per_warp = (size_t)dpad * 4 + (size_t)cap * 16;
+    unsigned char* mine = smem_raw + (size_t)warp * per_warp;
+    float* s_q = (float*)mine;
+    float* v_dist = (float*)(mine + (size_t)dpad * 4);
+    uint32_t* v_id = (uint32_t*)(v_dist + cap);   // bit31 = checked
+    float* i_dist = (float*)(v_id + cap);
+    uint32_t* i_id = (uint32_t*)(i_dist + cap);
+
+    const int64_t gw = (int64_t)blockIdx.x * kHnswWarps + warp;
+    uint32_t* vis = p.visited + gw * p.nwords;
+    int32_t* vlog = p.vis_log + gw * p.log_cap;
+    int32_t* queue = p.bfs_queue ? p.bfs_queue + gw * (int64_t)p.queue_cap : nullptr;
+    unsigned long long ndis_tot = 0, nhops_tot = 0;
+
+    for (;;) {
+        int qi = 0;
+        if (lane == 0) qi = atomicAdd(p.next_query, 1);
+        qi = __shfl_sync(0xffffffffu, qi, 0);
+        if (qi >= p.nq) break;
+        const int q = p.q_list ? p.q_list[qi] : qi;
+        for (int j = lane; j < p.d; j += kWarp) s_q[j] = p.queries[(int64_t)q * p.d + j];
+        __syncwarp();
+
+        int32_t nearest = p.entry_point;
+        float d_nearest = hnsw_key<METRIC>(p.vecs, p.d, s_q, nearest, lane);
+        hnsw_descend<METRIC>(p, s_q, lane, nearest, d_nearest, ndis_tot, nhops_tot);
+
+        int v_size = 0, v_cur = 0, i_size = 0, logn = 0;
+        bool log_overflow = false;
+        {
+            const bool member = !(p.bitset && bit_is_set(p.bitset, nearest));
+            if (lane == 0) {
+                if (member) { v_dist[0] = d_nearest; v_id[0] = (uint32_t)nearest; }
+                else { i_dist[0] = d_nearest; i_id[0] = (uint32_t)nearest; }
+                atomicOr(&vis[nearest >> 5], 1u << (nearest & 31));
+                vlog[0] = nearest;
+            }
+            if (member) v_size = 1; else i_size = 1;
+            logn = 1;
+        }
+        __syncwarp();
+        float alpha = 1.0f;   // initial_accumulated_alpha
+
+        for (;;) {
+            const float back = (v_size < cap) ? FLT_MAX : v_dist[cap - 1];
+            const bool has_res = v_cur < v_size, has_cand = i_size > 0;
+            if (!(has_res || (has_cand && i_dist[0] < back))) break;
+            const bool take_inv = has_cand && (!has_res || i_dist[0] < v_dist[v_cur]);
+            uint32_t cur_id;
+            if (take_inv) {
+                cur_id = i_id[0];
+                __syncwarp();
+                for (int base = 0; base < i_size - 1; base += kWarp) {   // pop front: shift left by one
+                    const int i = base + lane;
+                    float td = 0.f;
+                    uint32_t ti = 0;
+                    if (i < i_size - 1) { td = i_dist[i + 1]; ti = i_id[i + 1]; }
+                    __syncwarp();
+                    if (i < i_size - 1) { i_dist[i] = td; i_id[i] = ti; }
+                    __syncwarp();
+                }
+                i_size--;
+            } else {
+                cur_id = v_id[v_cur] & 0x7fffffffu;
+                __syncwarp();
+                if (lane == 0) v_id[v_cur] |= 0x80000000u;
+                __syncwarp();
+                v_cur++;
+                while (v_cur < v_size && (v_id[v_cur] & 0x80000000u)) v_cur++;
+            }
+            nhops_tot++;
+
+            const int64_t begin = p.offsets[cur_id] + p.cum[0];
+            const int64_t end = p.offsets[cur_id] + p.cum[1];
+            bool done = false;
+            for (int64_t b = begin; b < end && !done; b += kWarp) {
+                const int32_t v = (b + lane < end) ? p.neighbors[b + lane] : -1;
+                const unsigned neg = __ballot_sync(0xffffffffu, v < 0);
+                const int cnt = neg ? (__ffs(neg) - 1) : kWarp;
+                if (cnt < kWarp) done = true;
+                bool fresh = false, member = true;
+                if (lane < cnt) {
+                    const uint32_t bit = 1u << (v & 31);
+                    const uint32_t old = atomicOr(&vis[v >> 5], bit);
+                    fresh = !(old & bit);
+                    if (fresh && p.bitset) member = !bit_is_set(p.bitset, v);
+                }
+                const unsigned fm = __ballot_sync(0xffffffffu, fresh);
+                const int nf = __popc(fm);
+                if (nf == 0) continue;
+                if (logn + nf <= p.log_cap) {
+                    if (fresh) vlog[logn + __popc(fm & ((1u << lane) - 1))] = v;
+                } else {
+                    log_overflow = true;
+                }
+                logn += nf;
+                // which filtered-out fresh nodes are still evaluated: accumulated_alpha walk in slot order
+                const unsigned inv_m = __ballot_sync(0xffffffffu, fresh && !member);
+                unsigned take_m = fm & ~inv_m;
+                {
+                    unsigned rem = inv_m;
+                    while (rem) {
+                        const int j = __ffs(rem) - 1;
+                        rem &= rem - 1;
+                        alpha += p.k_alpha;
+                        if (alpha < 1.0f) continue;
+                        alpha -= 1.0f;
+                        take_m |= 1u << j;
+                    }
+                }
+                ndis_tot += __popc(take_m);
+                float myk = INFINITY;
+                {
+                    unsigned rem = take_m;
+                    while (rem) {
+                        const int ja = __ffs(rem) - 1;
+                        rem &= rem - 1;
+                        const int32_t va = __shfl_sync(0xffffffffu, v, ja);
+                        float ka, kb = INFINITY;
+                        int jb = -1;
+                        if (rem) {
+                            jb = __ffs(rem) - 1;
+                            rem &= rem - 1;
+                            const int32_t vb = __shfl_sync(0xffffffffu, v, jb);
+                            hnsw_key2<METRIC>(p.vecs, p.d, s_q, va, vb, lane, ka, kb);
+                        } else {
+                            ka = hnsw_key<METRIC>(p.vecs, p.d, s_q, va, lane);
+                        }
+                        if (lane == ja) myk = ka;
+                        if (lane == jb) myk = kb;
+                    }
+                }
+                unsigned ins = take_m;
+                while (ins) {
+                    const int j = __ffs(ins) - 1;
+                    ins &= ins - 1;
+                    const float key = __shfl_sync(0xffffffffu, myk, j);
+                    const uint32_t id = (uint32_t)__shfl_sync(0xffffffffu, v, j);
+                    if (!((inv_m >> j) & 1u)) {
+                        const int pos = hnsw_upper_bound(v_dist, v_size, key, lane);
+                        if (pos >= cap) continue;
+                        v_size = hnsw_shift_insert(v_dist, v_id, v_size, cap, pos, key, id, lane);
+                        if (pos < v_cur) v_cur = pos;
+                    } else {
+                        const float bk = (v_size < cap) ? FLT_MAX : v_dist[cap - 1];
+                        if (!(key < bk)) continue;
+                        const int pos = hnsw_upper_bound(i_dist, i_size, key, lane);
+                        if (pos >= cap) continue;
+                        i_size = hnsw_shift_insert(i_dist, i_id, i_size, cap, pos, key, id, lane);
+                    }
+                }
+            }
+        }
+
+        // clear the visited bits of the traversal
+        __syncwarp();
+        if (!log_overflow) {
+            for (int i = lane; i < logn; i += kWarp) vis[vlog[i] >> 5] = 0u;
+        } else {
+            for (int64_t i = lane; i < p.nwords; i += kWarp) vis[i] = 0u;
+        }
+        __syncwarp();
+
+        if (!p.range_mode) {
+            const int len = min(v_size, p.k);
+            for (int i = lane; i < p.k; i += kWarp) {
+                const int64_t o = (int64_t)q * p.k + i;
+                if (i < len) {
+                    const int64_t id = (int64_t)(v_id[i] & 0x7fffffffu);
+                    p.out_ids[o] = p.labels ? p.labels[id] : id;
+                    p.out_dist[o] = (METRIC == KB2_METRIC_L2) ? v_dist[i] : -v_dist[i];
+                } else {
+                    p.out_ids[o] = -1;
+                    p.out_dist[o] = (METRIC == KB2_METRIC_L2) ? FLT_MAX : -FLT_MAX;
+                }
+            }
+            __syncwarp();
+            continue;
+        }
+
+        // ---- range search, second phase (HnswSearcher.h:497-545): closure of the in-range valid candidates over the
+        //      level-0 links; a node is expanded iff it is a member with key < radius (so the result is order-free)
+        int qh = 0, qt = 0;           // queue head / tail (entries [qh, qt) pending)
+        bool q_over = false;
+        logn = 0;
+        log_overflow = false;
+        auto emit = [&](uint32_t id, float key, bool mine_) {   // lanes with mine_ append one hit each
+            const unsigned m = __ballot_sync(0xffffffffu, mine_);
+            if (!m) return;
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(p.hit_count, (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (mine_) {
+                const unsigned long long slot = base + __popc(m & ((1u << lane) - 1));
+                if (slot < p.hit_cap) {
+                    RangeHit h;
+                    h.q = q;
+                    h.probe = 0;
+                    h.pos = id;
+                    h.dist = (METRIC == KB2_METRIC_L2) ? key : -key;
+                    p.hits[slot] = h;
+                }
+                const int qs = qt + __popc(m & ((1u << lane) - 1));
+                if (qs < p.queue_cap) queue[qs] = (int32_t)id; else q_over = true;
+            }
+            qt += __popc(m);
+            q_over = __any_sync(0xffffffffu, q_over);
+            // remember the visited bit for the clean-up
+        };
+        for (int base = 0; base < v_size; base += kWarp) {
+            const int i = base + lane;
+            const bool ok = i < v_size && v_dist[i] < p.radius_key;
+            const uint32_t id = ok ? (v_id[i] & 0x7fffffffu) : 0u;
+            if (ok) atomicOr(&vis[id >> 5], 1u << (id & 31));
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (logn + __popc(m) <= p.log_cap) {
+                if (ok) vlog[logn + __popc(m & ((1u << lane) - 1))] = (int32_t)id;
+            } else {
+                log_overflow = true;
+            }
+            logn += __popc(m);
+            emit(id, ok ? v_dist[i] : 0.f, ok);
+        }
+        while (qh < min(qt, p.queue_cap) && !q_over) {
+            const int32_t cur = queue[qh++];
+            const int64_t begin = p.offsets[cur] + p.cum[0];
+            const int64_t end = p.offsets[cur] + p.cum[1];
+            bool done = false;
+            for (int64_t b = begin; b < end && !done; b += kWarp) {
+                const int32_t v = (b + lane < end) ? p.neighbors[b + lane] : -1;
+                const unsigned neg = __ballot_sync(0xffffffffu, v < 0);
+                const int cnt = neg ? (__ffs(neg) - 1) : kWarp;
+                if (cnt < kWarp) done = true;
+                bool fresh = false, member = true;
+                if (lane < cnt) {
+                    const uint32_t bit = 1u << (v & 31);
+                    const uint32_t old = atomicOr(&vis[v >> 5], bit);
+                    fresh = !(old & bit);
+                    if (fresh && p.bitset) member = !bit_is_set(p.bitset, v);
+                }
+                const unsigned fm = __ballot_sync(0xffffffffu, fresh);
+                const int nf = __popc(fm);
+                if (nf == 0) continue;
+                if (logn + nf <= p.log_cap) {
+                    if (fresh) vlog[logn + __popc(fm & ((1u << lane) - 1))] = v;
+                } else {
+                    log_overflow = true;
+                }
+                logn += nf;
+                const unsigned take_m = __ballot_sync(0xffffffffu, fresh && member);
+                ndis_tot += __popc(take_m);
+                float myk = INFINITY;
+                unsigned rem = take_m;
+                while (rem) {
+                    const int ja = __ffs(rem) - 1;
+                    rem &= rem - 1;
+                    const int32_t va = __shfl_sync(0xffffffffu, v, ja);
+                    float ka, kb = INFINITY;
+                    int jb = -1;
+                    if (rem) {
+                        jb = __ffs(rem) - 1;
+                        rem &= rem - 1;
+                        const int32_t vb = __shfl_sync(0xffffffffu, v, jb);
+                        hnsw_key2<METRIC>(p.vecs, p.d, s_q, va, vb, lane, ka, kb);
+                    } else {
+                        ka = hnsw_key<METRIC>(p.vecs, p.d, s_q, va, lane);
+                    }
+                    if (lane == ja) myk = ka;
+                    if (lane == jb) myk = kb;
+                }
+                const bool hit = ((take_m >> lane) & 1u) && myk < p.radius_key;
+                emit((uint32_t)v, myk, hit);
+            }
+        }
+        if (q_over && lane == 0) p.q_overflow[q] = 1u;
+        __syncwarp();
+        if (!log_overflow) {
+            for (int i = lane; i < logn; i += kWarp) vis[vlog[i] >> 5] = 0u;
+        } else {
+            for (int64_t i = lane; i < p.nwords; i += kWarp) vis[i] = 0u;
+        }
+        __syncwarp();
+    }
+    if (p.stats && lane == 0) {
+        atomicAdd(&p.stats[0], ndis_tot);
+        atomicAdd(&p.stats[1], nhops_tot);
+    }
+}
+
+// number of set bits among the first nbits of a bitmap (grid-stride, one atomic per CTA)
+__global__ void __launch_bounds__(256)
+bitset_count_kernel(const uint8_t* __restrict__ bits, int64_t nbits, unsigned long long* __restrict__ out) {
+    unsigned long long acc = 0;
+    const int64_t nbytes = (nbits + 7) >> 3;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbytes; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t b = bits[i];
+        if (i == nbytes - 1 && (nbits & 7)) b &= (1u << (nbits & 7)) - 1u;
+        acc += __popc(b);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+// queries whose result row holds fewer than min(k, n_valid) ids -> compact list (brute-force fallback, faiss_hnsw.cc:1464-1478)
+__global__ void __launch_bounds__(256)
+short_rows_kernel(const int64_t* __restrict__ ids, int64_t nq, int k, int64_t n_valid, int32_t* __restrict__ list,
+                  uint32_t* __restrict__ count) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    int real = 0;
+    for (int j = 0; j < k; j++) real += ids[q * k + j] >= 0;
+    if (real < k && real < n_valid) list[atomicAdd(count, 1u)] = (int32_t)q;
+}
+__global__ void
+scatter_result_rows_kernel(const int64_t* __restrict__ src_ids, const float* __restrict__ src_dist, const int32_t* __restrict__ list,
+                           int64_t n, int k, int64_t* __restrict__ dst_ids, float* __restrict__ dst_dist) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * k) return;
+    const int64_t i = t / k, j = t % k;
+    dst_ids[(int64_t)list[i] * k + j] = src_ids[t];
+    dst_dist[(int64_t)list[i] * k + j] = src_dist[t];
+}
+
 // ============================================================================================
 struct HnswIndex : IndexBase {
     int M = 30, efConstruction = 360;
@@ -343,8 +733,10 @@ struct HnswIndex : IndexBase {
     std::vector<int64_t> h_labels;
     bool custom_labels = false;
     // device
-    DevBuf<float> d_vecs;
-    DevBuf<int32_t> d_neighbors, d_cum, d_vlog;
+    DevBuf<float> d_vecs, d_norms, s_bf_q, s_bf_dist;
+    DevBuf<int32_t> d_neighbors, d_cum, d_vlog, s_short, d_queue;
+    DevBuf<int64_t> s_bf_ids;
+    DevBuf<uint32_t> d_qover;
     DevBuf<int64_t> d_offsets, d_labels;
     DevBuf<uint32_t> d_visited;
     DevBuf<int> d_next;
@@ -610,53 +1002,82 @@ struct HnswIndex : IndexBase {
             KB2_CUDA_CHECK(cudaMemcpyAsync(d_labels.p, h_labels.data(), h_labels.size() * 8, cudaMemcpyHostToDevice, stream));
         }
         d_next.ensure(1);
+        d_norms.alloc_exact((size_t)n);   // brute-force fallback over the stored vectors
+        row_norms_kernel<<<grid1d(n * 32, 256), 256, 0, stream>>>(d_vecs.p, n, dim, d_norms.p);
         KB2_CUDA_CHECK(cudaStreamSynchronize(stream));
         uploaded = true;
     }
 
-    void
-    search(const float* q, int64_t nq, int k, const JsonObj& cfg, const uint8_t* bitset, int64_t, int64_t* out_ids,
-           float* out_dist) override {
-        KB2_REQUIRE(n > 0 && entry_point >= 0, KB2_EMPTY_INDEX, "index is empty");
-        KB2_REQUIRE(bitset == nullptr, KB2_NOT_IMPLEMENTED, "HNSW: bitset-filtered search is not implemented yet");
-        upload();
+    static void
+    init_attrs() {
         static PerDeviceOnce once;
         once.run([] {
-            cudaFuncSetAttribute((const void*)hnsw_search_kernel<KB2_METRIC_L2>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
-            cudaFuncSetAttribute((const void*)hnsw_search_kernel<KB2_METRIC_IP>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+            for (const void* f : {(const void*)hnsw_search_kernel<KB2_METRIC_L2>, (const void*)hnsw_search_kernel<KB2_METRIC_IP>,
+                                  (const void*)hnsw_filtered_kernel<KB2_METRIC_L2>, (const void*)hnsw_filtered_kernel<KB2_METRIC_IP>})
+                cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
         });
-        // base_hnsw_config.h:40-71: search key is "ef", default max(k,16), must be >= k
-        int ef = (int)cfg.get_int("ef", std::max(k, 16));
-        KB2_REQUIRE(ef >= k, KB2_OUT_OF_RANGE_IN_JSON, "ef must be >= k");
-        const int ef_cap = std::max(ef, k);
-        cudaStream_t st = stream;
-        const float* dq = to_device(q, (size_t)nq * dim, s_q);
-        const bool dev_out = is_device_ptr(out_ids);
-        int64_t* d_ids = out_ids;
-        float* d_dist = out_dist;
-        if (!dev_out) {
-            s_out_ids.ensure((size_t)nq * k);
-            s_out_dist.ensure((size_t)nq * k);
-            d_ids = s_out_ids.p;
-            d_dist = s_out_dist.p;
-        }
+    }
+
+    // exact scan of the stored vectors (the reference's brute-force wrapper: IndexConditionalWrapper.cc:103-200)
+    void
+    brute_force(const float* dq, int64_t nq, int k, const uint8_t* dbits, int64_t* d_ids, float* d_dist) {
+        DensePlan pl = dense_candidates(*this, dq, nq, d_vecs.p, d_norms.p, n, dim, metric, k + 16, dbits, nullptr);
+        FinalizeParams fp{};
+        fp.partial = s_partial.p;
+        fp.partial_stride = pl.stride();
+        fp.n_partial = pl.used * pl.Ksel;
+        fp.k_sel = std::min(pl.Ksel, k + 16);
+        fp.k_out = k;
+        fp.labels = custom_labels ? d_labels.p : nullptr;
+        fp.rerank = 1;
+        fp.raw = d_vecs.p;
+        fp.raw_by_pos = 1;
+        fp.queries = dq;
+        fp.d = dim;
+        fp.metric = metric;
+        fp.out_ids = d_ids;
+        fp.out_dist = d_dist;
+        launch_finalize(*this, fp, nq);
+    }
+
+    // set bits among the first n of the (device) bitmap
+    int64_t
+    count_filtered(const uint8_t* dbits) {
+        if (!dbits) return 0;
+        KB2_CUDA_CHECK(cudaMemsetAsync(d_counter.p + 4, 0, 8, stream));
+        bitset_count_kernel<<<std::min<int64_t>(1024, (n / 8 + 255) / 256 + 1), 256, 0, stream>>>(dbits, n, d_counter.p + 4);
+        unsigned long long* hc = (unsigned long long*)h_counter.p;
+        KB2_CUDA_CHECK(cudaMemcpyAsync(hc, d_counter.p + 4, 8, cudaMemcpyDeviceToHost, stream));
+        KB2_CUDA_CHECK(cudaStreamSynchronize(stream));
+        return (int64_t)hc[0];
+    }
+
+    struct Launch {
+        int grid;
+        int64_t total_warps, nwords;
+        int log_cap;
+        size_t smem;
+    };
+    Launch
+    plan_launch(int64_t nq, int ef_cap, bool two_pools) {
+        Launch L;
         const int dpad = (dim + 3) & ~3;
-        const size_t smem = kHnswWarps * ((size_t)dpad * 4 + (size_t)ef_cap * 8);
-        KB2_REQUIRE(smem <= (size_t)kMaxDynSmem, KB2_OUT_OF_RANGE_IN_JSON, "ef / dim too large for shared memory");
-        const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)kMaxDynSmem / std::max<size_t>(smem, 1)));
-        const int grid = (int)std::min<int64_t>((nq + kHnswWarps - 1) / kHnswWarps, (int64_t)kNumSMs * ctas_per_sm);
-        const int64_t total_warps = (int64_t)grid * kHnswWarps;
-        const int64_t nwords = (n + 31) / 32;
-        const int log_cap = (int)std::min<int64_t>(n, (int64_t)ef_cap * h_cum[1] * 4 + 256);
-        if (d_visited.n < (size_t)(total_warps * nwords)) {
-            d_visited.ensure((size_t)(total_warps * nwords));
-            KB2_CUDA_CHECK(cudaMemsetAsync(d_visited.p, 0, (size_t)(total_warps * nwords) * 4, st));
+        L.smem = kHnswWarps * ((size_t)dpad * 4 + (size_t)ef_cap * (two_pools ? 16 : 8));
+        KB2_REQUIRE(L.smem <= (size_t)kMaxDynSmem, KB2_OUT_OF_RANGE_IN_JSON, "ef / dim too large for shared memory");
+        const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)kMaxDynSmem / std::max<size_t>(L.smem, 1)));
+        L.grid = (int)std::min<int64_t>((nq + kHnswWarps - 1) / kHnswWarps, (int64_t)kNumSMs * ctas_per_sm);
+        L.total_warps = (int64_t)L.grid * kHnswWarps;
+        L.nwords = (n + 31) / 32;
+        L.log_cap = (int)std::min<int64_t>(n, (int64_t)ef_cap * h_cum[1] * 4 + 256);
+        if (d_visited.n < (size_t)(L.total_warps * L.nwords)) {
+            d_visited.ensure((size_t)(L.total_warps * L.nwords));
+            KB2_CUDA_CHECK(cudaMemsetAsync(d_visited.p, 0, (size_t)(L.total_warps * L.nwords) * 4, stream));
         }
-        d_vlog.ensure((size_t)(total_warps * log_cap));
-        KB2_CUDA_CHECK(cudaMemsetAsync(d_next.p, 0, 4, st));
-        KB2_CUDA_CHECK(cudaMemsetAsync(d_counter.p, 0, 16, st));
+        d_vlog.ensure((size_t)(L.total_warps * L.log_cap));
+        return L;
+    }
+    HnswSearchParams
+    base_params(const float* dq, int64_t nq, int ef_cap, int k, const Launch& L) {
         HnswSearchParams p{};
         p.vecs = d_vecs.p;
         p.d = dim;
@@ -672,32 +1093,195 @@ struct HnswIndex : IndexBase {
         p.ef_cap = ef_cap;
         p.k = k;
         p.visited = d_visited.p;
-        p.nwords = nwords;
+        p.nwords = L.nwords;
         p.vis_log = d_vlog.p;
-        p.log_cap = log_cap;
+        p.log_cap = L.log_cap;
         p.next_query = d_next.p;
         p.labels = custom_labels ? d_labels.p : nullptr;
-        p.out_ids = d_ids;
-        p.out_dist = d_dist;
         p.stats = d_counter.p;
+        return p;
+    }
+
+    void
+    search(const float* q, int64_t nq, int k, const JsonObj& cfg, const uint8_t* bitset, int64_t nbits, int64_t* out_ids,
+           float* out_dist) override {
+        KB2_REQUIRE(n > 0 && entry_point >= 0, KB2_EMPTY_INDEX, "index is empty");
+        upload();
+        init_attrs();
+        // base_hnsw_config.h:40-71: search key is "ef", default max(k,16), must be >= k
+        int ef = (int)cfg.get_int("ef", std::max(k, 16));
+        KB2_REQUIRE(ef >= k, KB2_OUT_OF_RANGE_IN_JSON, "ef must be >= k");
+        const int ef_cap = std::max(ef, k);
+        cudaStream_t st = stream;
+        const float* dq = to_device(q, (size_t)nq * dim, s_q);
+        const uint8_t* dbits = bitset_to_device(bitset, nbits);
+        const bool dev_out = is_device_ptr(out_ids);
+        int64_t* d_ids = out_ids;
+        float* d_dist = out_dist;
+        if (!dev_out) {
+            s_out_ids.ensure((size_t)nq * k);
+            s_out_dist.ensure((size_t)nq * k);
+            d_ids = s_out_ids.p;
+            d_dist = s_out_dist.p;
+        }
+        // WhetherPerformBruteForceSearch (IndexConditionalWrapper.cc:35-62): huge k or an almost-all-filtered bitset
+        const int64_t n_filtered = count_filtered(dbits);
+        const int64_t n_valid = n - n_filtered;
+        bool bf = (double)k >= (double)n * 0.5;
+        if (dbits) bf = bf || (double)n_filtered >= (double)n * 0.93 || (double)k >= (double)n_valid * 0.5;
+        KB2_CUDA_CHECK(cudaMemsetAsync(d_counter.p, 0, 16, st));
         if (timing) KB2_CUDA_CHECK(cudaEventRecord(ev0, st));
-        if (metric == KB2_METRIC_L2)
-            hnsw_search_kernel<KB2_METRIC_L2><<<grid, kHnswWarps * 32, smem, st>>>(p);
-        else
-            hnsw_search_kernel<KB2_METRIC_IP><<<grid, kHnswWarps * 32, smem, st>>>(p);
+        if (bf) {
+            KB2_REQUIRE(k <= kMaxK - 16, KB2_INVALID_ARGS, "k out of range (1..1008)");
+            brute_force(dq, nq, k, dbits, d_ids, d_dist);
+        } else {
+            const Launch L = plan_launch(nq, ef_cap, dbits != nullptr);
+            KB2_CUDA_CHECK(cudaMemsetAsync(d_next.p, 0, 4, st));
+            HnswSearchParams p = base_params(dq, nq, ef_cap, k, L);
+            p.out_ids = d_ids;
+            p.out_dist = d_dist;
+            if (!dbits) {
+                if (metric == KB2_METRIC_L2)
+                    hnsw_search_kernel<KB2_METRIC_L2><<<L.grid, kHnswWarps * 32, L.smem, st>>>(p);
+                else
+                    hnsw_search_kernel<KB2_METRIC_IP><<<L.grid, kHnswWarps * 32, L.smem, st>>>(p);
+            } else {
+                p.bitset = dbits;
+                p.k_alpha = (float)((double)n_filtered / (double)n) * 0.7f;   // faiss_hnsw.cc:1425
+                if (metric == KB2_METRIC_L2)
+                    hnsw_filtered_kernel<KB2_METRIC_L2><<<L.grid, kHnswWarps * 32, L.smem, st>>>(p);
+                else
+                    hnsw_filtered_kernel<KB2_METRIC_IP><<<L.grid, kHnswWarps * 32, L.smem, st>>>(p);
+            }
+            last.launches++;
+            KB2_CUDA_CHECK(cudaGetLastError());
+        }
         if (timing) KB2_CUDA_CHECK(cudaEventRecord(ev1, st));
-        last.launches++;
-        KB2_CUDA_CHECK(cudaGetLastError());
-        unsigned long long hs[2] = {0, 0};
+        // rows with fewer than k results although more valid vectors exist: exact fallback (faiss_hnsw.cc:1464-1478)
+        if (dbits && !bf && !cfg.get_bool("disable_fallback_brute_force", false) && k <= kMaxK - 16) {
+            s_short.ensure((size_t)nq + 1);
+            KB2_CUDA_CHECK(cudaMemsetAsync(s_short.p, 0, 4, st));
+            short_rows_kernel<<<grid1d(nq, 256), 256, 0, st>>>(d_ids, nq, k, n_valid, s_short.p + 1, (uint32_t*)s_short.p);
+            uint32_t* hc = (uint32_t*)h_counter.p + 8;
+            KB2_CUDA_CHECK(cudaMemcpyAsync(hc, s_short.p, 4, cudaMemcpyDeviceToHost, st));
+            KB2_CUDA_CHECK(cudaStreamSynchronize(st));
+            const int64_t ns = hc[0];
+            if (ns > 0) {
+                s_bf_q.ensure((size_t)ns * dim);
+                s_bf_ids.ensure((size_t)ns * k);
+                s_bf_dist.ensure((size_t)ns * k);
+                gather_rows_kernel<<<grid1d(ns * 32, 256), 256, 0, st>>>(dq, s_short.p + 1, ns, dim, dim, s_bf_q.p);
+                brute_force(s_bf_q.p, ns, k, dbits, s_bf_ids.p, s_bf_dist.p);
+                scatter_result_rows_kernel<<<grid1d(ns * k, 256), 256, 0, st>>>(s_bf_ids.p, s_bf_dist.p, s_short.p + 1, ns, k, d_ids,
+                                                                             d_dist);
+                KB2_CUDA_CHECK(cudaGetLastError());
+                last.flagged = ns;
+            }
+        }
+        unsigned long long* hs = (unsigned long long*)h_counter.p;
         KB2_CUDA_CHECK(cudaMemcpyAsync(hs, d_counter.p, 16, cudaMemcpyDeviceToHost, st));
         results_out(nq, k, out_ids, out_dist, d_ids, d_dist);
-        last_ndis = (int64_t)hs[0];
-        last_nhops = (int64_t)hs[1];
+        last_ndis = bf ? nq * n_valid : (int64_t)hs[0];
+        last_nhops = bf ? 0 : (int64_t)hs[1];
         last.codes = last_ndis;
         last.code_bytes = last_ndis * (int64_t)dim * 4 + last_nhops * (int64_t)h_cum[1] * 4;
         last.pairs = last_nhops;
         if (timing) KB2_CUDA_CHECK(cudaEventElapsedTime(&last_kernel_ms, ev0, ev1));
     }
+
+    // RangeSearch (faiss_hnsw.cc:1631-1800 -> IndexHNSWWrapper.cc:207-400 -> HnswSearcher.h:435-553): appends every hit
+    // to `hits` (device) and returns the count; queries whose BFS queue overflowed are rerun with a queue of n entries.
+    // `bf_out` is set when the reference would run the brute-force range search instead (IndexConditionalWrapper.cc:68-97).
+    uint64_t
+    range_hits(const float* dq, int64_t nq, float radius, const JsonObj& cfg, const uint8_t* dbits, DevBuf<RangeHit>& hits,
+               bool& bf_out) {
+        KB2_REQUIRE(n > 0 && entry_point >= 0, KB2_EMPTY_INDEX, "index is empty");
+        upload();
+        init_attrs();
+        const int ef = (int)cfg.get_int("ef", 16);
+        KB2_REQUIRE(ef >= 1, KB2_OUT_OF_RANGE_IN_JSON, "ef must be positive");
+        const int64_t n_filtered = count_filtered(dbits);
+        const int64_t n_valid = n - n_filtered;
+        bf_out = (double)ef >= (double)n * 0.5;
+        if (dbits) bf_out = bf_out || (double)n_filtered >= (double)n * 0.97 || (double)ef >= (double)n_valid * 0.97;
+        if (bf_out) return 0;
+        cudaStream_t st = stream;
+        const Launch L = plan_launch(nq, ef, true);
+        d_qover.ensure((size_t)nq);
+        DevBuf<unsigned long long> cnt;
+        cnt.ensure(1);
+        unsigned long long cap = (unsigned long long)std::max<int64_t>(1 << 20, nq * 256);
+        std::vector<uint32_t> h_over(nq);
+        std::vector<int32_t> redo;
+        uint64_t found = 0;
+        for (int pass = 0; pass < 2; pass++) {
+            const int64_t nrun = pass == 0 ? nq : (int64_t)redo.size();
+            if (nrun == 0) break;
+            // pass 1 (overflowed queries only): a queue that can hold every node, as many warps as ~2 GB of queues allow
+            const int64_t qcap = pass == 0 ? std::min<int64_t>(n, 16384) : n;
+            int grid = L.grid;
+            if (pass == 1) {
+                const int64_t max_warps = std::max<int64_t>(kHnswWarps, (int64_t)(2ll << 30) / (qcap * 4));
+                grid = (int)std::min<int64_t>(std::min<int64_t>(L.grid, (nrun + kHnswWarps - 1) / kHnswWarps), max_warps / kHnswWarps);
+            }
+            d_queue.ensure((size_t)grid * kHnswWarps * qcap);
+            DevBuf<int32_t> d_redo;
+            if (pass == 1) {
+                d_redo.ensure(redo.size());
+                KB2_CUDA_CHECK(cudaMemcpyAsync(d_redo.p, redo.data(), redo.size() * 4, cudaMemcpyHostToDevice, st));
+            }
+            const uint64_t found_before = found;
+            for (int attempt = 0; attempt < 2; attempt++) {
+                hits.ensure(cap);   // NOTE: grow-only without preserving contents: pass 1 appends after a copy (below)
+                KB2_CUDA_CHECK(cudaMemsetAsync(cnt.p, 0, 8, st));
+                if (pass == 0) KB2_CUDA_CHECK(cudaMemsetAsync(d_qover.p, 0, (size_t)nq * 4, st));
+                KB2_CUDA_CHECK(cudaMemsetAsync(d_next.p, 0, 4, st));
+                KB2_CUDA_CHECK(cudaMemsetAsync(d_counter.p, 0, 16, st));
+                HnswSearchParams p = base_params(dq, nrun, ef, 1, L);
+                p.bitset = dbits;
+                p.k_alpha = (float)((double)n_filtered / (double)n) * 0.7f;
+                p.range_mode = 1;
+                p.radius_key = (metric == KB2_METRIC_L2) ? radius : -radius;
+                p.hits = hits.p + found_before;
+                p.hit_count = cnt.p;
+                p.hit_cap = cap - found_before;
+                p.bfs_queue = d_queue.p;
+                p.queue_cap = (int)qcap;
+                p.q_overflow = d_qover.p;
+                p.q_list = pass == 1 ? d_redo.p : nullptr;
+                if (metric == KB2_METRIC_L2)
+                    hnsw_filtered_kernel<KB2_METRIC_L2><<<grid, kHnswWarps * 32, L.smem, st>>>(p);
+                else
+                    hnsw_filtered_kernel<KB2_METRIC_IP><<<grid, kHnswWarps * 32, L.smem, st>>>(p);
+                last.launches++;
+                KB2_CUDA_CHECK(cudaGetLastError());
+                unsigned long long got = 0;
+                KB2_CUDA_CHECK(cudaMemcpyAsync(&got, cnt.p, 8, cudaMemcpyDeviceToHost, st));
+                KB2_CUDA_CHECK(cudaStreamSynchronize(st));
+                if (found_before + got <= cap) { found = found_before + got; break; }
+                // the hit buffer was too small: grow it (keeping the hits of the previous pass) and run the pass again
+                KB2_REQUIRE(attempt == 0, KB2_INTERNAL_ERROR, "range search: hit buffer overflow after resizing");
+                DevBuf<RangeHit> bigger;
+                cap = found_before + got;
+                bigger.ensure(cap);
+                if (found_before)
+                    KB2_CUDA_CHECK(cudaMemcpyAsync(bigger.p, hits.p, found_before * sizeof(RangeHit), cudaMemcpyDeviceToDevice, st));
+                KB2_CUDA_CHECK(cudaStreamSynchronize(st));
+                hits = std::move(bigger);
+            }
+            if (pass == 0) {
+                range_pass0_hits = found;
+                KB2_CUDA_CHECK(cudaMemcpy(h_over.data(), d_qover.p, (size_t)nq * 4, cudaMemcpyDeviceToHost));
+                for (int64_t i = 0; i < nq; i++)
+                    if (h_over[i]) redo.push_back((int32_t)i);
+            }
+        }
+        // the caller drops the pass-0 hits (index < range_pass0_hits) of overflowed queries: pass 1 holds their full set
+        range_overflowed.assign(h_over.begin(), h_over.end());
+        return found;
+    }
+    std::vector<uint32_t> range_overflowed;   // per query: 1 = its pass-0 hits are incomplete (pass 1 holds the full set)
+    uint64_t range_pass0_hits = 0;
 
     void
     get_vectors(const int64_t* ids, int64_t cnt, float* out) override {

@@ -14,13 +14,6 @@
 
 namespace kb2 {
 
-struct RangeHit {
-    int32_t q;
-    int32_t probe;
-    uint32_t pos;
-    float dist;
-};
-
 struct RangeParams {
     IvfScanParams sp;
     int kind;            // 0 vectors [pos][d], 1 PQ rotated groups, 2 PQ plain bytes
@@ -36,6 +29,12 @@ struct RangeParams {
 
 __device__ __forceinline__ bool
 in_range(float dist, float radius, float range_filter, int has_filter, int metric) {
+    if (metric == KB2_METRIC_L2) return dist < radius && (!has_filter || dist >= range_filter);
+    return dist > radius && (!has_filter || dist <= range_filter);
+}
+
+static inline bool
+in_range_host(float dist, float radius, float range_filter, bool has_filter, int metric) {
     if (metric == KB2_METRIC_L2) return dist < radius && (!has_filter || dist >= range_filter);
     return dist > radius && (!has_filter || dist <= range_filter);
 }
@@ -159,7 +158,8 @@ range_search_index(IndexBase& ix, const float* queries, int64_t nq, float radius
     cudaStream_t st = ix.stream;
     FlatIndex* fi = dynamic_cast<FlatIndex*>(&ix);
     IvfIndex* iv = dynamic_cast<IvfIndex*>(&ix);
-    KB2_REQUIRE(fi || iv, KB2_NOT_IMPLEMENTED, "RangeSearch is implemented for FLAT / IVF_FLAT / IVF_PQ");
+    HnswIndex* hn = dynamic_cast<HnswIndex*>(&ix);
+    KB2_REQUIRE(fi || iv || hn, KB2_NOT_IMPLEMENTED, "RangeSearch: unknown index class");
     KB2_REQUIRE(ix.count() > 0, KB2_EMPTY_INDEX, "index is empty");
     if (nq == 0) {
         *out_lims = (int64_t*)calloc(1, sizeof(int64_t));
@@ -183,15 +183,24 @@ range_search_index(IndexBase& ix, const float* queries, int64_t nq, float radius
     int nprobe = 1;
     int max_empty = 0;
     size_t smem = (size_t)ix.dim * 4 + 64;
-    if (fi) {
+    DevBuf<RangeHit> hits;
+    unsigned long long found = 0;
+    bool graph_hits = false;   // hits came from the HNSW traversal (range_filter still to be applied)
+    if (hn) {
+        bool bf = false;
+        found = hn->range_hits(dq, nq, radius, cfg, dbits, hits, bf);
+        graph_hits = !bf;
+    }
+    if (fi || (hn && !graph_hits)) {
+        // exact scan of the stored vectors (FLAT; HNSW when the reference falls back to brute force)
         rp.kind = 0;
-        sp.vecs = fi->base.p;
+        sp.vecs = fi ? fi->base.p : hn->d_vecs.p;
         sp.rows = nullptr;
-        rp.single_len = fi->count();
+        rp.single_len = ix.count();
         sp.nsplit = (int)std::min<int64_t>(std::max<int64_t>(1, (2 * kNumSMs + nq - 1) / nq),
-                                           std::max<int64_t>(1, fi->count() / 1024));
+                                           std::max<int64_t>(1, ix.count() / 1024));
         smem += 64;
-    } else {
+    } else if (iv) {
         KB2_REQUIRE(iv->trained, KB2_INDEX_NOT_TRAINED, "index not trained");
         iv->seal();
         nprobe = (int)std::min<int64_t>(std::max<int64_t>(cfg.get_int("nprobe", 8), 1), iv->nlist);
@@ -238,12 +247,10 @@ range_search_index(IndexBase& ix, const float* queries, int64_t nq, float radius
         if (iv->is_pq) smem += (size_t)iv->M * 1024;
         KB2_REQUIRE(smem <= (size_t)kMaxDynSmem, KB2_NOT_IMPLEMENTED, "range search: m too large");
     }
-    DevBuf<RangeHit> hits;
     DevBuf<unsigned long long> cnt;
     cnt.ensure(1);
     unsigned long long cap = (unsigned long long)std::max<int64_t>(1 << 20, nq * 256);
-    unsigned long long found = 0;
-    for (int attempt = 0; attempt < 2; attempt++) {
+    for (int attempt = 0; attempt < 2 && !graph_hits; attempt++) {
         hits.ensure(cap);
         KB2_CUDA_CHECK(cudaMemsetAsync(cnt.p, 0, 8, st));
         rp.hits = hits.p;
@@ -263,7 +270,7 @@ range_search_index(IndexBase& ix, const float* queries, int64_t nq, float radius
     // labels
     std::vector<int32_t> hrows;
     std::vector<int64_t> hlabels;
-    const bool custom = fi ? fi->custom_labels : iv->custom_labels;
+    const bool custom = fi ? fi->custom_labels : (iv ? iv->custom_labels : hn->custom_labels);
     if (iv) {
         hrows.resize(iv->npad);
         KB2_CUDA_CHECK(cudaMemcpy(hrows.data(), iv->rows.p, iv->npad * 4, cudaMemcpyDeviceToHost));
@@ -271,14 +278,22 @@ range_search_index(IndexBase& ix, const float* queries, int64_t nq, float radius
     if (custom) {
         const int64_t n = ix.count();
         hlabels.resize(n);
-        KB2_CUDA_CHECK(cudaMemcpy(hlabels.data(), fi ? fi->labels.p : iv->labels.p, n * 8, cudaMemcpyDeviceToHost));
+        if (hn) hlabels = hn->h_labels;
+        else KB2_CUDA_CHECK(cudaMemcpy(hlabels.data(), fi ? fi->labels.p : iv->labels.p, n * 8, cudaMemcpyDeviceToHost));
     }
     struct Out { int64_t q; int probe; float dist; int64_t label; };
-    std::vector<Out> o(found);
+    std::vector<Out> o;
+    o.reserve(found);
     for (size_t i = 0; i < found; i++) {
+        if (graph_hits) {
+            // pass-0 hits of a query whose BFS queue overflowed are incomplete: the rerun (later entries) has them all
+            if (i < hn->range_pass0_hits && hn->range_overflowed[h[i].q]) continue;
+            if (!in_range_host(h[i].dist, radius, range_filter, has_filter, ix.metric)) continue;
+        }
         int64_t row = iv ? (int64_t)hrows[h[i].pos] : (int64_t)h[i].pos;
-        o[i] = Out{h[i].q, h[i].probe, h[i].dist, custom ? hlabels[row] : row};
+        o.push_back(Out{h[i].q, h[i].probe, h[i].dist, custom ? hlabels[row] : row});
     }
+    found = o.size();
     const bool is_ip = ix.metric == KB2_METRIC_IP;
     std::sort(o.begin(), o.end(), [&](const Out& a, const Out& b) {
         if (a.q != b.q) return a.q < b.q;

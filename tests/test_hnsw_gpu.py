@@ -37,6 +37,101 @@ def test_hnsw_imported_graph_parity(kb, ref, metric, n, d, M, ef, k):
     assert abs(ndis - ndis0) <= 0.02 * ndis0 and abs(nhops - nhops0) <= 0.02 * nhops0
 
 
+def _ref_graph(kb, ref, n, d, M, metric, seed=42):
+    xb = datagen.clustered(n, d, seed)
+    h = ref.RefHnsw(d, M, metric, 100)
+    h.add(xb)
+    g = h.export()
+    ix = kb.Index("HNSW", "L2" if metric == 0 else "IP", d, {"M": M, "efConstruction": 100})
+    ix.hnsw_import(xb, g["levels"], g["offsets"], g["neighbors"], g["cum"], g["entry_point"], g["max_level"])
+    return xb, h, ix
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+@pytest.mark.parametrize("frac", [0.1, 0.5, 0.9])
+def test_hnsw_bitset_filter_parity(kb, ref, metric, frac):
+    """Filtered search: two-pool traversal with the kAlpha budget (HnswSearcher.h:213-225, Neighbor.h:155-210) on the
+    reference's own graph; ids must match the reference searcher's, and no filtered id may be returned."""
+    n, d, M, ef, k = 20000, 64, 16, 64, 10
+    xb, h, ix = _ref_graph(kb, ref, n, d, M, metric)
+    xq = datagen.clustered(200, d, 43)
+    rng = np.random.default_rng(7)
+    mask = rng.random(n) < frac
+    bits = np.packbits(mask, bitorder="little")
+    I0, D0, (ndis0, nhops0) = h.search_filtered(xq, k, ef, bits, n)
+    ids, dist = ix.search(xq, k, {"ef": ef, "disable_fallback_brute_force": True}, bitset=bits)
+    assert not mask[ids[ids >= 0]].any()
+    same_rows = (ids == I0).all(axis=1).mean()
+    print(f"filtered metric={metric} frac={frac}: identical rows {same_rows:.3f}")
+    assert same_rows > 0.9
+    eq = ids == I0
+    np.testing.assert_allclose(dist[eq], D0[eq], rtol=1e-4, atol=1e-4)
+    ndis, nhops = ix.hnsw_last_stats()
+    assert abs(ndis - ndis0) <= 0.03 * ndis0 and abs(nhops - nhops0) <= 0.03 * nhops0
+    # recall against the exact filtered ground truth is not below the reference's
+    gt, _ = ref.flat_search(xb[~mask], xq, k, metric)
+    gt = np.nonzero(~mask)[0][gt]
+    assert recall_at_k(gt, ids) >= recall_at_k(gt, I0) - 0.005
+
+
+def test_hnsw_bitset_brute_force_paths(kb, ref):
+    """>= 93 % filtered => the reference runs brute force (IndexConditionalWrapper.cc:35-62): results are exact;
+    a traversal that returns fewer than k ids falls back to brute force per query (faiss_hnsw.cc:1464-1478)."""
+    n, d, M, k = 5000, 32, 8, 10
+    xb, h, ix = _ref_graph(kb, ref, n, d, M, 0)
+    xq = datagen.clustered(50, d, 43)
+    mask = np.ones(n, bool)
+    mask[::20] = False                      # 95 % filtered out
+    bits = np.packbits(mask, bitorder="little")
+    ids, dist = ix.search(xq, k, {"ef": 32}, bitset=bits)
+    gt, gd = ref.flat_search(xb[~mask], xq, k, 0)
+    gt = np.nonzero(~mask)[0][gt]
+    assert np.array_equal(ids, gt)
+    np.testing.assert_allclose(dist, gd, rtol=1e-5, atol=1e-5)
+    # 92 % filtered: graph traversal; any short row is completed by the exact fallback
+    mask2 = np.ones(n, bool)
+    mask2[::12] = False
+    bits2 = np.packbits(mask2, bitorder="little")
+    ids2, _ = ix.search(xq, k, {"ef": 16}, bitset=bits2)
+    assert (ids2 >= 0).all() and not mask2[ids2].any()
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+@pytest.mark.parametrize("with_bitset", [False, True])
+def test_hnsw_range_search_parity(kb, ref, metric, with_bitset):
+    """RangeSearch (HnswSearcher.h:435-553): ef-bounded beam, then the closure of the in-range candidates over level-0
+    links.  Same graph => the hit sets must be the reference's (up to radius-boundary fp32 flips)."""
+    n, d, M, ef = 8000, 32, 16, 32
+    xb, h, ix = _ref_graph(kb, ref, n, d, M, metric)
+    xq = datagen.clustered(60, d, 43)
+    gt, gd = ref.flat_search(xb, xq, 40, metric)
+    radius = float(np.median(gd[:, 25]))
+    bits = None
+    if with_bitset:
+        mask = np.random.default_rng(3).random(n) < 0.3
+        bits = np.packbits(mask, bitorder="little")
+    lims0, ids0, dis0 = h.range_search(xq, radius, ef, bits, n)
+    lims, ids, dis = ix.range_search(xq, radius, config={"ef": ef}, bitset=bits)
+    tot0 = tot1 = inter = 0
+    for i in range(len(xq)):
+        a = set(ids0[lims0[i]:lims0[i + 1]].tolist())
+        b = set(ids[lims[i]:lims[i + 1]].tolist())
+        tot0 += len(a); tot1 += len(b); inter += len(a & b)
+        seg = dis[lims[i]:lims[i + 1]]
+        assert (np.diff(seg) >= 0).all() if metric == 0 else (np.diff(seg) <= 0).all()
+        if with_bitset:
+            assert not mask[list(b)].any()
+    print(f"range metric={metric} bitset={with_bitset}: ref hits {tot0} gpu hits {tot1} common {inter}")
+    assert tot0 > 0 and inter >= 0.98 * max(tot0, tot1)
+    # range_filter keeps radius-side open, filter-side closed (range_util.h:23-26)
+    rf = float(np.median(gd[:, 5]))
+    l2, i2, d2 = ix.range_search(xq, radius, range_filter=rf, config={"ef": ef}, bitset=bits)
+    if metric == 0:
+        assert (d2 >= rf).all() and (d2 < radius).all()
+    else:
+        assert (d2 <= rf).all() and (d2 > radius).all()
+
+
 def test_hnsw_own_build_recall(kb, ref):
     n, d, M, k = 20000, 64, 16, 10
     xb = datagen.clustered(n, d, 1)

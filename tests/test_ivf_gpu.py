@@ -247,3 +247,70 @@ def test_ivf_list_sharding_single_gpu(kb, world):
     assert_topk_parity(mi, md, I0, D0, rtol=1e-6, atol=1e-6, what="sharded ADC merge", max_tie_rows=nq // 10)
     mi, md = kb.merge_topk(np.stack(ref_ids), np.stack(ref_dis), "L2")
     assert (md <= D1 * (1 + 1e-6)).all()
+
+
+@pytest.mark.parametrize("kind,m", [("IVF_FLAT", 0), ("IVF_PQ", 16)])
+def test_ivf_bitset_after_import_and_deserialize(kb, ref, kind, m):
+    """A BitsetView addresses vectors by id (bitsetview.h:131-175).  After import / Deserialize the rows used to be
+    numbered in list order, so the filter hit the wrong vectors; now rows are renumbered by label.  Checked against the
+    reference's own filtered search (ids identical) and through GetVectorByIds."""
+    nb, d, nlist, nq, k = 12000, 64, 32, 50, 10
+    xb = datagen.clustered(nb, d, 21)
+    xq = datagen.clustered(nq, d, 22)
+    r = _mk_ref(ref, kind, xb, 0, nlist, m, refine=False)
+    ix = _import(kb, r, kind, 0, xb)
+    mask = np.random.default_rng(5).random(nb) < 0.4
+    bits = np.packbits(mask, bitorder="little")
+    a_ids, a_dis = ix.search(xq, k, {"nprobe": nlist}, bitset=bits)
+    assert not mask[a_ids[a_ids >= 0]].any()
+    # exact expectation for IVF_FLAT with every list probed: brute force over the kept rows
+    if kind == "IVF_FLAT":
+        gt, gd = ref.flat_search(xb[~mask], xq, k, 0)
+        gt = np.nonzero(~mask)[0][gt]
+        assert_topk_parity(a_ids, a_dis, gt, gd, what="IVF_FLAT bitset after import")
+        v = ix.get_vector_by_ids(np.array([0, 17, nb - 1]))
+        assert np.array_equal(v, xb[[0, 17, nb - 1]])
+    ix2 = kb.Index.deserialize(ix.serialize())
+    b_ids, b_dis = ix2.search(xq, k, {"nprobe": nlist}, bitset=bits)
+    assert np.array_equal(a_ids, b_ids) and np.allclose(a_dis, b_dis)
+    # an index built here, serialised and loaded: same filtered answer as before the round trip
+    ix3 = kb.Index(kind, "L2", d, dict({"nlist": nlist}, **({"m": m} if m else {})))
+    ix3.build(xb)
+    c_ids, _ = ix3.search(xq, k, {"nprobe": 8}, bitset=bits)
+    ix4 = kb.Index.deserialize(ix3.serialize())
+    d_ids, _ = ix4.search(xq, k, {"nprobe": 8}, bitset=bits)
+    assert np.array_equal(c_ids, d_ids) and not mask[d_ids[d_ids >= 0]].any()
+    with pytest.raises(kb.KnowhereError) as e:
+        ix.search(xq, k, {"nprobe": 4}, bitset=bits[: nb // 16])      # too short a bitmap
+    assert e.value.status == 1
+
+
+def test_ivfpq_add_after_search(kb):
+    """Add() after the first Search() (the sealed list layout is unpacked and rebuilt): same result as one big add."""
+    nb, d, nlist, m = 20000, 64, 32, 16
+    xb = datagen.clustered(nb, d, 31)
+    xq = datagen.clustered(40, d, 32)
+    one = kb.Index("IVF_PQ", "L2", d, {"nlist": nlist, "m": m})
+    one.train(xb)
+    cent, pq = one.ivf_export_centroids(m)
+    one.add(xb)
+    two = kb.Index("IVF_PQ", "L2", d, {"nlist": nlist, "m": m})
+    kb._check(kb.lib().kb2_ivf_import_begin(two.h, nlist, cent.ctypes.data, pq.ctypes.data))
+    two.add(xb[:12000].copy())
+    two.search(xq, 10, {"nprobe": 8})
+    two.add(xb[12000:].copy())
+    a = one.search(xq, 10, {"nprobe": 8})
+    b = two.search(xq, 10, {"nprobe": 8})
+    assert two.count() == nb and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_ivf_build_is_deterministic(kb):
+    """two GPU builds of the same data give bit-identical quantizers (no float atomics in k-means)"""
+    nb, d, nlist, m = 30000, 64, 64, 16
+    xb = datagen.clustered(nb, d, 9)
+    outs = []
+    for _ in range(2):
+        ix = kb.Index("IVF_PQ", "L2", d, {"nlist": nlist, "m": m})
+        ix.train(xb)
+        outs.append(ix.ivf_export_centroids(m))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
