@@ -133,23 +133,34 @@ def recall_of(gt, ids):
     return hit / float(gt.shape[0] * gt.shape[1])
 
 
-def build_index(kb, torch, dist, wl, xb, rank, world, stream):
+def make_comm(kb, dist, rank, world, device_index):
+    """library-owned NCCL communicator; torch.distributed only ships rank 0's 128-byte id"""
+    def bcast(b):
+        box = [b]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+    return kb.Comm(rank, world, device_index, bcast)
+
+
+def build_index(kb, torch, dist, wl, xb, rank, world, stream, comm=None, build_cfg=None):
     """GPU build; for world>1 rank 0 trains and broadcasts centroids/codebooks so that every rank
     encodes against the same quantizers, then each rank keeps the lists l % world == rank."""
     d = wl["d"]
     dev_i = xb.device.index or 0
-    ix = kb.Index(wl["index"], wl["metric"], d, wl["build"], device=dev_i)
+    cfgb = build_cfg or wl["build"]
+    ix = kb.Index(wl["index"], wl["metric"], d, cfgb, device=dev_i)
     ix.set_stream(stream)
-    m = wl["build"].get("m", 0)
+    m = cfgb.get("m", 0)
     if world == 1:
         ix.train(xb)
+        return_q = None
     else:
         ix.set_shard(rank, world)
-        nlist = wl["build"]["nlist"]
+        nlist = cfgb["nlist"]
         cent = torch.empty((nlist, d), dtype=torch.float32, device=xb.device)
         pq = torch.empty((max(m, 1), 256, d // max(m, 1)), dtype=torch.float32, device=xb.device)
         if rank == 0:
-            t = kb.Index(wl["index"], wl["metric"], d, wl["build"], device=dev_i)
+            t = kb.Index(wl["index"], wl["metric"], d, cfgb, device=dev_i)
             t.set_stream(stream)
             t.train(xb)
             c_h, pq_h = t.ivf_export_centroids(m)
@@ -161,8 +172,51 @@ def build_index(kb, torch, dist, wl, xb, rank, world, stream):
         dist.broadcast(pq, 0)
         torch.cuda.synchronize()
         kb._check(kb.lib().kb2_ivf_import_begin(ix.h, nlist, cent.data_ptr(), pq.data_ptr() if m else None))
+        return_q = (cent, pq)
     ix.add(xb)
+    if comm is not None:
+        ix.set_comm(comm)
+    ix._quantizers = return_q
     return ix
+
+
+def multi_gpu_parity(kb, torch, wl, xb, xq, k, rank, world, stream, comm, quantizers):
+    """merged == unsharded, proven inside the run: a sharded and (rank 0) an unsharded PURE-ADC index (no refine, same
+    quantizers) answer the whole batch; the merged collective result must equal the unsharded one id for id (refine
+    would only ADD candidates on the sharded side, so pure ADC is the exact comparison)."""
+    d, m = wl["d"], wl["build"].get("m", 0)
+    nlist = wl["build"]["nlist"]
+    cfgb = {kk: v for kk, v in wl["build"].items() if kk not in ("refine", "refine_type")}
+    cent, pq = quantizers
+    dev_i = xb.device.index or 0
+    sh = kb.Index(wl["index"], wl["metric"], d, cfgb, device=dev_i)
+    sh.set_stream(stream)
+    sh.set_shard(rank, world)
+    kb._check(kb.lib().kb2_ivf_import_begin(sh.h, nlist, cent.data_ptr(), pq.data_ptr() if m else None))
+    sh.add(xb)
+    sh.set_comm(comm)
+    cfg = dict(wl["search"])
+    mi, md = sh.search(xq, k, cfg)           # collective
+    torch.cuda.synchronize()
+    del sh
+    out = None
+    if rank == 0:
+        full = kb.Index(wl["index"], wl["metric"], d, cfgb, device=dev_i)
+        full.set_stream(stream)
+        kb._check(kb.lib().kb2_ivf_import_begin(full.h, nlist, cent.data_ptr(), pq.data_ptr() if m else None))
+        full.add(xb)
+        fi, fd = full.search(xq, k, cfg)
+        torch.cuda.synchronize()
+        a, b = mi.cpu().numpy(), fi.cpu().numpy()
+        da, db = md.cpu().numpy(), fd.cpu().numpy()
+        rows = (a == b).all(axis=1)
+        sets = np.array([set(x.tolist()) == set(y.tolist()) for x, y in zip(a, b)])
+        out = {"queries": int(a.shape[0]), "rows_identical": int(rows.sum()), "id_sets_identical": int(sets.sum()),
+               "distances_bit_identical_rows": int((da.view(np.uint32) == db.view(np.uint32)).all(axis=1).sum()),
+               "what": "sharded pure-ADC search (collective, merged inside the library) vs unsharded pure-ADC search, "
+                       "same quantizers, whole batch"}
+        del full
+    return out
 
 
 def run_ours(args):
@@ -170,7 +224,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     import knowhere_b200 as kb
-    from knowhere_b200 import datagen, sharding
+    from knowhere_b200 import datagen
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -189,30 +243,20 @@ def run_ours(args):
     xq = datagen.clustered_torch(nq, d, 43, dev)
     torch.cuda.synchronize()
     t_gen = time.time() - t0
+    comm = make_comm(kb, dist, rank, world, local_rank) if world > 1 else None
     t0 = time.time()
-    ix = build_index(kb, torch, dist, wl, xb, rank, world, stream)
+    ix = build_index(kb, torch, dist, wl, xb, rank, world, stream, comm=comm)
     torch.cuda.synchronize()
     t_build = time.time() - t0
 
-    # ---- search closure (device-resident I/O)
+    # ---- search closure (device-resident I/O).  world > 1: the SAME call is a collective inside the library (probe
+    #      all-gather, bound all-reduce, ONE all-gather of the per-shard top-k + merge kernel) and returns the merged result.
     ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
     dis = torch.empty((nq, k), dtype=torch.float32, device=dev)
-    if world > 1:
-        m_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
-        m_dis = torch.empty((nq, k), dtype=torch.float32, device=dev)
-
-    def merge_fn(g_ids, g_dis):
-        # the kernel that consumes the all-gather: per-query merge of the world x k candidates
-        kb._check(kb.lib().kb2_merge_topk(0 if wl["metric"] == "L2" else 1, world, nq, k, g_ids.data_ptr(),
-                                          g_dis.data_ptr(), m_ids.data_ptr(), m_dis.data_ptr(), local_rank, stream))
-        return m_ids, m_dis
 
     def search_dev(cfg, q=None):
         ix.search(xq if q is None else q, k, cfg, out=(ids, dis))
-        if world == 1:
-            return ids, dis
-        # ONE all-gather of the packed per-shard (id, distance) candidates, then the merge kernel
-        return sharding.gather_and_merge(torch, dist, ids, dis, merge_fn, world)
+        return ids, dis
 
     # ---- recall calibration: smallest refine_k reaching the target (benchmark_float_qps.cpp:80-108 method)
     cfg = dict(wl["search"])
@@ -252,7 +296,7 @@ def run_ours(args):
         kernel_ms.append(ix.last_kernel_ms())
         stage_info = ix.last_stage_info()
         stage_ms.append(stage_info["stage_ms"])
-        launches += ix.last_counters()["launches"] + (5 if world > 1 else 0)
+        launches += ix.last_counters()["launches"]
     e1.record()
     barrier()
     if os.environ.get("KB2_PROFILE"):
@@ -266,20 +310,26 @@ def run_ours(args):
     ctr = ix.last_counters()
     ix.enable_kernel_timing(False)
     breakdown = None
+    parity = None
     if world > 1:
-        # where the N>1 step goes: local search vs all-gather + merge (device events, this rank)
-        ea, eb, ec = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        ts, tm = [], []
+        # where the N>1 step goes (device events inside the library, this rank): list-scan stage, collectives + merge
+        ix.enable_kernel_timing(True)
+        ts, tm, tk = [], [], []
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for _ in range(5):
             ea.record()
-            ix.search(xq, k, cfg, out=(ids, dis))
+            search_dev(cfg)
             eb.record()
-            sharding.gather_and_merge(torch, dist, ids, dis, merge_fn, world)
-            ec.record()
             torch.cuda.synchronize()
+            info = ix.last_stage_info()
             ts.append(ea.elapsed_time(eb))
-            tm.append(eb.elapsed_time(ec))
-        breakdown = {"local_search_ms": statistics.median(ts), "allgather_merge_ms": statistics.median(tm)}
+            tm.append(info["comm_ms"])
+            tk.append(info["stage_ms"])
+        ix.enable_kernel_timing(False)
+        breakdown = {"step_ms": statistics.median(ts), "collectives_and_merge_ms": statistics.median(tm),
+                     "list_scan_stage_ms": statistics.median(tk),
+                     "collectives": "all-gather(probes) + min-all-reduce(bounds) + all-gather(top-k) + merge, NCCL inside the library"}
+        parity = multi_gpu_parity(kb, torch, wl, xb, xq, k, rank, world, stream, comm, ix._quantizers)
 
     # ---- end to end: pinned host queries in, host results out, through the same public call
     xq_h = torch.empty((nq, d), dtype=torch.float32).pin_memory()
@@ -289,14 +339,8 @@ def run_ours(args):
     xq_np, ids_np, dis_np = xq_h.numpy(), ids_h.numpy(), dis_h.numpy()
 
     def search_e2e():
-        if world == 1:
-            ix.search(xq_np, k, cfg, out=(ids_np, dis_np))
-        else:
-            xq.copy_(xq_h, non_blocking=True)
-            mi, md = search_dev(cfg)
-            ids_h.copy_(mi, non_blocking=True)
-            dis_h.copy_(md, non_blocking=True)
-            torch.cuda.synchronize()
+        # host buffers straight through the public call on every rank (H2D, collectives, D2H inside the library)
+        ix.search(xq_np, k, cfg, out=(ids_np, dis_np))
 
     for _ in range(max(1, args.warmup)):
         search_e2e()
@@ -310,7 +354,7 @@ def run_ours(args):
         t = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_ok = bool(np.array_equal(ids_np, (ids if world == 1 else m_ids).cpu().numpy()))
+    e2e_ok = bool(np.array_equal(ids_np, ids.cpu().numpy()))
 
     if rank != 0:
         if world > 1:
@@ -373,12 +417,15 @@ def run_ours(args):
                    "recall_at_10": recall, "recall_queries": n_gt, "refine_k": cfg.get("refine_k"),
                    "data": "clustered low-rank gaussian mixture, seeds base 42 / query 43 (SURVEY 8d)",
                    "l2_policy": "inputs larger than L2 (codes 200 MB + refine vectors 5 GB per pass)",
-                   "sharding": "replica-free list sharding, l % N" if world > 1 else "single GPU",
+                   "sharding": ("inverted lists sharded l % N, collectives inside libknowhere_b200.so (kb2_comm_*): probe "
+                                "all-gather, bound all-reduce, one all-gather of per-shard top-k + merge kernel")
+                   if world > 1 else "single GPU",
                    "build_s": round(t_build, 2), "datagen_s": round(t_gen, 2)},
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": nq * d * 4,
                 "d2h_bytes_per_step": nq * k * 12, "results_equal_device_path": e2e_ok},
         "gpu_launches": launches,
         "multi_gpu_breakdown": breakdown,
+        "multi_gpu_parity": parity,
         "clocks": clocks,
         "roofline": roofline,
     }

@@ -57,6 +57,7 @@ enum {
 enum { KB2_METRIC_L2 = 0, KB2_METRIC_IP = 1, KB2_METRIC_COSINE = 2 };
 
 typedef struct kb2_index* kb2_index_t;
+typedef struct kb2_comm* kb2_comm_t;
 
 /* ---- library ------------------------------------------------------------------------- */
 const char* kb2_version(void);
@@ -157,6 +158,23 @@ int kb2_hnsw_last_stats(kb2_index_t h, int64_t* out2);
 int kb2_index_serialize(kb2_index_t h, uint8_t** out, size_t* out_size);
 int kb2_index_deserialize(const uint8_t* blob, size_t size, int device, kb2_index_t* out);
 
+/* ---- the reference's wire format: faiss fourcc streams, i.e. the payload Knowhere stores in a BinarySet under the
+ * index type name (flat.cc:323-343, ivf.cc:1717-1741, faiss_hnsw.cc:188-217; K/impl/index_write.cpp:523-560,716-745,
+ * 776-822, K/impl/index_read.cpp).  Supported: "IxF2"/"IxFI"/"IxF9" (FLAT), "IwFl" (IVF_FLAT), "IwPQ" and "IxRF" over it
+ * (IVF_PQ, + flat fp32 refine store), "IHNf"/"IHN9" (HNSW over flat storage).  with_norm = 1 when the inverted lists
+ * carry per-row norms (the reference's IO_FLAG_WITH_NORM).  A CPU-built Knowhere index loads straight onto the GPU and
+ * a GPU-built index can be served by the reference's CPU nodes.  kb2_faiss_describe parses on the host only (no device
+ * needed) and returns a one-line JSON description. */
+int kb2_faiss_describe(const uint8_t* blob, size_t size, int with_norm, char* json_out, size_t cap);
+/* host-only: parse the stream and write it again with this library's writer (out: malloc'ed, kb2_free) */
+int kb2_faiss_rewrite(const uint8_t* blob, size_t size, int with_norm, uint8_t** out, size_t* out_size);
+int kb2_index_deserialize_faiss(const uint8_t* blob, size_t size, int with_norm, int device, kb2_index_t* out);
+int kb2_index_serialize_faiss(kb2_index_t h, uint8_t** out, size_t* out_size);
+/* IndexNode::DeserializeFromFile / GetIndexMeta (include/knowhere/index/index_node.h:329-395): the file may hold a
+ * faiss stream or this library's "KB2I" container; the meta is a JSON object (type, dim, rows, metric_type, ...) */
+int kb2_index_deserialize_from_file(const char* path, int device, kb2_index_t* out);
+int kb2_index_get_meta(kb2_index_t h, char* json_out, size_t cap);
+
 /* ---- index-less exact search: knowhere::BruteForce (include/knowhere/comp/brute_force.h:26-69;
  * src/common/comp/brute_force.cc:260-392,588-710) */
 int kb2_bruteforce_search(const float* base, int64_t nb, int dim, int metric, const float* queries,
@@ -166,6 +184,24 @@ int kb2_bruteforce_range_search(const float* base, int64_t nb, int dim, int metr
                                 int64_t nq, float radius, float range_filter, int has_range_filter,
                                 const uint8_t* bitset, int64_t bitset_nbits, int64_t** out_lims,
                                 int64_t** out_ids, float** out_dist, int device, void* cuda_stream);
+
+/* ---- multi-GPU: one process per GPU, inverted lists sharded (kb2_index_set_shard), collectives over NCCL/NVLink
+ * INSIDE the library (the reference has no multi-GPU path: one index per device,
+ * src/common/cuvs/integration/cuvs_knowhere_index.cuh:415-460).  Bootstrap as in NCCL: rank 0 obtains a 128-byte id,
+ * the host application distributes it (its own RPC; torch.distributed in the tests), every rank creates its
+ * communicator on its device.  After kb2_index_set_comm, kb2_index_search on a sharded IVF index is a COLLECTIVE call:
+ * every rank passes the same query batch and receives the same global top-k.  Per call: the coarse quantizer runs on
+ * 1/world of the batch per rank + one all-gather of the probe lists; (tensor-core IVF_PQ engine) phase-A bounds are
+ * computed by the rank owning each query's nearest list + one min all-reduce; every rank scans its own lists; ONE
+ * all-gather of the per-shard top-k candidates + the merge kernel.  NCCL is resolved with dlopen("libnccl.so.2"). */
+int kb2_comm_unique_id(uint8_t* out128);
+int kb2_comm_create(const uint8_t* id128, int rank, int world, int device, kb2_comm_t* out);
+void kb2_comm_destroy(kb2_comm_t c);
+/* every rank contributes `bytes` device bytes; recv holds world*bytes, rank-major (exposed for tests / host glue) */
+int kb2_comm_all_gather(kb2_comm_t c, const void* send, void* recv, size_t bytes, void* cuda_stream);
+/* attach (or detach with NULL) a communicator; rank/world/device must equal the handle's shard settings.  The
+ * communicator is not owned by the index and must outlive it. */
+int kb2_index_set_comm(kb2_index_t h, kb2_comm_t c);
 
 /* ---- multi-GPU candidate merge (the kernel that consumes the NCCL all-gather) ---
  * in_ids/in_dist: [world][nq][k] gathered per-shard results (device or host);
@@ -185,7 +221,8 @@ int kb2_index_enable_kernel_timing(kb2_index_t h, int on);
 int kb2_index_last_kernel_ms(kb2_index_t h, float* out_ms);
 /* out4: [0] device ms of the whole list-scan stage of the last search, [1] device ms of its dominant kernel
  * (== kb2_index_last_kernel_ms), [2] engine that served it: 0 = query-major scan kernels, 1 = list-major
- * tensor-core engine (IVF_PQ m=16 d=128 with large batches; kb2_ivfpq_tc.cuh), [3] reserved */
+ * tensor-core engine (IVF_PQ m=16 d=128 with large batches; kb2_ivfpq_tc.cuh), [3] device ms of the collectives
+ * (+ merge kernel) of a sharded search with a communicator */
 int kb2_index_last_stage_info(kb2_index_t h, float* out4);
 
 /* validation hook: writes the full key matrix [nq][round_up(nb,4)] of the dense contraction

@@ -82,6 +82,20 @@ def _declare(L):
     L.kb2_bruteforce_range_search.argtypes = [vp, i64, i32, i32, vp, i64, f32, f32, i32, vp, i64,
                                               c.POINTER(vp), c.POINTER(vp), c.POINTER(vp), i32, vp]
     L.kb2_merge_topk.argtypes = [i32, i32, i64, i32, vp, vp, vp, vp, i32, vp]
+    if hasattr(L, "kb2_faiss_describe"):
+        L.kb2_faiss_describe.argtypes = [vp, c.c_size_t, i32, vp, c.c_size_t]
+        L.kb2_faiss_rewrite.argtypes = [vp, c.c_size_t, i32, c.POINTER(vp), c.POINTER(c.c_size_t)]
+        L.kb2_index_deserialize_faiss.argtypes = [vp, c.c_size_t, i32, i32, c.POINTER(vp)]
+        L.kb2_index_serialize_faiss.argtypes = [vp, c.POINTER(vp), c.POINTER(c.c_size_t)]
+        L.kb2_index_deserialize_from_file.argtypes = [c.c_char_p, i32, c.POINTER(vp)]
+        L.kb2_index_get_meta.argtypes = [vp, vp, c.c_size_t]
+    if hasattr(L, "kb2_comm_unique_id"):   # (a stale build without the communicator API fails at Comm(), not at import)
+        L.kb2_comm_unique_id.argtypes = [vp]
+        L.kb2_comm_create.argtypes = [vp, i32, i32, i32, c.POINTER(vp)]
+        L.kb2_comm_destroy.argtypes = [vp]
+        L.kb2_comm_destroy.restype = None
+        L.kb2_comm_all_gather.argtypes = [vp, vp, vp, c.c_size_t, vp]
+        L.kb2_index_set_comm.argtypes = [vp, vp]
     L.kb2_index_last_search_counters.argtypes = [vp, vp]
     L.kb2_index_enable_kernel_timing.argtypes = [vp, i32]
     L.kb2_index_last_kernel_ms.argtypes = [vp, c.POINTER(f32)]
@@ -161,6 +175,11 @@ class Index:
 
     def set_shard(self, rank, world):
         _check(self.L.kb2_index_set_shard(self.h, rank, world))
+
+    def set_comm(self, comm):
+        """attach a Comm: search() on this sharded index becomes a collective returning the merged global top-k"""
+        self._comm = comm   # keep it alive
+        _check(self.L.kb2_index_set_comm(self.h, comm.h if comm is not None else None))
 
     def search(self, q, k, config=None, bitset=None, out=None):
         """q: [nq, dim] float32 numpy (host) or torch cuda tensor (device).  Returns (ids, dist)."""
@@ -272,6 +291,36 @@ class Index:
         _check(L.kb2_index_deserialize(ctypes.cast(buf, ctypes.c_void_p), len(blob), device, ctypes.byref(h)))
         return Index("?", _handle=h)
 
+    # -- the reference's wire format (faiss fourcc stream = the BinarySet payload)
+    def serialize_faiss(self):
+        p, n = ctypes.c_void_p(), ctypes.c_size_t()
+        _check(self.L.kb2_index_serialize_faiss(self.h, ctypes.byref(p), ctypes.byref(n)))
+        try:
+            return ctypes.string_at(p, n.value)
+        finally:
+            self.L.kb2_free(p)
+
+    @staticmethod
+    def deserialize_faiss(blob, device=0, with_norm=False):
+        L = lib()
+        h = ctypes.c_void_p()
+        buf = ctypes.create_string_buffer(blob, len(blob))
+        _check(L.kb2_index_deserialize_faiss(ctypes.cast(buf, ctypes.c_void_p), len(blob), 1 if with_norm else 0, device,
+                                             ctypes.byref(h)))
+        return Index("?", _handle=h)
+
+    @staticmethod
+    def deserialize_from_file(path, device=0):
+        L = lib()
+        h = ctypes.c_void_p()
+        _check(L.kb2_index_deserialize_from_file(path.encode(), device, ctypes.byref(h)))
+        return Index("?", _handle=h)
+
+    def meta(self):
+        buf = ctypes.create_string_buffer(1024)
+        _check(self.L.kb2_index_get_meta(self.h, ctypes.cast(buf, ctypes.c_void_p), 1024))
+        return json.loads(buf.value.decode())
+
     # -- introspection for bench.py
     def last_counters(self):
         c = np.zeros(8, np.int64)
@@ -285,12 +334,62 @@ class Index:
     def last_stage_info(self):
         v = np.zeros(4, np.float32)
         _check(self.L.kb2_index_last_stage_info(self.h, _ptr(v)))
-        return dict(stage_ms=float(v[0]), kernel_ms=float(v[1]), engine="tc" if v[2] > 0.5 else "scan")
+        return dict(stage_ms=float(v[0]), kernel_ms=float(v[1]), engine="tc" if v[2] > 0.5 else "scan", comm_ms=float(v[3]))
 
     def last_kernel_ms(self):
         v = ctypes.c_float()
         _check(self.L.kb2_index_last_kernel_ms(self.h, ctypes.byref(v)))
         return v.value
+
+
+def faiss_describe(blob, with_norm=False):
+    """host-only parse of a faiss fourcc stream -> dict (no GPU needed)"""
+    L = lib()
+    src = ctypes.create_string_buffer(blob, len(blob))
+    out = ctypes.create_string_buffer(1024)
+    _check(L.kb2_faiss_describe(ctypes.cast(src, ctypes.c_void_p), len(blob), 1 if with_norm else 0,
+                                ctypes.cast(out, ctypes.c_void_p), 1024))
+    return json.loads(out.value.decode())
+
+
+def faiss_rewrite(blob, with_norm=False):
+    """host-only: parse and re-emit with this library's writer"""
+    L = lib()
+    src = ctypes.create_string_buffer(blob, len(blob))
+    p, n = ctypes.c_void_p(), ctypes.c_size_t()
+    _check(L.kb2_faiss_rewrite(ctypes.cast(src, ctypes.c_void_p), len(blob), 1 if with_norm else 0, ctypes.byref(p), ctypes.byref(n)))
+    try:
+        return ctypes.string_at(p, n.value)
+    finally:
+        L.kb2_free(p)
+
+
+class Comm:
+    """NCCL communicator owned by the library (kb2_comm_*).  `bcast_bytes(bytes_or_None) -> bytes` is the host
+    application's way to ship rank 0's 128-byte id to every rank (tests / bench: torch.distributed.broadcast_object_list)."""
+
+    def __init__(self, rank, world, device, bcast_bytes):
+        self.L = lib()
+        self.rank, self.world = rank, world
+        uid = None
+        if rank == 0:
+            buf = (ctypes.c_uint8 * 128)()
+            _check(self.L.kb2_comm_unique_id(ctypes.cast(buf, ctypes.c_void_p)))
+            uid = bytes(buf)
+        uid = bcast_bytes(uid)
+        assert len(uid) == 128
+        self.h = ctypes.c_void_p()
+        src = ctypes.create_string_buffer(uid, 128)
+        _check(self.L.kb2_comm_create(ctypes.cast(src, ctypes.c_void_p), rank, world, device, ctypes.byref(self.h)))
+
+    def all_gather(self, send, recv, stream=0):
+        nbytes = send.numel() * send.element_size()
+        _check(self.L.kb2_comm_all_gather(self.h, _ptr(send), _ptr(recv), nbytes, ctypes.c_void_p(stream)))
+
+    def close(self):
+        if self.h:
+            self.L.kb2_comm_destroy(self.h)
+            self.h = None
 
 
 def _take_range(L, nq, pl, pi, pd):

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <memory>
 
+#include "kb2_fourcc.h"
 #include "kb2_hnsw.cuh"
 #include "kb2_index.cuh"
 #include "kb2_range.cuh"
@@ -444,6 +445,245 @@ kb2_index_deserialize(const uint8_t* blob, size_t size, int device, kb2_index_t*
     });
 }
 
+// ---------------------------------------------------------------- faiss fourcc streams (the reference's BinarySet payload)
+namespace {
+std::unique_ptr<IndexBase>
+index_from_faiss(const FaissIndexData& o, int device) {
+    std::unique_ptr<IndexBase> ix;
+    if (o.kind == "FLAT") {
+        auto* fi = new FlatIndex();
+        ix.reset(fi);
+    } else if (o.kind == "IVF_FLAT" || o.kind == "IVF_PQ") {
+        KB2_REQUIRE(!o.cosine, KB2_NOT_IMPLEMENTED, "faiss stream: cosine IVF indexes are not supported");
+        auto* iv = new IvfIndex();
+        ix.reset(iv);
+        iv->is_pq = (o.kind == "IVF_PQ");
+        iv->nlist = o.nlist;
+        iv->M = o.M;
+        iv->nbits = 8;
+        iv->refine = o.has_refine;
+    } else if (o.kind == "HNSW") {
+        auto* hn = new HnswIndex();
+        ix.reset(hn);
+        hn->M = o.cum.size() >= 2 ? o.cum[1] / 2 : 16;
+        hn->efConstruction = o.efConstruction;
+    } else {
+        throw Error(KB2_NOT_IMPLEMENTED, "faiss stream: unsupported index kind");
+    }
+    ix->type = o.kind;
+    ix->metric = o.metric;
+    ix->cosine = o.cosine;
+    if (o.cosine) ix->metric = KB2_METRIC_IP;
+    ix->dim = o.d;
+    ix->device = device;
+    ix->init_common();
+    if (auto* fi = dynamic_cast<FlatIndex*>(ix.get())) {
+        if (o.ntotal) fi->add(o.cosine ? fi->normalized(o.xb.data(), o.ntotal) : o.xb.data(), o.ntotal, nullptr);
+    } else if (auto* iv = dynamic_cast<IvfIndex*>(ix.get())) {
+        iv->import_begin(o.nlist, o.centroids.data(), iv->is_pq ? o.pq_centroids.data() : nullptr);
+        for (int64_t l = 0; l < o.nlist; l++)
+            if (!o.list_ids[l].empty()) iv->import_list(l, (int64_t)o.list_ids[l].size(), o.list_ids[l].data(), o.list_codes[l].data());
+        iv->import_finish(o.has_refine ? o.refine_xb.data() : nullptr, o.has_refine ? o.ntotal : 0);
+    } else if (auto* hn = dynamic_cast<HnswIndex*>(ix.get())) {
+        std::vector<int64_t> off(o.offsets.begin(), o.offsets.end());
+        std::vector<float> normed;
+        const float* xb = o.xb.data();
+        if (o.cosine) {   // the reference keeps raw rows + norms (IHN9); this core keeps unit rows
+            normed = o.xb;
+            for (int64_t i = 0; i < o.ntotal; i++) {
+                double s2 = 0;
+                for (int j = 0; j < o.d; j++) s2 += (double)normed[i * o.d + j] * normed[i * o.d + j];
+                const float inv = s2 > 0 ? (float)(1.0 / std::sqrt(s2)) : 1.f;
+                for (int j = 0; j < o.d; j++) normed[i * o.d + j] *= inv;
+            }
+            xb = normed.data();
+        }
+        hn->import_graph(o.ntotal, xb, o.levels.data(), off.data(), o.neighbors.data(), o.cum.data(), (int)o.cum.size(), o.entry_point,
+                         o.max_level);
+    }
+    return ix;
+}
+
+void
+index_to_faiss(IndexBase& ix, FaissIndexData& o) {
+    o.kind = ix.type;
+    o.d = ix.dim;
+    o.metric = ix.metric;
+    KB2_REQUIRE(!ix.cosine, KB2_NOT_IMPLEMENTED, "faiss stream: a COSINE index keeps normalised vectors only (the reference stores raw rows + norms)");
+    KB2_REQUIRE(ix.shard_world == 1, KB2_NOT_IMPLEMENTED, "serialising a shard");
+    o.ntotal = ix.count();
+    if (auto* fi = dynamic_cast<FlatIndex*>(&ix)) {
+        KB2_REQUIRE(!fi->custom_labels, KB2_NOT_IMPLEMENTED, "faiss stream: FLAT with custom ids");
+        o.xb.resize((size_t)o.ntotal * o.d);
+        if (o.ntotal) KB2_CUDA_CHECK(cudaMemcpy(o.xb.data(), fi->base.p, o.xb.size() * 4, cudaMemcpyDeviceToHost));
+    } else if (auto* iv = dynamic_cast<IvfIndex*>(&ix)) {
+        KB2_REQUIRE(iv->trained, KB2_INDEX_NOT_TRAINED, "index not trained");
+        iv->seal();
+        o.nlist = iv->nlist;
+        o.nprobe = 1;
+        o.centroids.resize((size_t)iv->nlist * o.d);
+        KB2_CUDA_CHECK(cudaMemcpy(o.centroids.data(), iv->centroids.p, o.centroids.size() * 4, cudaMemcpyDeviceToHost));
+        o.M = iv->M;
+        o.code_size = iv->is_pq ? (uint64_t)iv->M : (uint64_t)o.d * 4;
+        if (iv->is_pq) {
+            KB2_REQUIRE(iv->nbits == 8, KB2_NOT_IMPLEMENTED, "faiss stream: nbits != 8");
+            o.pq_centroids.resize((size_t)256 * o.d);
+            KB2_CUDA_CHECK(cudaMemcpy(o.pq_centroids.data(), iv->pqc.p, o.pq_centroids.size() * 4, cudaMemcpyDeviceToHost));
+        }
+        o.list_ids.assign(iv->nlist, {});
+        o.list_codes.assign(iv->nlist, {});
+        for (int64_t l = 0; l < iv->nlist; l++) {
+            const int64_t len = iv->h_list_len[l];
+            if (!len) continue;
+            o.list_ids[l].resize(len);
+            o.list_codes[l].resize((size_t)len * o.code_size);
+            iv->export_list(l, o.list_ids[l].data(), o.list_codes[l].data());
+        }
+        o.has_refine = iv->is_pq && iv->refine;
+        if (o.has_refine) {
+            KB2_REQUIRE(!iv->custom_labels, KB2_NOT_IMPLEMENTED, "faiss stream: refine store with custom ids");
+            // refine store in id order: row r lives at position pos_of_row[r]
+            DevBuf<float> byrow;
+            byrow.ensure((size_t)std::max<int64_t>(o.ntotal, 1) * o.d);
+            gather_rows_kernel<<<grid1d(o.ntotal * 32, 256), 256, 0, iv->stream>>>(iv->vecs.p, iv->pos_of_row.p, o.ntotal, o.d, o.d, byrow.p);
+            o.refine_xb.resize((size_t)o.ntotal * o.d);
+            KB2_CUDA_CHECK(cudaMemcpyAsync(o.refine_xb.data(), byrow.p, o.refine_xb.size() * 4, cudaMemcpyDeviceToHost, iv->stream));
+            KB2_CUDA_CHECK(cudaStreamSynchronize(iv->stream));
+            o.k_factor = 1.f;
+        }
+    } else if (auto* hn = dynamic_cast<HnswIndex*>(&ix)) {
+        KB2_REQUIRE(!hn->custom_labels, KB2_NOT_IMPLEMENTED, "faiss stream: HNSW with custom ids");
+        o.xb = hn->h_vecs;
+        o.levels = hn->h_levels;
+        o.neighbors = hn->h_neighbors;
+        o.offsets.assign(hn->h_offsets.begin(), hn->h_offsets.end());
+        o.entry_point = hn->entry_point;
+        o.max_level = hn->max_level;
+        o.efConstruction = hn->efConstruction;
+        // K/impl/HNSW.cpp:78-89 set_default_probas(M, 1 / ln M): the full level table, of which h_cum is a prefix
+        const double mult = 1.0 / std::log((double)hn->M);
+        int nn = 0;
+        o.cum.assign(1, 0);
+        for (int level = 0;; level++) {
+            const double proba = std::exp(-level / mult) * (1 - std::exp(-1 / mult));
+            if (proba < 1e-9) break;
+            o.assign_probas.push_back(proba);
+            nn += level == 0 ? hn->M * 2 : hn->M;
+            o.cum.push_back(nn);
+        }
+        KB2_REQUIRE(o.cum.size() >= hn->h_cum.size(), KB2_INTERNAL_ERROR, "HNSW level table shorter than the graph's");
+        for (size_t i = 0; i < hn->h_cum.size(); i++)
+            KB2_REQUIRE(o.cum[i] == hn->h_cum[i], KB2_NOT_IMPLEMENTED, "faiss stream: non-default HNSW link counts");
+    } else {
+        throw Error(KB2_NOT_IMPLEMENTED, "faiss stream: unknown index class");
+    }
+}
+}  // namespace
+
+int
+kb2_faiss_describe(const uint8_t* blob, size_t size, int with_norm, char* json_out, size_t cap) {
+    return guarded([&] {
+        KB2_REQUIRE(blob && json_out && cap > 0, KB2_INVALID_ARGS, "null argument");
+        FaissReader rd{BlobReader{blob, size}, with_norm != 0};
+        const FaissIndexData o = rd.read_index();
+        const std::string s = faiss_describe(o);
+        KB2_REQUIRE(s.size() + 1 <= cap, KB2_INVALID_ARGS, "output buffer too small");
+        memcpy(json_out, s.c_str(), s.size() + 1);
+    });
+}
+// parse + re-emit on the host (no device): the writer's output for exactly what the reader understood
+int
+kb2_faiss_rewrite(const uint8_t* blob, size_t size, int with_norm, uint8_t** out, size_t* out_size) {
+    return guarded([&] {
+        KB2_REQUIRE(blob && out && out_size, KB2_INVALID_ARGS, "null argument");
+        FaissReader rd{BlobReader{blob, size}, with_norm != 0};
+        const FaissIndexData o = rd.read_index();
+        std::vector<uint8_t> b;
+        FaissWriter wr{BlobWriter{b}};
+        wr.write_index(o);
+        *out = (uint8_t*)malloc(b.size() ? b.size() : 1);
+        KB2_REQUIRE(*out != nullptr, KB2_MALLOC_ERROR, "malloc failed");
+        memcpy(*out, b.data(), b.size());
+        *out_size = b.size();
+    });
+}
+int
+kb2_index_deserialize_faiss(const uint8_t* blob, size_t size, int with_norm, int device, kb2_index_t* out) {
+    return guarded([&] {
+        KB2_REQUIRE(blob && out, KB2_INVALID_ARGS, "null argument");
+        *out = nullptr;
+        FaissReader rd{BlobReader{blob, size}, with_norm != 0};
+        const FaissIndexData o = rd.read_index();   // parse (and reject) before touching the device
+        require_device(device);
+        std::unique_ptr<IndexBase> ix = index_from_faiss(o, device);
+        auto* hh = new Handle();
+        hh->ix = std::move(ix);
+        *out = reinterpret_cast<kb2_index_t>(hh);
+    });
+}
+int
+kb2_index_serialize_faiss(kb2_index_t h, uint8_t** out, size_t* out_size) {
+    return guarded([&] {
+        IndexBase* ix = ix_of(h);
+        KB2_REQUIRE(out && out_size, KB2_INVALID_ARGS, "null argument");
+        std::lock_guard<std::mutex> lk(ix->mu);
+        KB2_CUDA_CHECK(cudaSetDevice(ix->device));
+        FaissIndexData o;
+        index_to_faiss(*ix, o);
+        std::vector<uint8_t> blob;
+        FaissWriter wr{BlobWriter{blob}};
+        wr.write_index(o);
+        *out = (uint8_t*)malloc(blob.size() ? blob.size() : 1);
+        KB2_REQUIRE(*out != nullptr, KB2_MALLOC_ERROR, "malloc failed");
+        memcpy(*out, blob.data(), blob.size());
+        *out_size = blob.size();
+    });
+}
+// IndexNode::DeserializeFromFile (index_node.h:329-395): a file holding either container
+int
+kb2_index_deserialize_from_file(const char* path, int device, kb2_index_t* out) {
+    std::vector<uint8_t> buf;
+    int st = guarded([&] {
+        KB2_REQUIRE(path && out, KB2_INVALID_ARGS, "null argument");
+        FILE* f = fopen(path, "rb");
+        KB2_REQUIRE(f != nullptr, KB2_INVALID_ARGS, std::string("cannot open ") + path);
+        fseek(f, 0, SEEK_END);
+        const long n = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        buf.resize(n > 0 ? (size_t)n : 0);
+        const size_t got = buf.empty() ? 0 : fread(buf.data(), 1, buf.size(), f);
+        fclose(f);
+        KB2_REQUIRE(got == buf.size() && got >= 4, KB2_INVALID_BINARY_SET, "short read");
+    });
+    if (st != KB2_SUCCESS) return st;
+    uint32_t magic;
+    memcpy(&magic, buf.data(), 4);
+    if (magic == 0x4932424b) return kb2_index_deserialize(buf.data(), buf.size(), device, out);
+    return kb2_index_deserialize_faiss(buf.data(), buf.size(), 0, device, out);
+}
+// IndexNode::GetIndexMeta (index_node.h:329-395): JSON description of the loaded index
+int
+kb2_index_get_meta(kb2_index_t h, char* json_out, size_t cap) {
+    return guarded([&] {
+        IndexBase* ix = ix_of(h);
+        KB2_REQUIRE(json_out && cap > 0, KB2_INVALID_ARGS, "null argument");
+        std::string s = "{\"type\": \"" + ix->type + "\", \"dim\": " + std::to_string(ix->dim) + ", \"rows\": " + std::to_string(ix->count()) +
+                        ", \"metric_type\": \"" + (ix->cosine ? "COSINE" : (ix->metric == KB2_METRIC_IP ? "IP" : "L2")) + "\"" +
+                        ", \"size_bytes\": " + std::to_string(ix->size_bytes()) + ", \"device\": " + std::to_string(ix->device) +
+                        ", \"shard_rank\": " + std::to_string(ix->shard_rank) + ", \"shard_world\": " + std::to_string(ix->shard_world);
+        if (auto* iv = dynamic_cast<IvfIndex*>(ix)) {
+            s += ", \"nlist\": " + std::to_string(iv->nlist);
+            if (iv->is_pq) s += ", \"m\": " + std::to_string(iv->M) + ", \"nbits\": " + std::to_string(iv->nbits) + ", \"refine\": " + (iv->refine ? "true" : "false");
+        } else if (auto* hn = dynamic_cast<HnswIndex*>(ix)) {
+            s += ", \"M\": " + std::to_string(hn->M) + ", \"efConstruction\": " + std::to_string(hn->efConstruction) +
+                 ", \"max_level\": " + std::to_string(hn->max_level) + ", \"entry_point\": " + std::to_string(hn->entry_point);
+        }
+        s += "}";
+        KB2_REQUIRE(s.size() + 1 <= cap, KB2_INVALID_ARGS, "output buffer too small");
+        memcpy(json_out, s.c_str(), s.size() + 1);
+    });
+}
+
 // ---------------------------------------------------------------- BruteForce
 // One scratch FLAT object per device, reused across calls (stream, events, selection scratch); a device-resident base is
 // viewed in place (no copy), a host base is staged into the scratch buffer.
@@ -536,6 +776,62 @@ kb2_bruteforce_range_search(const float* base, int64_t nb, int dim, int metric, 
     });
 }
 
+// ---------------------------------------------------------------- multi-GPU: NCCL communicator behind the ABI
+int
+kb2_comm_unique_id(uint8_t* out128) {
+    return guarded([&] {
+        KB2_REQUIRE(out128 != nullptr, KB2_INVALID_ARGS, "null buffer");
+        static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+        ncclUniqueId id;
+        KB2_NCCL_CHECK(Comm::api().GetUniqueId(&id));
+        memcpy(out128, &id, 128);
+    });
+}
+int
+kb2_comm_create(const uint8_t* id128, int rank, int world, int device, kb2_comm_t* out) {
+    return guarded([&] {
+        KB2_REQUIRE(id128 && out, KB2_INVALID_ARGS, "null argument");
+        KB2_REQUIRE(world >= 1 && rank >= 0 && rank < world, KB2_INVALID_ARGS, "bad rank/world");
+        *out = nullptr;
+        require_device(device);
+        ncclUniqueId id;
+        memcpy(&id, id128, 128);
+        std::unique_ptr<Comm> c(new Comm());
+        c->rank = rank;
+        c->world = world;
+        c->device = device;
+        KB2_NCCL_CHECK(Comm::api().CommInitRank(&c->comm, world, id, rank));
+        *out = reinterpret_cast<kb2_comm_t>(c.release());
+    });
+}
+void
+kb2_comm_destroy(kb2_comm_t c) {
+    delete reinterpret_cast<Comm*>(c);
+}
+int
+kb2_comm_all_gather(kb2_comm_t c, const void* send, void* recv, size_t bytes, void* cuda_stream) {
+    return guarded([&] {
+        KB2_REQUIRE(c && send && recv, KB2_INVALID_ARGS, "null argument");
+        Comm* cc = reinterpret_cast<Comm*>(c);
+        KB2_CUDA_CHECK(cudaSetDevice(cc->device));
+        cc->all_gather(send, recv, bytes, (cudaStream_t)cuda_stream);
+    });
+}
+int
+kb2_index_set_comm(kb2_index_t h, kb2_comm_t c) {
+    return guarded([&] {
+        IndexBase* ix = ix_of(h);
+        std::lock_guard<std::mutex> lk(ix->mu);
+        Comm* cc = reinterpret_cast<Comm*>(c);
+        if (cc) {
+            KB2_REQUIRE(cc->rank == ix->shard_rank && cc->world == ix->shard_world, KB2_INVALID_ARGS,
+                        "communicator rank/world differ from kb2_index_set_shard");
+            KB2_REQUIRE(cc->device == ix->device, KB2_INVALID_ARGS, "communicator lives on another device");
+        }
+        ix->set_comm(cc);
+    });
+}
+
 // ---------------------------------------------------------------- multi-GPU merge
 int
 kb2_merge_topk(int metric, int world, int64_t nq, int k, const int64_t* in_ids, const float* in_dist, int64_t* out_ids,
@@ -601,7 +897,7 @@ kb2_index_last_stage_info(kb2_index_t h, float* out4) {
         out4[0] = ix->last_stage_ms;
         out4[1] = ix->last_kernel_ms;
         out4[2] = (float)ix->last_engine;
-        out4[3] = 0.f;
+        out4[3] = ix->last_comm_ms;
     });
 }
 

@@ -9,9 +9,11 @@
 #include <vector>
 
 #include "kb2_build.cuh"
+#include "kb2_comm.h"
 #include "kb2_gemm_tc.cuh"
 #include "kb2_ivf.cuh"
 #include "kb2_ivfpq_tc.cuh"
+#include "kb2_ivfflat_tc.cuh"
 #include "kb2_json.h"
 
 namespace kb2 {
@@ -72,6 +74,8 @@ init_kernel_attributes() {
         set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_IP>);
         set((const void*)pqtc::bound_kernel<KB2_METRIC_L2>);
         set((const void*)pqtc::bound_kernel<KB2_METRIC_IP>);
+        set((const void*)fltc::ivfflat_tc_kernel<KB2_METRIC_L2>);
+        set((const void*)fltc::ivfflat_tc_kernel<KB2_METRIC_IP>);
         cudaGetLastError();
     });
 }
@@ -156,7 +160,12 @@ struct IndexBase {
     float last_kernel_ms = 0.f;      // dominant kernel of the last search (IVF_PQ tensor-core engine: the filter kernel)
     float last_stage_ms = 0.f;       // whole list-scan stage of the last search (all engines)
     int last_engine = 0;             // 0: query-major scan kernels, 1: list-major tensor-core engine
+    float last_comm_ms = 0.f;        // collectives (+ merge) of the last sharded search
+    Comm* comm = nullptr;            // not owned (kb2_index_set_comm)
+    virtual void set_comm(Comm* c) { comm = c; }
+    bool distributed() const { return comm != nullptr && shard_world > 1; }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev_in = nullptr;
+    cudaEvent_t ev_c0 = nullptr, ev_c1 = nullptr, ev_c2 = nullptr, ev_c3 = nullptr;   // collectives of a sharded search
     DevBuf<unsigned long long> d_counter;
     PinnedBuf h_counter;   // pinned landing zone of the per-search device counters (no pageable async copy)
 
@@ -179,7 +188,7 @@ struct IndexBase {
     }
 
     virtual ~IndexBase() {
-        for (cudaEvent_t e : {ev0, ev1, ev2, ev3, ev_in})
+        for (cudaEvent_t e : {ev0, ev1, ev2, ev3, ev_in, ev_c0, ev_c1, ev_c2, ev_c3})
             if (e) cudaEventDestroy(e);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
@@ -204,6 +213,7 @@ struct IndexBase {
         KB2_CUDA_CHECK(cudaEventCreate(&ev2));
         KB2_CUDA_CHECK(cudaEventCreate(&ev3));
         KB2_CUDA_CHECK(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+        for (cudaEvent_t* e : {&ev_c0, &ev_c1, &ev_c2, &ev_c3}) KB2_CUDA_CHECK(cudaEventCreate(e));
         d_counter.ensure(8);
         h_counter.ensure(64);
     }
@@ -498,7 +508,7 @@ struct IvfIndex : IndexBase {
     DevBuf<int64_t> list_off;
     DevBuf<int32_t> list_len, rows, pos_of_row;
     DevBuf<uint8_t> codes;     // [G][npad][16] or [npad][M]
-    DevBuf<float> t1, vecs;
+    DevBuf<float> t1, vecs, vnorm2;   // vnorm2[pos] = |x|^2 (IVF_FLAT: row term of the list-major tensor-core engine)
     DevBuf<int64_t> labels;    // row -> label (sealed copy of f_labels)
     DevBuf<int32_t> s_qkey, s_qkey2, s_qidx, s_qperm;
     DevBuf<uint8_t> s_sort_tmp;
@@ -702,6 +712,10 @@ struct IvfIndex : IndexBase {
         if (keeps_vecs()) {
             vecs.alloc_exact((size_t)npad * dim);
             gather_rows_kernel<<<grid1d(npad * 32, 256), 256, 0, st>>>(f_vecs.p, rows.p, npad, dim, dim, vecs.p);
+            if (!is_pq) {
+                vnorm2.alloc_exact(npad);
+                row_norms_kernel<<<grid1d(npad * 32, 256), 256, 0, st>>>(vecs.p, npad, dim, vnorm2.p);
+            }
         }
         if (custom_labels) {
             labels.alloc_exact(std::max<int64_t>(n, 1));
@@ -791,13 +805,16 @@ struct IvfIndex : IndexBase {
     // ---------------------------------------------------------------- list-major tensor-core engine (kb2_ivfpq_tc.cuh)
     static constexpr int kTcCandCap = 1024;     // survivor slots per query (overflow -> LUT kernel redoes the query)
     DevBuf<uint16_t> tc_pqc16, s_qb16;
-    DevBuf<float> tc_maxn2, s_qnorm, s_pair_base, s_lut;
-    DevBuf<int32_t> s_lcount, s_lstart, s_items, s_pair_q, s_plan_out, s_flaglist;
-    DevBuf<uint64_t> s_cand, s_boundrows;
+    DevBuf<float> tc_maxn2, s_qnorm, s_pair_base, s_lut, s_bound;
+    DevBuf<int32_t> s_lcount, s_lstart, s_items, s_pair_q, s_plan_out, s_flaglist, s_resp;
+    DevBuf<uint64_t> s_cand;
     DevBuf<uint32_t> s_cand_cnt, s_logcnt;
     DevBuf<uint4> s_log;
-    float tc_rmax = 0.f;
+    float tc_rmax = 0.f, tc_rowmax = 0.f;
     bool tc_ready = false;
+    // multi-GPU (kb2_index_set_comm): every rank holds the lists l % world == rank and sees the whole batch
+    DevBuf<int64_t> s_loc_ids, s_g_ids;
+    DevBuf<float> s_loc_dist, s_g_dist;
 
     bool
     use_tc_engine(int64_t nq, int nprobe, int Ksel) const {
@@ -813,16 +830,21 @@ struct IvfIndex : IndexBase {
     void
     search_tc(IvfScanParams sp, int64_t nq, int nprobe, int Ksel, int k_base, bool has_bits) {
         cudaStream_t st = stream;
+        const bool dist = distributed();
         if (!tc_ready) {
             tc_pqc16.alloc_exact((size_t)16 * 256 * 8);
-            tc_maxn2.alloc_exact(16);
+            tc_maxn2.alloc_exact(20);
+            KB2_CUDA_CHECK(cudaMemsetAsync(tc_maxn2.p + 16, 0, 16, st));
             pqtc::prepare_tables_kernel<<<16, 256, 0, st>>>(pqc.p, (__nv_bfloat16*)tc_pqc16.p, tc_maxn2.p);
-            float h[16];
+            if (metric == KB2_METRIC_L2 && npad > 0)
+                pqtc::max_abs_kernel<<<kNumSMs * 2, 256, 0, st>>>(t1.p, npad, (uint32_t*)(tc_maxn2.p + 16));
+            float h[20];
             KB2_CUDA_CHECK(cudaMemcpyAsync(h, tc_maxn2.p, sizeof(h), cudaMemcpyDeviceToHost, st));
             KB2_CUDA_CHECK(cudaStreamSynchronize(st));
             double acc = 0;
-            for (float v : h) acc += v;
+            for (int i = 0; i < 16; i++) acc += h[i];
             tc_rmax = (float)std::sqrt(acc) * 1.0001f;
+            tc_rowmax = 0.5f * h[16] * 1.0001f;   // max |t1| / 2: the largest row term of the admission test
             tc_ready = true;
         }
         const int64_t npairs = nq * nprobe;
@@ -837,31 +859,47 @@ struct IvfIndex : IndexBase {
             marks.emplace_back(name, e);
         };
         mark("start");
-        // ---- phase A: LUT scan of the nearest lists -> per-query upper bound of the k_base-th best key
+        // ---- phase A: exact scan of each query's nearest lists -> upper bound of its k_base-th best key.  A bound taken from ANY
+        //      subset of the codes is valid on every rank, so with a communicator the query is handled by the rank that owns
+        //      its nearest list (1/world of the batch each; tables only for those) and the bounds are min-reduced.
         const char* e_p0 = getenv("KB2_TC_P0");
         const char* e_ac = getenv("KB2_TC_A_CODES");
         const int p0 = std::max(1, std::min((e_p0 ? atoi(e_p0) : 8) * std::max(1, shard_world), nprobe));   // at most this many lists
         const int a_codes = e_ac ? atoi(e_ac) : 3000;                                                        // ... until this many codes
-        s_boundrows.ensure((size_t)nq * Ksel);
+        s_bound.ensure((size_t)nq);
         s_lut.ensure((size_t)nq * 4096);
+        const int32_t* qlist = nullptr;
+        const uint32_t* qcount = nullptr;
+        unsigned bound_grid = (unsigned)nq;
+        if (dist) {
+            s_resp.ensure((size_t)nq + 1);
+            pqtc::compact_resp_kernel<<<1, 1024, 0, st>>>(sp.probe_ids, nprobe, nq, shard_world, shard_rank, s_resp.p + 1,
+                                                          (uint32_t*)s_resp.p);
+            pqtc::fill_f32_kernel<<<grid1d(nq, 256), 256, 0, st>>>(s_bound.p, nq, INFINITY);
+            qlist = s_resp.p + 1;
+            qcount = (const uint32_t*)s_resp.p;
+            bound_grid = (unsigned)std::min<int64_t>(nq, std::max<int64_t>(4 * kNumSMs, 2 * nq / shard_world));
+            last.launches += 2;
+        }
         {
             const size_t smem = pqtc::BOUND_SMEM;
             if (metric == KB2_METRIC_L2) {
-                pqtc::lut_build_kernel<KB2_METRIC_L2><<<kNumSMs, 256, 0, st>>>(sp.queries, nq, pqc.p, s_lut.p);
+                pqtc::lut_build_kernel<KB2_METRIC_L2><<<kNumSMs, 256, 0, st>>>(sp.queries, nq, qlist, qcount, pqc.p, s_lut.p);
                 mark("lut");
-                pqtc::bound_kernel<KB2_METRIC_L2><<<(unsigned)nq, 128, smem, st>>>(
-                    s_lut.p, sp.probe_ids, sp.probe_dis, nprobe, p0, a_codes, k_base, list_off.p, list_len.p, (const uint4*)codes.p,
-                    t1.p, sp.bitset, rows.p, Ksel, s_boundrows.p, d_counter.p + 4);
+                pqtc::bound_kernel<KB2_METRIC_L2><<<bound_grid, 128, smem, st>>>(
+                    s_lut.p, qlist, qcount, nq, sp.probe_ids, sp.probe_dis, nprobe, p0, a_codes, k_base, list_off.p, list_len.p,
+                    (const uint4*)codes.p, t1.p, sp.bitset, rows.p, s_bound.p, d_counter.p + 4);
             } else {
-                pqtc::lut_build_kernel<KB2_METRIC_IP><<<kNumSMs, 256, 0, st>>>(sp.queries, nq, pqc.p, s_lut.p);
+                pqtc::lut_build_kernel<KB2_METRIC_IP><<<kNumSMs, 256, 0, st>>>(sp.queries, nq, qlist, qcount, pqc.p, s_lut.p);
                 mark("lut");
-                pqtc::bound_kernel<KB2_METRIC_IP><<<(unsigned)nq, 128, smem, st>>>(
-                    s_lut.p, sp.probe_ids, sp.probe_dis, nprobe, p0, a_codes, k_base, list_off.p, list_len.p, (const uint4*)codes.p,
-                    t1.p, sp.bitset, rows.p, Ksel, s_boundrows.p, d_counter.p + 4);
+                pqtc::bound_kernel<KB2_METRIC_IP><<<bound_grid, 128, smem, st>>>(
+                    s_lut.p, qlist, qcount, nq, sp.probe_ids, sp.probe_dis, nprobe, p0, a_codes, k_base, list_off.p, list_len.p,
+                    (const uint4*)codes.p, t1.p, sp.bitset, rows.p, s_bound.p, d_counter.p + 4);
             }
             KB2_CUDA_CHECK(cudaGetLastError());
             last.launches += 2;
         }
+        if (dist) comm->all_reduce_min_f32(s_bound.p, s_bound.p, (size_t)nq, st);
         mark("phaseA");
         // ---- plan: pairs grouped by list, work items
         const int64_t max_items = nlist + npairs / pqtc::NQT + 2;
@@ -900,10 +938,10 @@ struct IvfIndex : IndexBase {
         tp.item_nq = item_nq;
         tp.pair_q = s_pair_q.p;
         tp.pair_base = s_pair_base.p;
-        tp.bound_rows = s_boundrows.p;
-        tp.bound_stride = Ksel;
+        tp.bound = s_bound.p;
         tp.k_need = k_base;
         tp.margin_coef = (metric == KB2_METRIC_L2 ? 2.f : 1.f) * pqtc::kErrCoef * tc_rmax;
+        tp.rmax = (metric == KB2_METRIC_L2) ? tc_rowmax : 0.f;
         tp.list_off = list_off.p;
         tp.list_len = list_len.p;
         tp.codes = (const uint4*)codes.p;
@@ -913,16 +951,15 @@ struct IvfIndex : IndexBase {
         tp.pqc16 = (const uint4*)tc_pqc16.p;
         tp.bitset = sp.bitset;
         tp.rows = rows.p;
-        const int n_logs = 2 * kNumSMs;   // one per epilogue group, + 1 shared
+        const int n_logs = 2 * kNumSMs;   // one per epilogue group (+ 1 legacy slot that stays empty)
         const uint32_t log_cap = (uint32_t)std::min<int64_t>(std::max<int64_t>(nq * 1024 / n_logs, 16384), 1 << 19);
-        const uint32_t shared_cap = std::max<uint32_t>(1u << 20, 8 * log_cap);   // tiles that overflow the smem queue
-        s_log.ensure((size_t)n_logs * log_cap + shared_cap);
+        s_log.ensure((size_t)(n_logs + 1) * log_cap);
         s_logcnt.ensure(n_logs + 8);
         KB2_CUDA_CHECK(cudaMemsetAsync(s_logcnt.p, 0, (n_logs + 8) * 4, st));
         tp.log = s_log.p;
         tp.log_cnt = s_logcnt.p;
         tp.log_cap = log_cap;
-        tp.shared_cap = shared_cap;
+        tp.shared_cap = log_cap;
         tp.qflag = s_cand_cnt.p + nq;
         tp.counters = d_counter.p;
         if (timing) KB2_CUDA_CHECK(cudaEventRecord(ev2, st));
@@ -934,16 +971,16 @@ struct IvfIndex : IndexBase {
         KB2_CUDA_CHECK(cudaGetLastError());
         mark("tc_filter");
         // ---- survivors: group by query, exact fp32 keys (bit-identical to the LUT engine's)
-        pqtc::scatter_survivors_kernel<<<dim3(16, n_logs + 1), 256, 0, st>>>(s_log.p, s_logcnt.p, log_cap, shared_cap, s_cand.p, s_cand_cnt.p,
+        pqtc::scatter_survivors_kernel<<<dim3(16, n_logs + 1), 256, 0, st>>>(s_log.p, s_logcnt.p, log_cap, log_cap, s_cand.p, s_cand_cnt.p,
                                                                          kTcCandCap, tp.qflag, d_counter.p);
         if (metric == KB2_METRIC_L2)
             pqtc::exact_eval_kernel<KB2_METRIC_L2><<<(unsigned)nq, 128, 0, st>>>(
-                s_lut.p, s_boundrows.p, Ksel, k_base, (const uint4*)codes.p, t1.p, sp.bitset, rows.p, s_cand.p, s_cand_cnt.p,
-                kTcCandCap, tp.qflag, s_logcnt.p + n_logs + 1);
+                sp.queries, pqc.p, s_bound.p, (const uint4*)codes.p, t1.p, sp.bitset, rows.p, s_cand.p, s_cand_cnt.p, kTcCandCap,
+                tp.qflag, s_logcnt.p + n_logs + 1);
         else
             pqtc::exact_eval_kernel<KB2_METRIC_IP><<<(unsigned)nq, 128, 0, st>>>(
-                s_lut.p, s_boundrows.p, Ksel, k_base, (const uint4*)codes.p, t1.p, sp.bitset, rows.p, s_cand.p, s_cand_cnt.p,
-                kTcCandCap, tp.qflag, s_logcnt.p + n_logs + 1);
+                sp.queries, pqc.p, s_bound.p, (const uint4*)codes.p, t1.p, sp.bitset, rows.p, s_cand.p, s_cand_cnt.p, kTcCandCap,
+                tp.qflag, s_logcnt.p + n_logs + 1);
         KB2_CUDA_CHECK(cudaGetLastError());
         last.launches += 7;
         mark("scatter+eval");
@@ -961,7 +998,7 @@ struct IvfIndex : IndexBase {
             f.flag_list = s_flaglist.p + 1;
             f.flag_count = (const uint32_t*)s_flaglist.p;
             f.qperm = nullptr;
-            f.lut_global = s_lut.p;
+            f.lut_global = nullptr;   // the redo pass builds its own tables (a handful of queries)
             f.counters = d_counter.p + 4;
             launch_scan(f, (unsigned)std::min<int64_t>(nq * f.nsplit, 3 * kNumSMs), Ksel, (nprobe + f.nsplit - 1) / f.nsplit, has_bits);
         }
@@ -978,13 +1015,142 @@ struct IvfIndex : IndexBase {
             cudaMemcpy(&hn, s_plan_out.p, 4, cudaMemcpyDeviceToHost);
             unsigned long long hc2[8];
             cudaMemcpy(hc2, d_counter.p, 64, cudaMemcpyDeviceToHost);
-            uint32_t hl[8];
-            cudaMemcpy(hl, s_logcnt.p + 2 * kNumSMs, 32, cudaMemcpyDeviceToHost);
-            fprintf(stderr, " [shared-log %u over %u | overflow tiles %u max pushes %u]", hl[0], hl[1], hl[2], hl[3]);
-            fprintf(stderr, " items %u survivors %llu flagged %llu (queue-overflow pushes %llu, row overflows %llu, no bound %llu)\n", hn,
-                    hc2[2], hc2[7], hc2[3], hc2[6] & 0xffffffffull, hc2[6] >> 32);
+            fprintf(stderr, " items %u survivors %llu flagged %llu (row overflows %llu, no bound %llu)\n", hn, hc2[2], hc2[7],
+                    hc2[6] & 0xffffffffull, hc2[6] >> 32);
             for (auto& m : marks) cudaEventDestroy(m.second);
         }
+    }
+
+    // ---------------------------------------------------------------- IVF_FLAT list-major tensor-core engine (kb2_ivfflat_tc.cuh)
+    DevBuf<float> s_qhi, s_qlo;
+    bool
+    use_flat_tc_engine(int64_t nq, int nprobe, int k) const {
+        if (is_pq || dim % fltc::BK != 0 || dim < fltc::BK || npad >= (1ll << 31)) return false;
+        const char* e = getenv("KB2_FLAT_ENGINE");
+        if (e && !strcmp(e, "scan")) return false;
+        if (k + 16 > kTcCandCap / 2) return false;
+        if (e && !strcmp(e, "tc")) return true;
+        // a list tile is amortised over the queries probing it
+        return (double)nq * nprobe >= 8.0 * (double)nlist && nq >= 64;
+    }
+
+    // returns false when some query overflowed its candidate row (caller falls back to the query-major scan)
+    bool
+    search_flat_tc(IvfScanParams sp, int64_t nq, int nprobe, int Ksel, int k, bool has_bits) {
+        cudaStream_t st = stream;
+        const int64_t npairs = nq * nprobe;
+        const int64_t npairs_pad = npairs + fltc::NQ_ITEM;
+        // ---- phase A: exact k-th best key over the query's nearest probed lists (query-major kernel) = admission bound
+        const int pA = std::min(nprobe, std::max(1, 2 * shard_world));
+        s_bound.ensure((size_t)nq);
+        {
+            IvfScanParams a = sp;
+            a.nprobe = pA;
+            a.probe_stride = nprobe;
+            a.nsplit = 1;
+            a.partial = s_partial2.p;
+            a.partial_stride = 0;
+            a.counters = nullptr;
+            a.qperm = nullptr;
+            launch_scan(a, (unsigned)nq, Ksel, pA, has_bits);
+            fltc::extract_bound_kernel<<<grid1d(nq, 256), 256, 0, st>>>(s_partial2.p, Ksel, k, nq, s_bound.p);
+            if (distributed()) comm->all_reduce_min_f32(s_bound.p, s_bound.p, (size_t)nq, st);
+            last.launches += 1;
+        }
+        // ---- plan: pairs grouped by list, items of <= 128 queries
+        const int64_t max_items = nlist + npairs / fltc::NQ_ITEM + 2;
+        s_lcount.ensure((size_t)2 * nlist);
+        s_lstart.ensure((size_t)nlist);
+        s_items.ensure((size_t)3 * max_items);
+        s_plan_out.ensure(4);
+        s_pair_q.ensure((size_t)npairs);
+        s_pair_base.ensure((size_t)npairs);
+        s_qnorm.ensure((size_t)nq);
+        s_cand.ensure((size_t)nq * kTcCandCap);
+        s_cand_cnt.ensure((size_t)2 * nq + 4);
+        s_qhi.ensure((size_t)npairs_pad * dim);
+        s_qlo.ensure((size_t)npairs_pad * dim);
+        KB2_CUDA_CHECK(cudaMemsetAsync(s_lcount.p, 0, (size_t)2 * nlist * 4, st));
+        KB2_CUDA_CHECK(cudaMemsetAsync(s_cand_cnt.p, 0, ((size_t)2 * nq + 4) * 4, st));
+        pqtc::count_pairs_kernel<<<grid1d(npairs, 256), 256, 0, st>>>(sp.probe_ids, npairs, list_len.p, s_lcount.p);
+        int32_t* item_list = s_items.p;
+        int32_t* item_q0 = s_items.p + max_items;
+        int32_t* item_nq = s_items.p + 2 * max_items;
+        fltc::plan_kernel<<<1, 1024, 0, st>>>(s_lcount.p, (int)nlist, s_lstart.p, item_list, item_q0, item_nq, s_plan_out.p);
+        pqtc::fill_pairs_kernel<<<grid1d(npairs, 256), 256, 0, st>>>(sp.probe_ids, sp.probe_dis, npairs, nprobe, metric, list_len.p,
+                                                                     s_lstart.p, s_lcount.p + nlist, s_pair_q.p, s_pair_base.p);
+        // pairs of lists owned by other shards leave holes at the end of the pair array: point them at no query
+        fltc::gather_split_queries_kernel<<<grid1d(npairs_pad * 32, 256), 256, 0, st>>>(sp.queries, s_pair_q.p, npairs, npairs_pad, dim,
+                                                                                     s_qhi.p, s_qlo.p);
+        row_norms_kernel<<<grid1d(nq * 32, 256), 256, 0, st>>>(sp.queries, nq, dim, s_qnorm.p);
+        CUtensorMap tx, thi, tlo;
+        KB2_REQUIRE(tc::make_tmap(&tx, vecs.p, npad, dim) && tc::make_tmap(&thi, s_qhi.p, npairs_pad, dim) &&
+                        tc::make_tmap(&tlo, s_qlo.p, npairs_pad, dim),
+                    KB2_INTERNAL_ERROR, "IVF_FLAT tensor-core engine: tensor map encoding failed");
+        fltc::Params fpar{};
+        fpar.metric = metric;
+        fpar.d = dim;
+        fpar.n_items = s_plan_out.p;
+        fpar.item_list = item_list;
+        fpar.item_q0 = item_q0;
+        fpar.item_nq = item_nq;
+        fpar.pair_q = s_pair_q.p;
+        fpar.qnorm2 = s_qnorm.p;
+        fpar.bound = s_bound.p;
+        fpar.list_off = list_off.p;
+        fpar.list_len = list_len.p;
+        fpar.xnorm2 = vnorm2.p;
+        fpar.bitset = sp.bitset;
+        fpar.rows = rows.p;
+        const uint32_t log_cap = (uint32_t)std::min<int64_t>(std::max<int64_t>(nq * 1024 / kNumSMs, 32768), 1 << 20);
+        s_log.ensure((size_t)kNumSMs * log_cap);
+        s_logcnt.ensure(kNumSMs + 8);
+        KB2_CUDA_CHECK(cudaMemsetAsync(s_logcnt.p, 0, (kNumSMs + 8) * 4, st));
+        fpar.log = s_log.p;
+        fpar.log_cnt = s_logcnt.p;
+        fpar.log_cap = log_cap;
+        fpar.counters = d_counter.p;
+        if (timing) KB2_CUDA_CHECK(cudaEventRecord(ev2, st));
+        if (metric == KB2_METRIC_L2)
+            fltc::ivfflat_tc_kernel<KB2_METRIC_L2><<<kNumSMs, fltc::THREADS, fltc::SMEM_BYTES, st>>>(tx, thi, tlo, fpar);
+        else
+            fltc::ivfflat_tc_kernel<KB2_METRIC_IP><<<kNumSMs, fltc::THREADS, fltc::SMEM_BYTES, st>>>(tx, thi, tlo, fpar);
+        if (timing) KB2_CUDA_CHECK(cudaEventRecord(ev3, st));
+        KB2_CUDA_CHECK(cudaGetLastError());
+        uint32_t* qflag = s_cand_cnt.p + nq;
+        fltc::scatter_kernel<<<dim3(16, kNumSMs), 256, 0, st>>>(s_log.p, s_logcnt.p, log_cap, s_cand.p, s_cand_cnt.p, kTcCandCap, qflag);
+        fltc::count_flags_kernel<<<grid1d(nq, 256), 256, 0, st>>>(qflag, nq, s_logcnt.p + kNumSMs, s_cand_cnt.p + 2 * nq);
+        last.launches += 9;
+        uint32_t* hflag = (uint32_t*)h_counter.p + 12;
+        KB2_CUDA_CHECK(cudaMemcpyAsync(hflag, s_cand_cnt.p + 2 * nq, 4, cudaMemcpyDeviceToHost, st));
+        KB2_CUDA_CHECK(cudaStreamSynchronize(st));
+        last.flagged = hflag[0];
+        return hflag[0] == 0;
+    }
+
+    // coarse quantizer for queries [q_lo, q_hi): top-nprobe centroids with exact dis0 (F/IndexIVF.cpp:336-342) into rows
+    // [q_lo, q_hi) of s_probe_ids / s_probe_dis
+    void
+    coarse_probes(const float* dq, int64_t q_lo, int64_t q_hi, int nprobe) {
+        const int64_t m = q_hi - q_lo;
+        if (m <= 0) return;
+        DensePlan pl = dense_candidates(*this, dq + q_lo * dim, m, centroids.p, cnorms.p, nlist, dim, metric, nprobe + 16, nullptr,
+                                        nullptr);
+        FinalizeParams fp{};
+        fp.partial = s_partial.p;
+        fp.partial_stride = pl.stride();
+        fp.n_partial = pl.used * pl.Ksel;
+        fp.k_sel = (int)std::min<int64_t>(std::min(pl.Ksel, nprobe + 16), nlist);
+        fp.k_out = nprobe;
+        fp.rerank = 1;
+        fp.raw = centroids.p;
+        fp.raw_by_pos = 1;
+        fp.queries = dq + q_lo * dim;
+        fp.d = dim;
+        fp.metric = metric;
+        fp.out_ids = s_probe_ids.p + q_lo * nprobe;
+        fp.out_dist = s_probe_dis.p + q_lo * nprobe;
+        launch_finalize(*this, fp, m);
     }
 
     // ---------------------------------------------------------------- Search (ivf.cc:887-1168)
@@ -1002,6 +1168,8 @@ struct IvfIndex : IndexBase {
         KB2_REQUIRE(refine_k >= 1.0, KB2_OUT_OF_RANGE_IN_JSON, "refine_k must be >= 1");
         const int k_base = use_refine ? (int)((double)k * refine_k) : k;  // K/IndexRefine.cpp:80-83
         KB2_REQUIRE(k > 0 && k_base <= kMaxK, KB2_INVALID_ARGS, "k (x refine_k) out of range (max 1024)");
+        const bool dist = distributed();
+        KB2_REQUIRE(!dist || (int64_t)shard_world * k <= kMaxSortEntries, KB2_INVALID_ARGS, "world * k too large for the merge");
 
         cudaStream_t st = stream;
         const float* dq = to_device(q, (size_t)nq * dim, s_q);
@@ -1016,27 +1184,21 @@ struct IvfIndex : IndexBase {
             d_dist = s_out_dist.p;
         }
 
-        // ---- coarse quantizer: top-nprobe centroids, exact dis0 (F/IndexIVF.cpp:336-342)
-        s_probe_ids.ensure((size_t)nq * nprobe);
-        s_probe_dis.ensure((size_t)nq * nprobe);
-        {
-            DensePlan pl = dense_candidates(*this, dq, nq, centroids.p, cnorms.p, nlist, dim, metric, nprobe + 16, nullptr,
-                                            nullptr);
-            FinalizeParams fp{};
-            fp.partial = s_partial.p;
-            fp.partial_stride = pl.stride();
-            fp.n_partial = pl.used * pl.Ksel;
-            fp.k_sel = (int)std::min<int64_t>(std::min(pl.Ksel, nprobe + 16), nlist);
-            fp.k_out = nprobe;
-            fp.rerank = 1;
-            fp.raw = centroids.p;
-            fp.raw_by_pos = 1;
-            fp.queries = dq;
-            fp.d = dim;
-            fp.metric = metric;
-            fp.out_ids = s_probe_ids.p;
-            fp.out_dist = s_probe_dis.p;
-            launch_finalize(*this, fp, nq);
+        // ---- coarse quantizer.  With a communicator every rank ranks the centroids for its slice of the batch only and the
+        //      probe lists are all-gathered (in place; slices padded to the same length).
+        const int64_t per = dist ? (nq + shard_world - 1) / shard_world : nq;
+        const int64_t nq_pad = dist ? per * shard_world : nq;
+        s_probe_ids.ensure((size_t)nq_pad * nprobe);
+        s_probe_dis.ensure((size_t)nq_pad * nprobe);
+        if (dist) {
+            const int64_t q_lo = std::min<int64_t>(nq, per * shard_rank), q_hi = std::min<int64_t>(nq, q_lo + per);
+            coarse_probes(dq, q_lo, q_hi, nprobe);
+            if (timing) KB2_CUDA_CHECK(cudaEventRecord(ev_c0, st));
+            comm->all_gather2(s_probe_ids.p + per * shard_rank * nprobe, s_probe_ids.p, (size_t)per * nprobe * 8,
+                              s_probe_dis.p + per * shard_rank * nprobe, s_probe_dis.p, (size_t)per * nprobe * 4, st);
+            if (timing) KB2_CUDA_CHECK(cudaEventRecord(ev_c1, st));
+        } else {
+            coarse_probes(dq, 0, nq, nprobe);
         }
 
         // ---- visiting order of the queries: sorted by nearest list, so that CTAs resident at the same
@@ -1096,6 +1258,7 @@ struct IvfIndex : IndexBase {
         int64_t fin_stride = (int64_t)nsplit * Ksel;
         int fin_n = nsplit * Ksel;
         const uint32_t *fin_counts = nullptr, *fin_flags = nullptr;
+        bool flat_tc = false;
         if (tc_engine) {
             search_tc(sp, nq, nprobe, Ksel, k_base, dbits != nullptr);
             fin_partial = s_cand.p;
@@ -1103,12 +1266,25 @@ struct IvfIndex : IndexBase {
             fin_n = kTcCandCap;
             fin_counts = s_cand_cnt.p;
             fin_flags = s_cand_cnt.p + nq;
+        } else if (use_flat_tc_engine(nq, nprobe, k_base) && search_flat_tc(sp, nq, nprobe, Ksel, k_base, dbits != nullptr)) {
+            flat_tc = true;
+            fin_partial = s_cand.p;
+            fin_stride = kTcCandCap;
+            fin_n = kTcCandCap;
+            fin_counts = s_cand_cnt.p;
         } else {
             launch_scan(sp, grid, Ksel, np_max, dbits != nullptr);
         }
         if (timing) KB2_CUDA_CHECK(cudaEventRecord(ev1, st));
 
-        // ---- finalize: merge CTA lists, optional exact refine, labels
+        // ---- finalize: merge CTA lists, optional exact refine, labels.  With a communicator the local top-k goes to a
+        //      staging buffer, ONE fused all-gather ships ids + distances of every shard, and the merge kernel writes the result.
+        if (dist) {
+            s_loc_ids.ensure((size_t)nq * k);
+            s_loc_dist.ensure((size_t)nq * k);
+            s_g_ids.ensure((size_t)shard_world * nq * k);
+            s_g_dist.ensure((size_t)shard_world * nq * k);
+        }
         {
             FinalizeParams fp{};
             fp.partial = fin_partial;
@@ -1116,19 +1292,26 @@ struct IvfIndex : IndexBase {
             fp.n_partial = fin_n;
             fp.counts = fin_counts;
             fp.count_flags = fin_flags;
-            fp.k_sel = k_base;
+            fp.k_sel = flat_tc ? k_base + 16 : k_base;   // tensor-core IVF_FLAT: 3xTF32 keys, exact re-rank of the k+16 best
             fp.k_out = k;
             fp.rows = rows.p;
             fp.labels = custom_labels ? labels.p : nullptr;
-            fp.rerank = use_refine ? 1 : 0;
+            fp.rerank = (use_refine || flat_tc) ? 1 : 0;
             fp.raw = vecs.p;
             fp.raw_by_pos = 1;
             fp.queries = dq;
             fp.d = dim;
             fp.metric = metric;
-            fp.out_ids = d_ids;
-            fp.out_dist = d_dist;
+            fp.out_ids = dist ? s_loc_ids.p : d_ids;
+            fp.out_dist = dist ? s_loc_dist.p : d_dist;
             launch_finalize(*this, fp, nq);
+        }
+        if (dist) {
+            if (timing) KB2_CUDA_CHECK(cudaEventRecord(ev_c2, st));
+            comm->all_gather2(s_loc_ids.p, s_g_ids.p, (size_t)nq * k * 8, s_loc_dist.p, s_g_dist.p, (size_t)nq * k * 4, st);
+            launch_merge_topk(metric, shard_world, nq, k, s_g_ids.p, s_g_dist.p, d_ids, d_dist, st);
+            if (timing) KB2_CUDA_CHECK(cudaEventRecord(ev_c3, st));
+            last.launches += 3;
         }
         unsigned long long* hc = (unsigned long long*)h_counter.p;
         KB2_CUDA_CHECK(cudaMemcpyAsync(hc, d_counter.p, 64, cudaMemcpyDeviceToHost, st));
@@ -1140,11 +1323,18 @@ struct IvfIndex : IndexBase {
         last.codes = (int64_t)scanned;
         last.code_bytes = (int64_t)scanned * (is_pq ? (int64_t)M : (int64_t)dim * 4);
         last.pairs = nq * nprobe;
-        last_engine = tc_engine ? 1 : 0;
+        last_engine = (tc_engine || flat_tc) ? 1 : 0;
         if (timing) {
             KB2_CUDA_CHECK(cudaEventElapsedTime(&last_stage_ms, ev0, ev1));
             last_kernel_ms = last_stage_ms;
-            if (tc_engine) KB2_CUDA_CHECK(cudaEventElapsedTime(&last_kernel_ms, ev2, ev3));
+            if (tc_engine || flat_tc) KB2_CUDA_CHECK(cudaEventElapsedTime(&last_kernel_ms, ev2, ev3));
+            last_comm_ms = 0.f;
+            if (dist) {
+                float a = 0.f, b = 0.f;
+                KB2_CUDA_CHECK(cudaEventElapsedTime(&a, ev_c0, ev_c1));
+                KB2_CUDA_CHECK(cudaEventElapsedTime(&b, ev_c2, ev_c3));
+                last_comm_ms = a + b;
+            }
         }
     }
 

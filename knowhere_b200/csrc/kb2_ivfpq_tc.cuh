@@ -47,21 +47,24 @@ namespace pqtc {
 
 constexpr int TM = 128;        // codes per tile (UMMA M)
 constexpr int NQT = 256;       // queries per item (UMMA N max)
-constexpr int KD = 128;        // dimensions (UMMA K total) — the engine is specialised to d=128, m=16, dsub=8
+constexpr int KD = 128;        // dimensions — the engine is specialised to d=128, m=16, dsub=8
+constexpr int KSTEPS = KD / 16 + 1;   // K = 144: the 9th K-step carries the admission test (row term / column threshold)
+constexpr int CHUNKS = 2 * KSTEPS;    // 16-byte chunks per operand row
+constexpr int GRP_BYTES = CHUNKS * 128;   // one 8-row group of an operand: 18 core matrices of 128 B (UMMA SBO)
 constexpr int THREADS = 544;          // warps 0-7 decoders (2 groups), 8-15 epilogue (2 groups), 16 MMA
 constexpr int GROUP_THREADS = 128;
 constexpr int MMA_WARP = 16;
-constexpr int TAB_BYTES = 65536, A_BYTES = 32768, B_BYTES = 65536;
-constexpr int META_BYTES = 4 * NQT * 4;   // h | (unused) | base | qidx
-constexpr int QREG = 1024;                // survivor-queue entries per region (two regions)
+constexpr int TAB_BYTES = 65536, A_BYTES = (TM / 8) * GRP_BYTES, B_BYTES = (NQT / 8) * GRP_BYTES;
+constexpr int META_BYTES = 3 * NQT * 4;   // h | base | qidx
 constexpr int OFF_TAB = 0;
 constexpr int OFF_A = TAB_BYTES;
 constexpr int OFF_B = OFF_A + 2 * A_BYTES;
 constexpr int OFF_META = OFF_B + B_BYTES;
-constexpr int OFF_QUEUE = OFF_META + 2 * META_BYTES;
-constexpr int OFF_BAR = OFF_QUEUE + 2 * QREG * 8;
+constexpr int OFF_BAR = OFF_META + 2 * META_BYTES;
 constexpr size_t SMEM_BYTES = OFF_BAR + 256 + 128 /*alignment slack*/;
+static_assert(SMEM_BYTES <= 227 * 1024, "filter kernel shared memory");
 constexpr float kErrCoef = 0.0085f;       // (2u + u^2) for bf16 operands + fp32 accumulation slack
+constexpr float kAccCoef = 4e-5f;         // fp32 accumulation of the K=144 contraction incl. the threshold terms (x (|h| + max|r|))
 
 struct Params {
     int metric;
@@ -77,10 +80,10 @@ struct Params {
     const int32_t* pair_q;         // [pairs] query index, grouped by list
     const float* pair_base;        // [pairs] key base: L2 |q-c|^2, IP -<q,c>
     // per-query bound from phase A
-    const uint64_t* bound_rows;    // [nq][bound_stride] sorted packed (key,pos) rows
-    int64_t bound_stride;
+    const float* bound;            // [nq] upper bound of the k_need-th best key (+inf: none -> the LUT kernel redoes the query)
     int k_need;
     float margin_coef;             // |alpha| * kErrCoef * Rmax  (multiplied by |q|)
+    float rmax;                    // max over the index of the row term |t1| / 2 (L2; 0 for IP)
     // index
     const int64_t* list_off;
     const int32_t* list_len;
@@ -130,13 +133,13 @@ bar_sync_epi() {
     asm volatile("bar.sync 1, 256;" ::: "memory");
 }
 // UMMA shared-memory descriptor, K-major, no swizzle: core matrix = 8 rows x 16 B (128 B contiguous);
-// LBO = distance between the two core matrices of one K=16 step (128 B), SBO = distance between 8-row groups (2048 B)
+// LBO = distance between the two core matrices of one K=16 step (128 B), SBO = distance between 8-row groups (GRP_BYTES)
 __device__ __forceinline__ uint64_t
 make_desc_ns(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
     d |= (uint64_t)(128 >> 4) << 16;
-    d |= (uint64_t)(2048 >> 4) << 32;
+    d |= (uint64_t)(GRP_BYTES >> 4) << 32;
     d |= (uint64_t)1 << 46;
     return d;
 }
@@ -155,6 +158,19 @@ mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint
         "}" ::"r"(d_tmem),
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+
+// x = hi + mid + lo with three bf16 terms (24 significant bits: exact for finite fp32 up to 2^-27 |x|); +-inf -> (+-inf, 0, 0)
+__device__ __forceinline__ void
+split3_bf16(float x, uint32_t& hi, uint32_t& mid, uint32_t& lo) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    hi = (uint32_t)__bfloat16_as_ushort(h);
+    if (!(fabsf(x) < INFINITY)) { mid = 0u; lo = 0u; return; }
+    const float r1 = x - __bfloat162float(h);
+    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(m);
+    mid = (uint32_t)__bfloat16_as_ushort(m);
+    lo = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(r2));
 }
 
 template <int METRIC>
@@ -216,14 +232,14 @@ ivfpq_tc_filter_kernel(Params p) {
         const int tid = dt & 127;      // code row inside the tile
         const uint4* tab = (const uint4*)(sm + OFF_TAB);
         // per-column thresholds of one item -> meta buffer (it & 1), one column per decoder thread; written one item
-        // AHEAD of its use so that the dependent global loads (pair -> bound row, norm) stay off the critical path
+        // AHEAD of its use so that the dependent global loads (pair -> bound, norm) stay off the critical path
         auto write_meta = [&](int item, int it) {
             const int par = it & 1;
             mbar_wait_g(bar_meta_free(par), (((uint32_t)it >> 1) & 1u) ^ 1u);
             const int q0 = p.item_q0[item];
             const int nqi = p.item_nq[item];
             float* m_h = (float*)(sm + OFF_META + par * META_BYTES);
-            float* m_base = m_h + 2 * NQT;
+            float* m_base = m_h + NQT;
             int* m_q = (int*)(m_base + NQT);
             const int j = dt;
             float h = -INFINITY, bs = 0.f;
@@ -231,14 +247,16 @@ ivfpq_tc_filter_kernel(Params p) {
             if (j < nqi) {
                 q = p.pair_q[q0 + j];
                 bs = p.pair_base[q0 + j];
-                const uint64_t e = p.bound_rows[(int64_t)q * p.bound_stride + p.k_need - 1];
-                if (e == kEmpty) {
+                const float bnd = p.bound[q];
+                if (!(bnd < INFINITY)) {
                     p.qflag[q] = 1u;   // no bound: the LUT kernel redoes this query
                     if (p.counters) atomicAdd(p.counters + 6, 1ull << 32);
                 } else {
-                    const float bnd = unpack_key(e);
+                    // pass  <=>  S' + h >= r  (S' bf16 contraction, r the row term); the margin covers the bf16 operand error,
+                    // the extra term the fp32 accumulation of the K=144 contraction that now carries h and r as well
                     const float margin = p.margin_coef * p.qnorm[q] * 1.01f + 1e-30f;
-                    h = (bnd + margin - bs) * inv_alpha;
+                    const float h0 = (bnd + margin - bs) * inv_alpha;
+                    h = h0 + kAccCoef * (fabsf(h0) + p.rmax) + 1e-30f;
                 }
             }
             m_h[j] = h;
@@ -259,17 +277,29 @@ ivfpq_tc_filter_kernel(Params p) {
             const int par = it & 1;
             const int t_first = (int)((dg - (int)(g0 & 1u)) & 1);   // this group's first tile of the item
             uint4 w_next = make_uint4(0, 0, 0, 0);
-            if (t_first < ntiles && off + (int64_t)t_first * TM + tid < p.npad)
+            float t_next = 0.f;
+            if (t_first < ntiles && off + (int64_t)t_first * TM + tid < p.npad) {
                 w_next = ldg_stream_u4(p.codes + off + (int64_t)t_first * TM + tid);
+                if (METRIC == KB2_METRIC_L2) t_next = __ldg(p.t1 + off + (int64_t)t_first * TM + tid);
+            }
             auto decode_tile = [&](int t) {
                 const uint32_t g = g0 + (uint32_t)t;      // g & 1 == dg
                 const uint4 w = w_next;
+                const float tv = t_next;
                 {
                     const int64_t pn = off + (int64_t)(t + 2) * TM + tid;
-                    if (t + 2 < ntiles && pn < p.npad) w_next = ldg_stream_u4(p.codes + pn);
+                    if (t + 2 < ntiles && pn < p.npad) {
+                        w_next = ldg_stream_u4(p.codes + pn);
+                        if (METRIC == KB2_METRIC_L2) t_next = __ldg(p.t1 + pn);
+                    }
                 }
+                // row term of the admission test, negated, as three bf16 terms; rows past the end of the list never pass
+                float r = INFINITY;
+                if (t * TM + tid < len) r = (METRIC == KB2_METRIC_L2) ? 0.5f * tv : 0.f;
+                uint32_t rh, rm, rl;
+                split3_bf16(-r, rh, rm, rl);
                 mbar_wait_g(bar_a_empty(dg), ((g >> 1) & 1u) ^ 1u);
-                unsigned char* A = sm + OFF_A + dg * A_BYTES + (tid >> 3) * 2048 + (tid & 7) * 16;
+                unsigned char* A = sm + OFF_A + dg * A_BYTES + (tid >> 3) * GRP_BYTES + (tid & 7) * 16;
                 const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
                 uint4 v[16];
 #pragma unroll
@@ -279,17 +309,22 @@ ivfpq_tc_filter_kernel(Params p) {
                 }
 #pragma unroll
                 for (int s = 0; s < 16; s++) *reinterpret_cast<uint4*>(A + ((s + tid) & 15) * 128) = v[s];
+                // chunk 16: [-r_hi, -r_mid, -r_lo, 1, 1, 1, 0, 0] (bf16 1.0 = 0x3F80); chunk 17: zeros
+                *reinterpret_cast<uint4*>(A + 16 * 128) = make_uint4(rh | (rm << 16), rl | (0x3F80u << 16), 0x3F803F80u, 0u);
+                *reinterpret_cast<uint4*>(A + 17 * 128) = make_uint4(0u, 0u, 0u, 0u);
                 tc::fence_proxy_async();
                 tc::mbar_arrive(bar_a_full(dg));
             };
             // the first tile of each group only needs a free A buffer: decode it while the tensor pipe still works on
             // the previous item, then stage the B operand (which must wait for that item's last MMA)
             if (t_first < ntiles) decode_tile(t_first);
-            // ---- B operand: the item's queries (bf16) gathered by index with cp.async, K-major no-swizzle layout
-            asm volatile("bar.sync 2, 256;" ::: "memory");          // meta[par] (query indices) written by all decoders
+            // ---- B operand: the item's queries (bf16) gathered by index with cp.async, K-major no-swizzle layout,
+            //      plus the threshold chunk [1, 1, 1, h_hi, h_mid, h_lo, 0, 0] of every column
+            asm volatile("bar.sync 2, 256;" ::: "memory");          // meta[par] (thresholds, query indices) written by all decoders
             mbar_wait_g(bar_b_free, ((uint32_t)it & 1u) ^ 1u);
             {
-                const int* m_q = (const int*)(sm + OFF_META + par * META_BYTES) + 3 * NQT;
+                const float* m_h = (const float*)(sm + OFF_META + par * META_BYTES);
+                const int* m_q = (const int*)(m_h + 2 * NQT);
                 const uint32_t Bs = base + OFF_B;
                 unsigned char* B = sm + OFF_B;
                 const int kc = tid >> 3;        // 16-byte chunk along K (0..15)
@@ -297,13 +332,20 @@ ivfpq_tc_filter_kernel(Params p) {
                 for (int blk = dg; blk < nmma / 8; blk += 2) {
                     const int row = blk * 8 + rsub;
                     const int q = m_q[row];
-                    const uint32_t dst = (uint32_t)(blk * 2048 + kc * 128 + rsub * 16);
+                    const uint32_t dst = (uint32_t)(blk * GRP_BYTES + kc * 128 + rsub * 16);
                     if (q >= 0) {
                         const void* src = reinterpret_cast<const uint4*>(p.qb16 + (int64_t)q * KD) + kc;
                         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(Bs + dst), "l"(src) : "memory");
                     } else {
                         *reinterpret_cast<uint4*>(B + dst) = make_uint4(0, 0, 0, 0);
                     }
+                }
+                if (dt < nmma) {   // one column per decoder thread
+                    uint32_t hh, hm, hl;
+                    split3_bf16(m_h[dt], hh, hm, hl);
+                    unsigned char* Bc = B + (dt >> 3) * GRP_BYTES + (dt & 7) * 16;
+                    *reinterpret_cast<uint4*>(Bc + 16 * 128) = make_uint4(0x3F803F80u, 0x3F80u | (hh << 16), hm | (hl << 16), 0u);
+                    *reinterpret_cast<uint4*>(Bc + 17 * 128) = make_uint4(0u, 0u, 0u, 0u);
                 }
                 asm volatile("cp.async.wait_all;" ::: "memory");
             }
@@ -336,7 +378,7 @@ ivfpq_tc_filter_kernel(Params p) {
                     const uint32_t b0 = base + OFF_B;
                     const uint32_t d = tmem_base + (uint32_t)buf * 256u;
 #pragma unroll
-                    for (int ks = 0; ks < KD / 16; ks++)
+                    for (int ks = 0; ks < KSTEPS; ks++)
                         mma_bf16(d, make_desc_ns(a0 + ks * 256), make_desc_ns(b0 + ks * 256), idesc, ks > 0 ? 1u : 0u);
                     tc::tc_commit(bar_a_empty(buf));
                     tc::tc_commit(bar_acc_full(buf));
@@ -348,19 +390,21 @@ ivfpq_tc_filter_kernel(Params p) {
         }
     } else {
         // =========================== epilogue: two groups of 4 warps, group e owns accumulator e (tiles g % 2 == e) ======
+        // The accumulator holds D = S' + h_col - r_row: a (code, query) pair survives iff D >= 0, i.e. iff its sign bit is
+        // clear.  "No survivor in these 32 columns" is an AND over the 32 words (LOP3 tree); survivors are rare (~0.1 %), so
+        // the exact mask is built only on a hit and the entries go straight to the group's survivor log in global memory
+        // (slot range reserved with one shared-memory atomic per warp and tile; plain stores, nothing waits for them).
         const int et = threadIdx.x - 256;        // 0..255
         const int eg = et >> 7;                  // group
         const int e = et & 127;                  // thread inside the group
         const int we = warp & 3;                 // TMEM lane quarter (== warp % 4)
         const int row = we * 32 + lane;          // code row inside the tile
-        uint64_t* my_q = (uint64_t*)(sm + OFF_QUEUE) + eg * QREG;
-        const uint32_t n_logs = 2u * gridDim.x;  // private logs; log n_logs is the shared one
+        const uint32_t n_logs = 2u * gridDim.x;  // private logs (log n_logs, the former shared one, stays empty)
         uint4* my_log = p.log + (size_t)(2 * blockIdx.x + eg) * p.log_cap;
-        uint4* shared_log = p.log + (size_t)n_logs * p.log_cap;
-        uint32_t log_off = 0;
+        uint32_t* my_cursor = qcnt + eg;
         bool log_over = false;
         unsigned long long n_codes = 0;
-        uint32_t g0 = 0, k_own = 0;
+        uint32_t g0 = 0;
         int it = 0;
 #define KB2_TMEM_LD32(V, TADDR)                                                                                          \
     asm volatile(                                                                                                        \
@@ -376,75 +420,69 @@ ivfpq_tc_filter_kernel(Params p) {
             const int l = p.item_list[item];
             const int nqi = p.item_nq[item];
             const int nmma = (nqi + 15) & ~15;
-            const int nch = (nmma + 31) >> 5;    // 32-column chunks (a 16-column tail reads columns whose h is -inf)
+            const int nch = (nmma + 31) >> 5;    // 32-column chunks; a 16-column tail reads 16 stale columns (masked below)
             const int len = p.list_len[l];
             const int64_t off = p.list_off[l];
             const int ntiles = (len + TM - 1) / TM;
             const int par = it & 1;
             mbar_wait_g(bar_meta_full(par), ((uint32_t)it >> 1) & 1u);
-            const float* m_h = (const float*)(sm + OFF_META + par * META_BYTES);
-            const float* m_base = m_h + 2 * NQT;
+            const float* m_base = (const float*)(sm + OFF_META + par * META_BYTES) + NQT;
             const int* m_q = (const int*)(m_base + NQT);
             if (et == 0) n_codes += (unsigned long long)len * (unsigned long long)nqi;
             const int t_first = (int)((eg - (int)(g0 & 1u)) & 1);
-            float t1_next = 0.f;
-            if (METRIC == KB2_METRIC_L2 && t_first * TM + row < len) t1_next = __ldg(p.t1 + off + t_first * TM + row);
-            for (int t = t_first; t < ntiles; t += 2, k_own++) {
+            const uint32_t tail_mask = (nmma & 31) ? 0x0000ffffu : 0xffffffffu;   // valid columns of the last chunk
+            for (int t = t_first; t < ntiles; t += 2) {
                 const uint32_t g = g0 + (uint32_t)t;   // g & 1 == eg
-                uint32_t* my_cnt = qcnt + eg * 2 + (k_own & 1u);
                 mbar_wait_g(bar_acc_full(eg), (g >> 1) & 1u);
                 tc::tc_fence_after();
                 const int rel = t * TM + row;
-                float r = INFINITY;
-                if (rel < len) r = (METRIC == KB2_METRIC_L2) ? 0.5f * t1_next : 0.f;
-                if (METRIC == KB2_METRIC_L2 && rel + 2 * TM < len) t1_next = __ldg(p.t1 + off + rel + 2 * TM);   // next own tile
                 const uint32_t taddr0 = tmem_base + ((uint32_t)(we * 32) << 16) + (uint32_t)(eg * 256);
                 uint32_t masks[8];
-                uint32_t va[32];
-                // pass  <=>  S' + h_col >= r_row
-                auto scan_chunk = [&](const uint32_t (&v)[32], int ci) -> uint32_t {
-                    const float4* h4 = reinterpret_cast<const float4*>(m_h + ci * 32);
-                    bool any = false;
+                uint32_t va[32], vb[32];
+                auto scan_chunk = [&](const uint32_t (&v)[32]) -> uint32_t {
+                    uint32_t a = v[0];
 #pragma unroll
-                    for (int u = 0; u < 8; u++) {
-                        const float4 hv = h4[u];
-                        any |= (__uint_as_float(v[4 * u + 0]) + hv.x >= r);
-                        any |= (__uint_as_float(v[4 * u + 1]) + hv.y >= r);
-                        any |= (__uint_as_float(v[4 * u + 2]) + hv.z >= r);
-                        any |= (__uint_as_float(v[4 * u + 3]) + hv.w >= r);
-                    }
+                    for (int u = 1; u < 32; u++) a &= v[u];
+                    if ((int32_t)a < 0) return 0u;   // all 32 sign bits set: nothing passes
                     uint32_t m = 0;
-                    if (any) {
 #pragma unroll
-                        for (int u = 0; u < 32; u++) m |= (__uint_as_float(v[u]) + m_h[ci * 32 + u] >= r) ? (1u << u) : 0u;
-                    }
+                    for (int u = 0; u < 32; u++) m |= ((~v[u]) >> 31) << u;
                     return m;
                 };
+                // software pipeline over the chunks: the TMEM load of chunk ci+1 is in flight while chunk ci is tested
+                KB2_TMEM_LD32(va, taddr0);
 #pragma unroll
                 for (int ci = 0; ci < 8; ci++) {
                     masks[ci] = 0;
                     if (ci < nch) {   // (the other epilogue group works on the other accumulator meanwhile)
-                        KB2_TMEM_LD32(va, taddr0 + (uint32_t)(ci * 32));
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        masks[ci] = scan_chunk(va, ci);
+                        if (ci + 1 < nch) {
+                            if (ci & 1) { KB2_TMEM_LD32(va, taddr0 + (uint32_t)((ci + 1) * 32)); }
+                            else { KB2_TMEM_LD32(vb, taddr0 + (uint32_t)((ci + 1) * 32)); }
+                        } else {
+                            // everything of this tile is in registers: hand the accumulator back before the last test
+                            tc::tc_fence_before();
+                            tc::mbar_arrive(bar_acc_empty(eg));
+                        }
+                        masks[ci] = (ci & 1) ? scan_chunk(vb) : scan_chunk(va);
+                        if (ci == nch - 1) masks[ci] &= tail_mask;
                     }
                 }
-                tc::tc_fence_before();
-                tc::mbar_arrive(bar_acc_empty(eg));
-                // ---- survivors of this thread's row: one slot reservation in the group's queue (and one in the shared
-                //      global log for what does not fit), then plain stores
+                // ---- survivors of this thread's row -> the group's log
                 uint32_t total = 0;
 #pragma unroll
                 for (int ci = 0; ci < 8; ci++) total += __popc(masks[ci]);
-                if (total) {
-                    const uint32_t slot = atomicAdd(my_cnt, total);
-                    const uint32_t n_in = slot < (uint32_t)QREG ? min(total, (uint32_t)QREG - slot) : 0u;
-                    uint32_t gslot = 0;
-                    if (n_in < total) {
-                        gslot = atomicAdd(p.log_cnt + n_logs, total - n_in);
-                        if (p.counters) atomicAdd(p.counters + 3, (unsigned long long)(total - n_in));
+                if (__any_sync(0xffffffffu, total != 0u)) {
+                    uint32_t incl = total;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t tv = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += tv;
                     }
-                    uint32_t i = 0;
+                    uint32_t wbase = 0;
+                    if (lane == 31) wbase = atomicAdd(my_cursor, incl);
+                    wbase = __shfl_sync(0xffffffffu, wbase, 31);
+                    uint32_t slot = wbase + incl - total;
 #pragma unroll
                     for (int ci = 0; ci < 8; ci++) {
                         uint32_t m = masks[ci];
@@ -452,59 +490,31 @@ ivfpq_tc_filter_kernel(Params p) {
                             const int u = __ffs(m) - 1;
                             m &= m - 1;
                             const int col = ci * 32 + u;
-                            if (i < n_in) {
-                                my_q[slot + i] = ((uint64_t)col << 32) | (uint32_t)rel;
+                            if (slot < p.log_cap) {
+                                uint4 o;
+                                o.x = (uint32_t)m_q[col];
+                                o.y = (uint32_t)(off + rel);
+                                o.z = __float_as_uint(m_base[col]);
+                                o.w = 0u;
+                                my_log[slot] = o;
                             } else {
-                                const uint32_t s2 = gslot + (i - n_in);
-                                if (s2 < p.shared_cap) {
-                                    uint4 o;
-                                    o.x = (uint32_t)m_q[col];
-                                    o.y = (uint32_t)(off + rel);
-                                    o.z = __float_as_uint(m_base[col]);
-                                    o.w = 0u;
-                                    shared_log[s2] = o;
-                                } else {
-                                    p.log_cnt[n_logs + 1] = 1u;
-                                }
+                                log_over = true;
                             }
-                            i++;
+                            slot++;
                         }
                     }
                 }
-                // ---- flush the group's queue to its survivor log (fire-and-forget stores)
-                if (eg == 0) asm volatile("bar.sync 3, 128;" ::: "memory"); else asm volatile("bar.sync 4, 128;" ::: "memory");
-                const uint32_t n_raw = *my_cnt;
-                const uint32_t n = min(n_raw, (uint32_t)QREG);
-                if (e == 0 && n_raw > (uint32_t)QREG) {   // diagnostics: overflowing tiles, their largest push count
-                    atomicAdd(p.log_cnt + n_logs + 2, 1u);
-                    atomicMax(p.log_cnt + n_logs + 3, n_raw);
-                }
-                if (log_off + n > p.log_cap) {
-                    log_over = true;
-                } else {
-                    for (uint32_t i = e; i < n; i += GROUP_THREADS) {
-                        const uint64_t ent = my_q[i];
-                        const int col = (int)(ent >> 32);
-                        uint4 o;
-                        o.x = (uint32_t)m_q[col];
-                        o.y = (uint32_t)(off + (int64_t)(uint32_t)ent);
-                        o.z = __float_as_uint(m_base[col]);
-                        o.w = 0u;
-                        my_log[log_off + i] = o;
-                    }
-                    log_off += n;
-                }
-                if (eg == 0) asm volatile("bar.sync 3, 128;" ::: "memory"); else asm volatile("bar.sync 4, 128;" ::: "memory");
-                if (e == 0) *my_cnt = 0;   // next used two own tiles later, i.e. after the next pair of barriers
             }
             tc::mbar_arrive(bar_meta_free(par));
             g0 += (uint32_t)ntiles;
         }
 #undef KB2_TMEM_LD32
+        if (log_over) p.log_cnt[n_logs + 1] = 1u;
+        if (eg == 0) asm volatile("bar.sync 3, 128;" ::: "memory"); else asm volatile("bar.sync 4, 128;" ::: "memory");
         if (e == 0) {
-            p.log_cnt[2 * blockIdx.x + eg] = log_off;
-            if (log_over) p.log_cnt[n_logs + 1] = 1u;
-            if (p.counters) atomicAdd(p.counters + 2, (unsigned long long)log_off);
+            const uint32_t n = min(*my_cursor, p.log_cap);
+            p.log_cnt[2 * blockIdx.x + eg] = n;
+            if (p.counters) atomicAdd(p.counters + 2, (unsigned long long)n);
         }
         if (et == 0 && p.counters) atomicAdd(p.counters, n_codes);
     }
@@ -546,8 +556,10 @@ plan_kernel(const int32_t* __restrict__ lcount, int nlist, int32_t* __restrict__
         if (l < nlist) {
             lstart[l] = ca + ex_a;
             if (nch > 0) {
-                // even chunks, multiples of 16 queries (the UMMA N granularity)
-                const int per = ((c + nch - 1) / nch + 15) & ~15;
+                // even chunks, multiples of 16 queries (the UMMA N granularity); full chunks when rounding would leave the
+                // last one empty (an item without queries would be an N = 0 MMA)
+                int per = ((c + nch - 1) / nch + 15) & ~15;
+                if ((nch - 1) * per >= c) per = NQT;
                 for (int ch = 0; ch < nch; ch++) {
                     const int i = cb + ex_b + ch;
                     item_list[i] = l;
@@ -642,10 +654,13 @@ scatter_survivors_kernel(const uint4* __restrict__ log, const uint32_t* __restri
 // grid = number of SMs, block = 256 (thread = code value j, its 16 sub-vectors live in registers).
 template <int METRIC>
 __global__ void __launch_bounds__(256, 1)
-lut_build_kernel(const float* __restrict__ queries, int64_t nq, const float* __restrict__ pqc, float* __restrict__ lut) {
+lut_build_kernel(const float* __restrict__ queries, int64_t nq, const int32_t* __restrict__ qlist, const uint32_t* __restrict__ qcount,
+                 const float* __restrict__ pqc, float* __restrict__ lut) {
+    // qlist != NULL: table i belongs to query qlist[i], i < *qcount (the queries this rank runs phase A for)
     __shared__ __align__(16) float s_q[2][KD];
     const int j = threadIdx.x;
     const float scale = (METRIC == KB2_METRIC_L2) ? -2.f : -1.f;
+    if (qlist) nq = (int64_t)*qcount;
     // thread j keeps the 16 sub-vectors c_pq[.][j] (128 floats) in registers for all the queries of this CTA
     float4 c[32];
 #pragma unroll
@@ -656,11 +671,12 @@ lut_build_kernel(const float* __restrict__ queries, int64_t nq, const float* __r
     }
     const int64_t per = (nq + gridDim.x - 1) / gridDim.x;
     const int64_t q_beg = (int64_t)blockIdx.x * per, q_end = min(nq, q_beg + per);
-    if (q_beg < q_end && threadIdx.x < KD) s_q[0][threadIdx.x] = queries[q_beg * KD + threadIdx.x];
+    auto qrow = [&](int64_t i) { return queries + (qlist ? (int64_t)qlist[i] : i) * KD; };
+    if (q_beg < q_end && threadIdx.x < KD) s_q[0][threadIdx.x] = qrow(q_beg)[threadIdx.x];
     __syncthreads();
     for (int64_t q = q_beg; q < q_end; q++) {
         const int cur = (int)((q - q_beg) & 1);
-        if (q + 1 < q_end && threadIdx.x < KD) s_q[cur ^ 1][threadIdx.x] = queries[(q + 1) * KD + threadIdx.x];
+        if (q + 1 < q_end && threadIdx.x < KD) s_q[cur ^ 1][threadIdx.x] = qrow(q + 1)[threadIdx.x];
         float* dst = lut + q * 4096 + j * 16;
 #pragma unroll
         for (int m4 = 0; m4 < 16; m4 += 4) {
@@ -681,25 +697,31 @@ lut_build_kernel(const float* __restrict__ queries, int64_t nq, const float* __r
     }
 }
 
-// exact fp32 keys of the survivors: the LUT kernel's own values in its own order (two interleaved accumulators over
-// the stored byte order; key = base + (acc0 + acc1)), so both engines produce bit-identical keys.
+// exact fp32 keys of the survivors: the LUT kernel's own values in its own order — every table entry is the 8-term fma
+// chain of <q_m, c_pq[m][code]> times the scale, rounded once (never contracted into the sum), and the 16 entries are
+// added into two interleaved accumulators over the stored byte order, key = base + (acc0 + acc1) — so both engines
+// produce bit-identical keys.  The entries are recomputed from the fp32 codebook (L1/L2 resident) instead of read from
+// a per-query table: no [nq][4096] table has to exist for the queries whose phase A ran on another rank.
 // grid = nq, block = 128.  Survivors above the bound become kEmpty.
 template <int METRIC>
 __global__ void __launch_bounds__(128)
-exact_eval_kernel(const float* __restrict__ lut, const uint64_t* __restrict__ bound_rows, int64_t bound_stride, int k_need,
+exact_eval_kernel(const float* __restrict__ queries, const float* __restrict__ pqc, const float* __restrict__ bound_of,
                   const uint4* __restrict__ codes, const float* __restrict__ t1, const uint8_t* __restrict__ bitset,
                   const int32_t* __restrict__ rows, uint64_t* __restrict__ cand, const uint32_t* __restrict__ cand_cnt, int cap,
                   uint32_t* __restrict__ qflag, const uint32_t* __restrict__ log_over) {
+    __shared__ __align__(16) float s_q[KD];
     const int64_t q = blockIdx.x;
     if (*log_over) {
         if (threadIdx.x == 0) qflag[q] = 1u;
         return;
     }
     if (qflag[q]) return;
-    const uint64_t be = bound_rows[q * bound_stride + k_need - 1];
-    const float bound = unpack_key(be);
     const uint32_t n = min(cand_cnt[q], (uint32_t)cap);
-    const float* lq = lut + q * 4096;
+    if (n == 0) return;
+    s_q[threadIdx.x] = queries[q * KD + threadIdx.x];
+    __syncthreads();
+    const float bound = bound_of[q];
+    const float scale = (METRIC == KB2_METRIC_L2) ? -2.f : -1.f;
     uint64_t* row = cand + q * cap;
     for (uint32_t i = threadIdx.x; i < n; i += 128) {
         const uint64_t ent = row[i];
@@ -711,14 +733,52 @@ exact_eval_kernel(const float* __restrict__ lut, const uint64_t* __restrict__ bo
 #pragma unroll
         for (int s = 0; s < 16; s++) {
             const uint32_t byte = (ww[s >> 2] >> (8 * (s & 3))) & 255u;
-            const float a = __ldg(lq + byte * 16 + ((pos + s) & 15u));
-            if (s & 1) acc1 += a; else acc0 += a;
+            const uint32_t m = (pos + s) & 15u;
+            const float4 c0 = __ldg(reinterpret_cast<const float4*>(pqc + ((size_t)m * 256 + byte) * 8));
+            const float4 c1 = __ldg(reinterpret_cast<const float4*>(pqc + ((size_t)m * 256 + byte) * 8) + 1);
+            const float4 qa = *reinterpret_cast<const float4*>(&s_q[m * 8]);
+            const float4 qb = *reinterpret_cast<const float4*>(&s_q[m * 8 + 4]);
+            float a = 0.f;
+            a = fmaf(qa.x, c0.x, a); a = fmaf(qa.y, c0.y, a); a = fmaf(qa.z, c0.z, a); a = fmaf(qa.w, c0.w, a);
+            a = fmaf(qb.x, c1.x, a); a = fmaf(qb.y, c1.y, a); a = fmaf(qb.z, c1.z, a); a = fmaf(qb.w, c1.w, a);
+            const float v = __fmul_rn(a, scale);
+            if (s & 1) acc1 = __fadd_rn(acc1, v); else acc0 = __fadd_rn(acc0, v);
         }
-        const float key = base + (acc0 + acc1);
+        const float key = __fadd_rn(base, __fadd_rn(acc0, acc1));
         bool keep = key <= bound;
         if (keep && bitset) keep = !bit_is_set(bitset, rows[pos]);
         row[i] = keep ? pack_kp(key, pos) : kEmpty;
     }
+}
+
+// queries whose nearest list is owned by this rank (list l lives on rank l % world) -> compact list: this rank runs their
+// phase A (one CTA; order is irrelevant)
+__global__ void __launch_bounds__(1024)
+compact_resp_kernel(const int64_t* __restrict__ probe_ids, int nprobe, int64_t nq, int world, int rank, int32_t* __restrict__ list,
+                    uint32_t* __restrict__ count) {
+    __shared__ uint32_t s_n;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for (int64_t q = threadIdx.x; q < nq; q += 1024) {
+        const int64_t l = probe_ids[q * nprobe];
+        if (l >= 0 && (int)(l % world) == rank) list[atomicAdd(&s_n, 1u)] = (int32_t)q;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *count = s_n;
+}
+__global__ void
+fill_f32_kernel(float* __restrict__ out, int64_t n, float v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = v;
+}
+// max |x[i]| (one atomicMax on the bit pattern of a non-negative float)
+__global__ void __launch_bounds__(256)
+max_abs_kernel(const float* __restrict__ x, int64_t n, uint32_t* __restrict__ out) {
+    float m = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
 }
 
 // flagged queries -> compact list (one CTA; order is irrelevant)
@@ -757,25 +817,30 @@ constexpr size_t BOUND_SMEM = 32768 + BOUND_KMAX * 4 + BOUND_BINS * 4 + 64;
 
 template <int METRIC>
 __global__ void __launch_bounds__(128)
-bound_kernel(const float* __restrict__ lut, const int64_t* __restrict__ probe_ids, const float* __restrict__ probe_dis,
+bound_kernel(const float* __restrict__ lut, const int32_t* __restrict__ qlist, const uint32_t* __restrict__ qcount, int64_t nq,
+             const int64_t* __restrict__ probe_ids, const float* __restrict__ probe_dis,
              int probe_stride, int p0_max, int min_codes, int k_need, const int64_t* __restrict__ list_off,
              const int32_t* __restrict__ list_len, const uint4* __restrict__ codes, const float* __restrict__ t1,
-             const uint8_t* __restrict__ bitset, const int32_t* __restrict__ rows, int K, uint64_t* __restrict__ out,
+             const uint8_t* __restrict__ bitset, const int32_t* __restrict__ rows, float* __restrict__ out,
              unsigned long long* __restrict__ counters) {
+    // work list: table i / query qlist[i] for i < *qcount (qlist == NULL: query i, i < nq); CTAs stride the list
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* s_lut = (float*)smem_raw;                              // [256][32]
     float* s_keys = (float*)(smem_raw + 32768);                   // [BOUND_KMAX]
     uint32_t* s_hist = (uint32_t*)(s_keys + BOUND_KMAX);          // [BOUND_BINS]
     float* s_red = (float*)(s_hist + BOUND_BINS);                 // [16]
-    const int64_t q = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if ((uint32_t)__cvta_generic_to_shared(smem_raw) != (uint32_t)KB2_SMEM_BASE) {
         if (threadIdx.x == 0 && counters) atomicExch(counters + 1, 0xBAD5ull);   // layout assumption violated: host raises an error
         return;
     }
+    const int64_t n_work = qlist ? (int64_t)*qcount : nq;
+    for (int64_t wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+    const int64_t q = qlist ? (int64_t)qlist[wi] : wi;
+    __syncthreads();   // the previous iteration's readers of the shared tables are done
     {
         // lut[q][j*16 + m] -> s_lut[j*32 + m] and s_lut[j*32 + 16 + m]
-        const float4* src = reinterpret_cast<const float4*>(lut + q * 4096);
+        const float4* src = reinterpret_cast<const float4*>(lut + wi * 4096);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const int idx = threadIdx.x + i * 128;       // float4 index: j = idx / 4, m4 = (idx % 4) * 4
@@ -882,7 +947,7 @@ bound_kernel(const float* __restrict__ lut, const int64_t* __restrict__ probe_id
     const uint32_t total = s_wsum[0] + s_wsum[1] + s_wsum[2] + s_wsum[3];
     const uint32_t need = (uint32_t)k_need;
     if (total < need || seen < 4 * k_need) {
-        if (threadIdx.x == 0) out[q * K + k_need - 1] = kEmpty;   // no (or only a loose) bound: the LUT kernel redoes the query
+        if (threadIdx.x == 0) out[q] = INFINITY;   // no (or only a loose) bound: the LUT kernel redoes the query
     } else if (before < need && before + tsum >= need) {
         uint32_t cum = before;
         int b = 0;
@@ -891,8 +956,9 @@ bound_kernel(const float* __restrict__ lut, const int64_t* __restrict__ probe_id
             if (cum < need) { cum += mine[bb]; b = bb; }
         }
         const float bound = (scale > 0.f) ? lo + ((float)(threadIdx.x * 8 + b) + 1.01f) / scale : hi;
-        out[q * K + k_need - 1] = pack_kp(fmaxf(bound, lo) + 4e-7f * fmaxf(fabsf(lo), fabsf(hi)), 0u);
+        out[q] = fmaxf(bound, lo) + 4e-7f * fmaxf(fabsf(lo), fabsf(hi));
     }
+    }   // work list
 }
 #undef KB2_BOUND_STEP
 

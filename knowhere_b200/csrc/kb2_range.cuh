@@ -338,44 +338,6 @@ range_search_index(IndexBase& ix, const float* queries, int64_t nq, float radius
     *out_dist = dist;
 }
 
-// ------------------------------------------------------------------------------------------
-// Merge of per-shard top-k lists after the all-gather: one CTA per query, rank by (key, id).
-// in: [world][nq][k]; out: [nq][k]
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-merge_topk_kernel(int metric, int world, int64_t nq, int k, const int64_t* __restrict__ in_ids,
-                  const float* __restrict__ in_dist, int64_t* __restrict__ out_ids, float* __restrict__ out_dist) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int n = world * k;
-    int64_t* s_id = (int64_t*)smem_raw;
-    float* s_key = (float*)(s_id + n);
-    const int64_t q = blockIdx.x;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int w = i / k, j = i % k;
-        const int64_t id = in_ids[((int64_t)w * nq + q) * k + j];
-        const float d = in_dist[((int64_t)w * nq + q) * k + j];
-        s_id[i] = id < 0 ? INT64_MAX : id;
-        s_key[i] = id < 0 ? INFINITY : (metric == KB2_METRIC_L2 ? d : -d);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const float ki = s_key[i];
-        const int64_t li = s_id[i];
-        int rank = 0;
-        for (int j = 0; j < n; j++) {
-            const float kj = s_key[j];
-            const int64_t lj = s_id[j];
-            rank += (kj < ki) || (kj == ki && (lj < li || (lj == li && j < i)));
-        }
-        if (rank < k) {
-            const bool empty = (li == INT64_MAX);
-            out_ids[q * k + rank] = empty ? -1 : li;
-            out_dist[q * k + rank] = empty ? (metric == KB2_METRIC_L2 ? FLT_MAX : -FLT_MAX)
-                                           : (metric == KB2_METRIC_L2 ? ki : -ki);
-        }
-    }
-}
-
 inline void
 merge_topk_device(int metric, int world, int64_t nq, int k, const int64_t* in_ids, const float* in_dist,
                   int64_t* out_ids, float* out_dist, cudaStream_t st) {
@@ -401,12 +363,7 @@ merge_topk_device(int metric, int world, int64_t nq, int k, const int64_t* in_id
         d_oids = b_oids.p;
         d_odist = b_odist.p;
     }
-    const size_t smem = (size_t)world * k * 12 + 16;
-    static PerDeviceOnce once;
-    once.run([] {
-        cudaFuncSetAttribute((const void*)merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
-    });
-    merge_topk_kernel<<<(unsigned)nq, 256, smem, st>>>(metric, world, nq, k, d_in_ids, d_in_dist, d_oids, d_odist);
+    launch_merge_topk(metric, world, nq, k, d_in_ids, d_in_dist, d_oids, d_odist, st);
     KB2_CUDA_CHECK(cudaGetLastError());
     if (!dev_out) {
         KB2_CUDA_CHECK(cudaMemcpyAsync(out_ids, d_oids, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));

@@ -314,3 +314,56 @@ def test_ivf_build_is_deterministic(kb):
         ix.train(xb)
         outs.append(ix.ivf_export_centroids(m))
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+def _with_env(name, value, fn):
+    import os
+    old = os.environ.get(name)
+    os.environ[name] = value
+    try:
+        return fn()
+    finally:
+        if old is None:
+            os.environ.pop(name, None)
+        else:
+            os.environ[name] = old
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+@pytest.mark.parametrize("d", [128, 96])
+def test_ivfflat_tc_engine_matches_scan_and_reference(kb, ref, metric, d):
+    """IVF_FLAT list-major tcgen05 engine (kb2_ivfflat_tc.cuh: 3xTF32 filter + exact fp32 re-rank) against the query-major
+    exact scan of the same index and against the reference's IndexIVFFlat: identical ids, distances to fp32 rounding."""
+    nb, nlist, nprobe, nq, k = 60000, 64, 16, 2000, 10
+    xb = datagen.clustered(nb, d, 42)
+    xq = datagen.clustered(nq, d, 43)
+    r = _mk_ref(ref, "IVF_FLAT", xb, metric, nlist)
+    ix = _import(kb, r, "IVF_FLAT", metric, xb)
+    ix.enable_kernel_timing(True)
+    a_ids, a_dis = _with_env("KB2_FLAT_ENGINE", "tc", lambda: ix.search(xq, k, {"nprobe": nprobe}))
+    assert ix.last_stage_info()["engine"] == "tc"
+    b_ids, b_dis = _with_env("KB2_FLAT_ENGINE", "scan", lambda: ix.search(xq, k, {"nprobe": nprobe}))
+    assert ix.last_stage_info()["engine"] == "scan"
+    assert_topk_parity(a_ids, a_dis, b_ids, b_dis, rtol=2e-6, atol=1e-5, what="IVF_FLAT tc vs scan", max_tie_rows=2)
+    I0, D0 = r.search(xq, k, nprobe)
+    assert_topk_parity(a_ids, a_dis, I0, D0, what="IVF_FLAT tc vs reference")
+    # with a bitset
+    mask = np.random.default_rng(1).random(nb) < 0.5
+    bits = np.packbits(mask, bitorder="little")
+    c_ids, c_dis = _with_env("KB2_FLAT_ENGINE", "tc", lambda: ix.search(xq, k, {"nprobe": nprobe}, bitset=bits))
+    d_ids, d_dis = _with_env("KB2_FLAT_ENGINE", "scan", lambda: ix.search(xq, k, {"nprobe": nprobe}, bitset=bits))
+    assert not mask[c_ids[c_ids >= 0]].any()
+    assert_topk_parity(c_ids, c_dis, d_ids, d_dis, rtol=2e-6, atol=1e-5, what="IVF_FLAT tc vs scan (bitset)", max_tie_rows=2)
+
+
+def test_ivfflat_tc_engine_small_lists_and_fallback(kb):
+    """lists shorter than k (no phase-A bound => every row survives => candidate rows overflow) must fall back to the exact
+    scan transparently; ragged tails (list length not a multiple of 128) are masked."""
+    nb, d, nlist, nq, k = 3000, 32, 256, 600, 10      # ~12 rows per list
+    xb = datagen.clustered(nb, d, 7)
+    xq = datagen.clustered(nq, d, 8)
+    ix = kb.Index("IVF_FLAT", "L2", d, {"nlist": nlist})
+    ix.build(xb)
+    a = _with_env("KB2_FLAT_ENGINE", "tc", lambda: ix.search(xq, k, {"nprobe": 64}))
+    b = _with_env("KB2_FLAT_ENGINE", "scan", lambda: ix.search(xq, k, {"nprobe": 64}))
+    assert_topk_parity(a[0], a[1], b[0], b[1], rtol=2e-6, atol=1e-5, what="IVF_FLAT tc small lists", max_tie_rows=2)
