@@ -96,6 +96,15 @@ int kb2_index_train(kb2_index_t h, const float* x, int64_t n);
  * labels continuing from Count(). */
 int kb2_index_add(kb2_index_t h, const float* x, int64_t n, const int64_t* ids);
 
+/* Typed variants: element type of x / queries.  The reference registers FLAT / IVF_* for fp16, bf16 and int8 through a
+ * wrapper that converts the dataset and every query batch to fp32 (index_factory.h:95-103,
+ * index_node_data_mock_wrapper.cc:24-60); these entry points do that conversion on the device.  Distances are fp32. */
+enum { KB2_DTYPE_F32 = 0, KB2_DTYPE_F16 = 1, KB2_DTYPE_BF16 = 2, KB2_DTYPE_INT8 = 3 };
+int kb2_index_train_typed(kb2_index_t h, const void* x, int dtype, int64_t n);
+int kb2_index_add_typed(kb2_index_t h, const void* x, int dtype, int64_t n, const int64_t* ids);
+int kb2_index_search_typed(kb2_index_t h, const void* queries, int dtype, int64_t nq, int k, const char* json,
+                           const uint8_t* bitset, int64_t bitset_nbits, int64_t* out_ids, float* out_dist);
+
 /* IndexNode::Search (index_node.h:164-166; ivf.cc:887-1168; flat.cc:75-152;
  * faiss_hnsw.cc:1344-1527).  json: search keys k is passed explicitly; nprobe, ef,
  * refine_k (ivf_config.h:33-45,97-128; base_hnsw_config.h:40-71).

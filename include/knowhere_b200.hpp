@@ -15,10 +15,12 @@
 // Every method is noexcept and returns Status / expected<> exactly like the reference facade
 // (src/index/index.cc:159-420 wraps node calls in GuardedCall, expected.h:408-430).
 #pragma once
+#include <algorithm>
 #include <cstring>
 #include <functional>
 #include <map>
 #include <memory>
+#include <set>
 #include <sstream>
 #include <string>
 #include <utility>
@@ -161,6 +163,8 @@ class DataSet {
     void SetLims(const size_t* p) { lims_ = p; }
     void SetIsOwner(bool o) { is_owner_ = o; }
     void SetOwnedTensor(bool o) { owned_tensor_ = o; }
+    void SetJsonInfo(std::string j) { json_info_ = std::move(j); }
+    const std::string& GetJsonInfo() const { return json_info_; }
     int64_t GetRows() const { return rows_; }
     int64_t GetDim() const { return dim_; }
     const void* GetTensor() const { return tensor_; }
@@ -174,6 +178,7 @@ class DataSet {
     const float* dist_ = nullptr;
     const size_t* lims_ = nullptr;
     bool is_owner_ = true, owned_tensor_ = false;
+    std::string json_info_;
 };
 using DataSetPtr = std::shared_ptr<DataSet>;
 
@@ -201,18 +206,49 @@ inline DataSetPtr GenIdsDataSet(int64_t rows, const int64_t* ids) {
 }
 
 // ------------------------------------------------------------------ BitsetView (bit set => filtered out)
+// include/knowhere/bitsetview.h:131-175: bit index = out_ids[internal_id + id_offset] when an id map is attached, else
+// internal_id + id_offset.  The GPU kernels take a plain bitmap over internal ids, so a view with an offset or an id map
+// is materialised once per call (as the in-tree GPU precedent does: src/index/gpu_cuvs/gpu_cuvs.h:139-156).
 class BitsetView {
  public:
     BitsetView() = default;
-    BitsetView(const uint8_t* data, size_t num_bits) : bits_(data), num_bits_(num_bits) {}
+    BitsetView(const uint8_t* data, size_t num_bits) : bits_(data), num_bits_(num_bits), vector_count_(num_bits) {}
     BitsetView(std::nullptr_t) {}
     bool empty() const { return num_bits_ == 0; }
-    size_t size() const { return num_bits_; }
+    size_t size() const { return vector_count_; }
+    size_t num_bits() const { return num_bits_; }
     const uint8_t* data() const { return bits_; }
-    bool test(int64_t i) const { return (bits_[i >> 3] >> (i & 7)) & 1; }
+    void set_vector_count(size_t n) { vector_count_ = n; }
+    void set_id_offset(size_t o) { id_offset_ = o; }
+    size_t id_offset() const { return id_offset_; }
+    void set_out_ids(const int64_t* out_ids, size_t count) { out_ids_ = out_ids; out_ids_count_ = count; }
+    bool has_out_ids() const { return out_ids_count_ != 0; }
+    bool is_plain() const { return id_offset_ == 0 && out_ids_count_ == 0; }
+    // true when backend (internal) id `index` is to be skipped
+    bool test(int64_t index) const {
+        if (index < 0) return true;
+        size_t out_id = (size_t)index + id_offset_;
+        if (has_out_ids()) {
+            if (out_id >= out_ids_count_) return true;
+            const int64_t mapped = out_ids_[out_id];
+            if (mapped < 0) return true;
+            out_id = (size_t)mapped;
+        }
+        if (out_id >= num_bits_) return true;
+        return (bits_[out_id >> 3] >> (out_id & 7)) & 1;
+    }
+    // plain bitmap over internal ids [0, n)
+    std::vector<uint8_t> materialize(size_t n) const {
+        std::vector<uint8_t> out((n + 7) / 8, 0);
+        for (size_t i = 0; i < n; i++)
+            if (test((int64_t)i)) out[i >> 3] |= (uint8_t)(1u << (i & 7));
+        return out;
+    }
  private:
     const uint8_t* bits_ = nullptr;
-    size_t num_bits_ = 0;
+    size_t num_bits_ = 0, vector_count_ = 0, id_offset_ = 0;
+    const int64_t* out_ids_ = nullptr;
+    size_t out_ids_count_ = 0;
 };
 
 // ------------------------------------------------------------------ BinarySet
@@ -234,6 +270,14 @@ struct fp32 {};  // data-type tag (include/knowhere/operands.h); this library se
 // ------------------------------------------------------------------ IndexNode over the C ABI
 class IndexNode {
  public:
+    // IndexNode::iterator (index_node.h:69-88): results in best-first order, one at a time
+    class iterator {
+     public:
+        virtual ~iterator() = default;
+        virtual expected<std::pair<int64_t, float>> Next() noexcept = 0;
+        virtual expected<bool> HasNext() noexcept = 0;
+    };
+    using IteratorPtr = std::shared_ptr<iterator>;
     virtual ~IndexNode() = default;
     virtual Status Train(const DataSetPtr ds, const Json& cfg) = 0;
     virtual Status Add(const DataSetPtr ds, const Json& cfg) = 0;
@@ -247,6 +291,9 @@ class IndexNode {
     virtual bool HasRawData(const std::string& metric_type) const = 0;
     virtual Status Serialize(BinarySet& bs) const = 0;
     virtual Status Deserialize(const BinarySet& bs, const Json& cfg) = 0;
+    virtual Status DeserializeFromFile(const std::string& filename, const Json& cfg) = 0;
+    virtual expected<DataSetPtr> GetIndexMeta(const Json& cfg) const = 0;
+    virtual expected<std::vector<IteratorPtr>> AnnIterator(const DataSetPtr ds, const Json& cfg, const BitsetView& bitset) const = 0;
     virtual int64_t Dim() const = 0;
     virtual int64_t Size() const = 0;
     virtual int64_t Count() const = 0;
@@ -283,6 +330,22 @@ class B200IndexNode : public IndexNode {
         if (!h_) return Status::index_not_trained;
         return (Status)kb2_index_add(h_, (const float*)ds->GetTensor(), ds->GetRows(), nullptr);
     }
+    // plain internal-id bitmap for the C ABI (a view with an id offset / id map is materialised)
+    struct PlainBits {
+        std::vector<uint8_t> store;
+        const uint8_t* data = nullptr;
+        int64_t nbits = 0;
+    };
+    PlainBits plain_bits(const BitsetView& bitset) const {
+        PlainBits p;
+        if (bitset.empty()) return p;
+        if (bitset.is_plain()) { p.data = bitset.data(); p.nbits = (int64_t)bitset.num_bits(); return p; }
+        const int64_t n = kb2_index_count(h_);
+        p.store = bitset.materialize((size_t)n);
+        p.data = p.store.data();
+        p.nbits = n;
+        return p;
+    }
     expected<DataSetPtr> Search(const DataSetPtr ds, const Json& cfg, const BitsetView& bitset) const override {
         if (!h_) return expected<DataSetPtr>::Err(Status::empty_index, "index not loaded");
         const int64_t nq = ds->GetRows();
@@ -290,8 +353,9 @@ class B200IndexNode : public IndexNode {
         if (k <= 0) return expected<DataSetPtr>::Err(Status::invalid_args, "k must be positive");
         auto ids = std::make_unique<int64_t[]>(nq * k);   // index.cc: ids/dist = new[rows*k] (ivf.cc:913-914)
         auto dis = std::make_unique<float[]>(nq * k);
-        int rc = kb2_index_search(h_, (const float*)ds->GetTensor(), nq, k, cfg.dump().c_str(), bitset.data(),
-                                  (int64_t)bitset.size(), ids.get(), dis.get());
+        const PlainBits pb = plain_bits(bitset);
+        int rc = kb2_index_search(h_, (const float*)ds->GetTensor(), nq, k, cfg.dump().c_str(), pb.data, pb.nbits, ids.get(),
+                                  dis.get());
         if (rc) return expected<DataSetPtr>::Err((Status)rc, kb2_last_error());
         return GenResultDataSet(nq, k, ids.release(), dis.release());
     }
@@ -302,9 +366,10 @@ class B200IndexNode : public IndexNode {
         int64_t *lims = nullptr, *ids = nullptr;
         float* dist = nullptr;
         const bool has_rf = cfg.contains(meta::RANGE_FILTER);
+        const PlainBits pb = plain_bits(bitset);
         int rc = kb2_index_range_search(h_, (const float*)ds->GetTensor(), nq, cfg.get<float>(meta::RADIUS, 0.f),
                                         cfg.get<float>(meta::RANGE_FILTER, 0.f), has_rf ? 1 : 0, cfg.dump().c_str(),
-                                        bitset.data(), (int64_t)bitset.size(), &lims, &ids, &dist);
+                                        pb.data, pb.nbits, &lims, &ids, &dist);
         if (rc) return expected<DataSetPtr>::Err((Status)rc, kb2_last_error());
         const int64_t tot = lims[nq];
         auto o_l = new size_t[nq + 1];
@@ -327,10 +392,14 @@ class B200IndexNode : public IndexNode {
         return r;
     }
     bool HasRawData(const std::string&) const override { return h_ && kb2_index_has_raw_data(h_); }
+    // Serialize: ONE binary named after the index type holding the faiss fourcc stream, exactly what the reference's
+    // nodes write (flat.cc:323-343, ivf.cc:1717-1741, faiss_hnsw.cc:188-217), so the reference's CPU nodes can load it.
+    // Indexes the wire format cannot express (COSINE keeps unit vectors only; custom ids) fall back to the "KB2I" container.
     Status Serialize(BinarySet& bs) const override {
         if (!h_) return Status::empty_index;
         uint8_t* p = nullptr; size_t n = 0;
-        int rc = kb2_index_serialize(h_, &p, &n);
+        int rc = kb2_index_serialize_faiss(h_, &p, &n);
+        if (rc == KB2_NOT_IMPLEMENTED) rc = kb2_index_serialize(h_, &p, &n);
         if (rc) return (Status)rc;
         std::shared_ptr<uint8_t[]> buf(new uint8_t[n]);
         memcpy(buf.get(), p, n);
@@ -342,7 +411,91 @@ class B200IndexNode : public IndexNode {
         auto b = bs.GetByName(type_);
         if (!b) return Status::invalid_binary_set;
         if (h_) { kb2_index_destroy(h_); h_ = nullptr; }
-        return (Status)kb2_index_deserialize(b->data.get(), (size_t)b->size, device_, &h_);
+        uint32_t magic = 0;
+        if (b->size >= 4) memcpy(&magic, b->data.get(), 4);
+        if (magic == 0x4932424b) return (Status)kb2_index_deserialize(b->data.get(), (size_t)b->size, device_, &h_);
+        return (Status)kb2_index_deserialize_faiss(b->data.get(), (size_t)b->size, 0, device_, &h_);
+    }
+    Status DeserializeFromFile(const std::string& filename, const Json&) override {
+        if (h_) { kb2_index_destroy(h_); h_ = nullptr; }
+        return (Status)kb2_index_deserialize_from_file(filename.c_str(), device_, &h_);
+    }
+    expected<DataSetPtr> GetIndexMeta(const Json&) const override {
+        if (!h_) return expected<DataSetPtr>::Err(Status::empty_index, "index not loaded");
+        char buf[1024];
+        int rc = kb2_index_get_meta(h_, buf, sizeof(buf));
+        if (rc) return expected<DataSetPtr>::Err((Status)rc, kb2_last_error());
+        auto r = std::make_shared<DataSet>();
+        r->SetJsonInfo(buf);
+        return r;
+    }
+    // AnnIterator (index.h:187-195, index_node.h:1099-1200): one iterator per query yielding (id, distance) best-first.
+    // Backed by batched searches with a doubling k (64, 128, ... up to the selection kernels' 1008): results are a
+    // deterministic prefix-stable order, so the iterator resumes where the previous batch ended.
+    class SearchIterator : public iterator {
+     public:
+        SearchIterator(const B200IndexNode* node, std::vector<float> q, Json cfg, PlainBits bits)
+            : node_(node), q_(std::move(q)), cfg_(std::move(cfg)), bits_(std::move(bits)) {
+            if (!bits_.store.empty()) bits_.data = bits_.store.data();
+        }
+        expected<bool> HasNext() noexcept override {
+            skip_seen();
+            if (pos_ < ids_.size() && ids_[pos_] >= 0) return true;
+            if (exhausted_) return false;
+            refill();
+            skip_seen();
+            return pos_ < ids_.size() && ids_[pos_] >= 0;
+        }
+        expected<std::pair<int64_t, float>> Next() noexcept override {
+            auto h = HasNext();
+            if (!h.has_value() || !h.value()) return expected<std::pair<int64_t, float>>::Err(Status::invalid_args, "iterator exhausted");
+            auto r = std::make_pair(ids_[pos_], dis_[pos_]);
+            seen_.insert(ids_[pos_]);
+            pos_++;
+            return r;
+        }
+     private:
+        // a larger batch repeats the earlier results (exactly for FLAT / IVF; a graph search with a larger beam may reorder a
+        // few of them): never hand out an id twice
+        void skip_seen() {
+            while (pos_ < ids_.size() && ids_[pos_] >= 0 && seen_.count(ids_[pos_])) pos_++;
+        }
+        void refill() {
+            pos_ = 0;
+            const int64_t count = kb2_index_count(node_->h_);
+            const int next_k = (int)std::min<int64_t>(std::min<int64_t>(count, 1008), k_ == 0 ? 64 : 2 * (int64_t)k_);
+            if (next_k <= k_) { exhausted_ = true; return; }
+            k_ = next_k;
+            ids_.assign(k_, -1);
+            dis_.assign(k_, 0.f);
+            Json c = cfg_;
+            c[indexparam::EF] = std::max<int>(k_, c.get<int>(indexparam::EF, 0));
+            int rc = kb2_index_search(node_->h_, q_.data(), 1, k_, c.dump().c_str(), bits_.data, bits_.nbits, ids_.data(), dis_.data());
+            if (rc) { exhausted_ = true; ids_.clear(); return; }
+            if (k_ >= std::min<int64_t>(count, 1008)) exhausted_ = true;   // nothing larger can be asked for
+        }
+        const B200IndexNode* node_;
+        std::vector<float> q_;
+        Json cfg_;
+        PlainBits bits_;
+        std::vector<int64_t> ids_;
+        std::vector<float> dis_;
+        std::set<int64_t> seen_;
+        size_t pos_ = 0;
+        int k_ = 0;
+        bool exhausted_ = false;
+    };
+    expected<std::vector<IteratorPtr>> AnnIterator(const DataSetPtr ds, const Json& cfg, const BitsetView& bitset) const override {
+        if (!h_) return expected<std::vector<IteratorPtr>>::Err(Status::empty_index, "index not loaded");
+        const int64_t nq = ds->GetRows(), d = ds->GetDim();
+        std::vector<IteratorPtr> out;
+        for (int64_t i = 0; i < nq; i++) {
+            const float* q = (const float*)ds->GetTensor() + i * d;
+            PlainBits pb = plain_bits(bitset);
+            if (pb.store.empty() && pb.data) { pb.store.assign(pb.data, pb.data + (pb.nbits + 7) / 8); }   // own a copy: the view may die
+            out.push_back(std::make_shared<SearchIterator>(this, std::vector<float>(q, q + d), cfg, std::move(pb)));
+        }
+        return out;
     }
     int64_t Dim() const override { return h_ ? kb2_index_dim(h_) : 0; }
     int64_t Size() const override { return h_ ? kb2_index_size_bytes(h_) : 0; }
@@ -377,6 +530,13 @@ class Index {
     bool HasRawData(const std::string& m) const noexcept { return node->HasRawData(m); }
     Status Serialize(BinarySet& bs) const noexcept { return guard([&] { return node->Serialize(bs); }); }
     Status Deserialize(const BinarySet& bs, const Json& cfg = {}) noexcept { return guard([&] { return node->Deserialize(bs, cfg); }); }
+    Status DeserializeFromFile(const std::string& f, const Json& cfg = {}) noexcept { return guard([&] { return node->DeserializeFromFile(f, cfg); }); }
+    expected<DataSetPtr> GetIndexMeta(const Json& cfg = {}) const noexcept {
+        try { return node->GetIndexMeta(cfg); } catch (const std::exception& e) { return expected<DataSetPtr>::Err(Status::internal_error, e.what()); }
+    }
+    expected<std::vector<IndexNode::IteratorPtr>> AnnIterator(const DataSetPtr ds, const Json& cfg, const BitsetView& bs, void* = nullptr) const noexcept {
+        try { return node->AnnIterator(ds, cfg, bs); } catch (const std::exception& e) { return expected<std::vector<IndexNode::IteratorPtr>>::Err(Status::internal_error, e.what()); }
+    }
     int64_t Dim() const noexcept { return node->Dim(); }
     int64_t Size() const noexcept { return node->Size(); }
     int64_t Count() const noexcept { return node->Count(); }

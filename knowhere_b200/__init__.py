@@ -49,6 +49,9 @@ def _declare(L):
     L.kb2_index_set_stream.argtypes = [vp, vp]
     L.kb2_index_set_shard.argtypes = [vp, i32, i32]
     L.kb2_index_train.argtypes = [vp, vp, i64]
+    L.kb2_index_train_typed.argtypes = [vp, vp, i32, i64]
+    L.kb2_index_add_typed.argtypes = [vp, vp, i32, i64, vp]
+    L.kb2_index_search_typed.argtypes = [vp, vp, i32, i64, i32, c.c_char_p, vp, i64, vp, vp]
     L.kb2_index_add.argtypes = [vp, vp, i64, vp]
     L.kb2_index_search.argtypes = [vp, vp, i64, i32, c.c_char_p, vp, i64, vp, vp]
     L.kb2_index_range_search.argtypes = [vp, vp, i64, f32, f32, i32, c.c_char_p, vp, i64,
@@ -124,6 +127,15 @@ def _is_torch(a):
     return hasattr(a, "data_ptr")
 
 
+def _dtype_code(a):
+    """KB2_DTYPE_* of a numpy array / torch tensor (fp32 0, fp16 1, bf16 2, int8 3)"""
+    name = str(a.dtype).replace("torch.", "")
+    code = {"float32": 0, "float16": 1, "bfloat16": 2, "int8": 3}.get(name)
+    if code is None:
+        raise TypeError(f"unsupported element type {a.dtype}")
+    return code
+
+
 def _cfg(cfg):
     return json.dumps(cfg or {}).encode()
 
@@ -161,10 +173,10 @@ class Index:
 
     # -- Build = Train + Add (index_node.h:100-104)
     def train(self, x):
-        _check(self.L.kb2_index_train(self.h, _ptr(x), x.shape[0]))
+        _check(self.L.kb2_index_train_typed(self.h, _ptr(x), _dtype_code(x), x.shape[0]))
 
     def add(self, x, ids=None):
-        _check(self.L.kb2_index_add(self.h, _ptr(x), x.shape[0], _ptr(ids)))
+        _check(self.L.kb2_index_add_typed(self.h, _ptr(x), _dtype_code(x), x.shape[0], _ptr(ids)))
 
     def build(self, x, ids=None):
         self.train(x)
@@ -194,8 +206,8 @@ class Index:
             ids = np.empty((nq, k), np.int64)
             dist = np.empty((nq, k), np.float32)
         nbits = 0 if bitset is None else (bitset.numel() if _is_torch(bitset) else bitset.size) * 8
-        _check(self.L.kb2_index_search(self.h, _ptr(q), nq, k, _cfg(config), _ptr(bitset), nbits, _ptr(ids),
-                                       _ptr(dist)))
+        _check(self.L.kb2_index_search_typed(self.h, _ptr(q), _dtype_code(q), nq, k, _cfg(config), _ptr(bitset), nbits,
+                                             _ptr(ids), _ptr(dist)))
         return ids, dist
 
     def range_search(self, q, radius, range_filter=None, config=None, bitset=None):

@@ -13,8 +13,59 @@
 #include <vector>
 
 #include "kb2_flat.cuh"
+#include "kb2_gemm_tc.cuh"
 
 namespace kb2 {
+
+#ifndef KB2_DEFAULT_GEMM_MODE
+#define KB2_DEFAULT_GEMM_MODE 1
+#endif
+// 0 = fp32 CUDA-core contraction, 1 = tcgen05 (3xTF32) contraction.  KB2_GEMM=fp32|tc overrides.
+inline int
+gemm_mode() {
+    static int mode = [] {
+        const char* e = getenv("KB2_GEMM");
+        if (e && strcmp(e, "fp32") == 0) return 0;
+        if (e && strcmp(e, "tc") == 0) return 1;
+        return KB2_DEFAULT_GEMM_MODE;
+    }();
+    return mode;
+}
+
+// keys[nq][ldk] <- contraction of Q[nq][d] with X[cols][d]; returns true if the tensor-core path ran
+inline bool
+launch_gemm_keys(cudaStream_t st, int mode, int metric, const float* Q, const float* X, const float* qn,
+                 const float* xn, int nq, int cols, int d, float* keys, int64_t ldk, const uint8_t* bitset,
+                 const int32_t* rows, int64_t row_base) {
+    if (mode == 1 && (ldk & 3) == 0) {
+        CUtensorMap tq, tx;
+        if (tc::make_tmap(&tq, Q, nq, d) && tc::make_tmap(&tx, X, cols, d)) {
+            static PerDeviceOnce once;
+            once.run([] {
+                cudaFuncSetAttribute((const void*)tc::gemm_keys_tc_kernel<KB2_METRIC_L2>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
+                cudaFuncSetAttribute((const void*)tc::gemm_keys_tc_kernel<KB2_METRIC_IP>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
+            });
+            dim3 g((unsigned)((cols + tc::BN - 1) / tc::BN), (unsigned)((nq + tc::BM - 1) / tc::BM));
+            if (metric == KB2_METRIC_L2)
+                tc::gemm_keys_tc_kernel<KB2_METRIC_L2><<<g, tc::THREADS, tc::SMEM_BYTES, st>>>(tq, tx, qn, xn, nq, cols, d, keys,
+                                                                                           ldk, bitset, rows, row_base);
+            else
+                tc::gemm_keys_tc_kernel<KB2_METRIC_IP><<<g, tc::THREADS, tc::SMEM_BYTES, st>>>(tq, tx, qn, xn, nq, cols, d, keys,
+                                                                                           ldk, bitset, rows, row_base);
+            return true;
+        }
+    }
+    dim3 g((unsigned)((cols + GK_BN - 1) / GK_BN), (unsigned)((nq + GK_BM - 1) / GK_BM));
+    if (metric == KB2_METRIC_L2)
+        gemm_keys_kernel<KB2_METRIC_L2><<<g, 256, 0, st>>>(Q, X, qn, xn, nq, cols, d, keys, ldk, bitset, rows, row_base);
+    else
+        gemm_keys_kernel<KB2_METRIC_IP><<<g, 256, 0, st>>>(Q, X, qn, xn, nq, cols, d, keys, ldk, bitset, rows, row_base);
+    return false;
+}
+
+
 
 // ---------------------------------------------------------------- small kernels
 __global__ void
@@ -291,20 +342,19 @@ assign_nearest(const float* x, int64_t n, int d, const float* cent, int k, int m
     row_norms_kernel<<<grid1d((int64_t)k * 32, 256), 256, 0, st>>>(cent, k, d, sc.cn.p);
     int64_t chunk = std::max<int64_t>(128, std::min<int64_t>(n, (int64_t)(64ll << 20) / std::max(k, 1)));
     chunk = std::min<int64_t>(chunk, 1 << 20);
-    sc.keys.ensure((size_t)chunk * k);
+    // wide codebooks (IVF coarse quantizers): the tcgen05 3xTF32 contraction (keys to ~5e-6 relative; the reference's own
+    // add()/k-means assignment goes through BLAS sgemm, F/utils/distances.cpp:400-520).  Narrow ones (PQ sub-quantizers,
+    // k = 256, d = 2..8) stay on the fp32 CUDA-core kernel.
+    const int mode = (k >= 512 && (d & 3) == 0 && n >= 1024) ? gemm_mode() : 0;
+    const int64_t ldk = (k + 3) & ~3;
+    sc.keys.ensure((size_t)chunk * ldk);
     sc.xn.ensure((size_t)chunk);
     for (int64_t i0 = 0; i0 < n; i0 += chunk) {
         const int64_t m = std::min(chunk, n - i0);
         const float* xc = x + i0 * d;
         row_norms_kernel<<<grid1d(m * 32, 256), 256, 0, st>>>(xc, m, d, sc.xn.p);
-        dim3 g((k + GK_BN - 1) / GK_BN, (unsigned)((m + GK_BM - 1) / GK_BM));
-        if (metric == KB2_METRIC_L2)
-            gemm_keys_kernel<KB2_METRIC_L2><<<g, 256, 0, st>>>(xc, cent, sc.xn.p, sc.cn.p, (int)m, k, d, sc.keys.p, k,
-                                                               nullptr, nullptr, 0);
-        else
-            gemm_keys_kernel<KB2_METRIC_IP><<<g, 256, 0, st>>>(xc, cent, sc.xn.p, sc.cn.p, (int)m, k, d, sc.keys.p, k,
-                                                               nullptr, nullptr, 0);
-        argmin_rows_kernel<<<grid1d(m * 32, 256), 256, 0, st>>>(sc.keys.p, k, m, k, assign + i0,
+        launch_gemm_keys(st, mode, metric, xc, cent, sc.xn.p, sc.cn.p, (int)m, k, d, sc.keys.p, ldk, nullptr, nullptr, 0);
+        argmin_rows_kernel<<<grid1d(m * 32, 256), 256, 0, st>>>(sc.keys.p, ldk, m, k, assign + i0,
                                                                out_val ? out_val + i0 : nullptr);
     }
     KB2_CUDA_CHECK(cudaGetLastError());

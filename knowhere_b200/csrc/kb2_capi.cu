@@ -1,6 +1,9 @@
 // kb2_capi.cu — the extern "C" boundary declared in include/knowhere_b200.h.
 // Everything behind it is CUDA; there is no CPU fallback: without a usable sm_100 device every
 // entry point fails with KB2_CUDA_RUNTIME_ERROR.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include <atomic>
 #include <cstring>
 #include <memory>
@@ -209,33 +212,78 @@ kb2_index_set_shard(kb2_index_t h, int rank, int world) {
     });
 }
 
+namespace {
+// element types of the reference's data-type registrations: fp16 / bf16 / int8 indexes are "mock" wrappers that convert the
+// whole dataset and every query batch to fp32 (include/knowhere/index/index_factory.h:95-103,
+// src/index/index_node_data_mock_wrapper.cc:24-60); here the widening runs on the device
+__global__ void
+widen_kernel(const void* __restrict__ src, int dtype, int64_t n, float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v;
+    if (dtype == KB2_DTYPE_F16) v = __half2float(((const __half*)src)[i]);
+    else if (dtype == KB2_DTYPE_BF16) v = __bfloat162float(((const __nv_bfloat16*)src)[i]);
+    else v = (float)((const int8_t*)src)[i];
+    out[i] = v;
+}
+// device fp32 view of `count` elements of type dtype (host or device source); valid until the next typed call on the handle
+const float*
+widen_to_f32(IndexBase* ix, const void* x, int dtype, int64_t count) {
+    if (dtype == KB2_DTYPE_F32) return (const float*)x;
+    KB2_REQUIRE(dtype == KB2_DTYPE_F16 || dtype == KB2_DTYPE_BF16 || dtype == KB2_DTYPE_INT8, KB2_INVALID_ARGS, "unknown data type");
+    if (count <= 0 || !x) return nullptr;
+    const size_t esz = dtype == KB2_DTYPE_INT8 ? 1 : 2;
+    const void* dsrc = x;
+    if (!is_device_ptr(x)) {
+        ix->s_typed_raw.ensure((size_t)count * esz);
+        KB2_CUDA_CHECK(cudaMemcpyAsync(ix->s_typed_raw.p, x, (size_t)count * esz, cudaMemcpyHostToDevice, ix->stream));
+        ix->last.h2d += (int64_t)count * (int64_t)esz;
+        dsrc = ix->s_typed_raw.p;
+    }
+    ix->s_typed_f32.ensure((size_t)count);
+    widen_kernel<<<grid1d(count, 256), 256, 0, ix->stream>>>(dsrc, dtype, count, ix->s_typed_f32.p);
+    KB2_CUDA_CHECK(cudaGetLastError());
+    return ix->s_typed_f32.p;
+}
+}  // namespace
+
 int
-kb2_index_train(kb2_index_t h, const float* x, int64_t n) {
+kb2_index_train_typed(kb2_index_t h, const void* x, int dtype, int64_t n) {
     return guarded([&] {
         IndexBase* ix = ix_of(h);
         std::lock_guard<std::mutex> lk(ix->mu);
         KB2_CUDA_CHECK(cudaSetDevice(ix->device));
         KB2_REQUIRE(x != nullptr || n == 0, KB2_INVALID_ARGS, "null training data");
         ix->wait_caller_work();
-        ix->train(ix->cosine ? ix->normalized(x, n) : x, n);
+        const float* xf = widen_to_f32(ix, x, dtype, n * ix->dim);
+        ix->train(ix->cosine ? ix->normalized(xf, n) : xf, n);
     });
+}
+int
+kb2_index_train(kb2_index_t h, const float* x, int64_t n) {
+    return kb2_index_train_typed(h, x, KB2_DTYPE_F32, n);
 }
 
 int
-kb2_index_add(kb2_index_t h, const float* x, int64_t n, const int64_t* ids) {
+kb2_index_add_typed(kb2_index_t h, const void* x, int dtype, int64_t n, const int64_t* ids) {
     return guarded([&] {
         IndexBase* ix = ix_of(h);
         std::lock_guard<std::mutex> lk(ix->mu);
         KB2_CUDA_CHECK(cudaSetDevice(ix->device));
         KB2_REQUIRE(x != nullptr || n == 0, KB2_INVALID_ARGS, "null data");
         ix->wait_caller_work();
-        ix->add(ix->cosine ? ix->normalized(x, n) : x, n, ids);
+        const float* xf = widen_to_f32(ix, x, dtype, n * ix->dim);
+        ix->add(ix->cosine ? ix->normalized(xf, n) : xf, n, ids);
     });
+}
+int
+kb2_index_add(kb2_index_t h, const float* x, int64_t n, const int64_t* ids) {
+    return kb2_index_add_typed(h, x, KB2_DTYPE_F32, n, ids);
 }
 
 int
-kb2_index_search(kb2_index_t h, const float* queries, int64_t nq, int k, const char* json, const uint8_t* bitset,
-                 int64_t bitset_nbits, int64_t* out_ids, float* out_dist) {
+kb2_index_search_typed(kb2_index_t h, const void* queries, int dtype, int64_t nq, int k, const char* json, const uint8_t* bitset,
+                       int64_t bitset_nbits, int64_t* out_ids, float* out_dist) {
     return guarded([&] {
         IndexBase* ix = ix_of(h);
         std::lock_guard<std::mutex> lk(ix->mu);
@@ -249,8 +297,14 @@ kb2_index_search(kb2_index_t h, const float* queries, int64_t nq, int k, const c
         KB2_REQUIRE(cfg.ok, KB2_INVALID_PARAM_IN_JSON, "malformed json");
         ix->last = Counters{};
         ix->wait_caller_work();
-        ix->search(ix->cosine ? ix->normalized(queries, nq) : queries, nq, k, cfg, bitset, bitset_nbits, out_ids, out_dist);
+        const float* qf = widen_to_f32(ix, queries, dtype, nq * ix->dim);
+        ix->search(ix->cosine ? ix->normalized(qf, nq) : qf, nq, k, cfg, bitset, bitset_nbits, out_ids, out_dist);
     });
+}
+int
+kb2_index_search(kb2_index_t h, const float* queries, int64_t nq, int k, const char* json, const uint8_t* bitset,
+                 int64_t bitset_nbits, int64_t* out_ids, float* out_dist) {
+    return kb2_index_search_typed(h, queries, KB2_DTYPE_F32, nq, k, json, bitset, bitset_nbits, out_ids, out_dist);
 }
 
 int

@@ -27,9 +27,6 @@ constexpr int kMaxDynSmem = 227 * 1024;
 #ifndef KB2_DEFAULT_SCAN_NT
 #define KB2_DEFAULT_SCAN_NT 256
 #endif
-#ifndef KB2_DEFAULT_GEMM_MODE
-#define KB2_DEFAULT_GEMM_MODE 1
-#endif
 
 inline void
 init_kernel_attributes() {
@@ -70,59 +67,16 @@ init_kernel_attributes() {
         set((const void*)ivfpq_scan_generic_kernel<KB2_METRIC_IP>);
         set((const void*)ivfflat_scan_kernel<KB2_METRIC_L2>);
         set((const void*)ivfflat_scan_kernel<KB2_METRIC_IP>);
-        set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_L2>);
-        set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_IP>);
+        set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_L2, 1, 8>);
+        set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_IP, 1, 8>);
+        set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_L2, 3, 2>);
+        set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_IP, 3, 2>);
         set((const void*)pqtc::bound_kernel<KB2_METRIC_L2>);
         set((const void*)pqtc::bound_kernel<KB2_METRIC_IP>);
         set((const void*)fltc::ivfflat_tc_kernel<KB2_METRIC_L2>);
         set((const void*)fltc::ivfflat_tc_kernel<KB2_METRIC_IP>);
         cudaGetLastError();
     });
-}
-
-// 0 = fp32 CUDA-core contraction, 1 = tcgen05 (3xTF32) contraction.  KB2_GEMM=fp32|tc overrides.
-inline int
-gemm_mode() {
-    static int mode = [] {
-        const char* e = getenv("KB2_GEMM");
-        if (e && strcmp(e, "fp32") == 0) return 0;
-        if (e && strcmp(e, "tc") == 0) return 1;
-        return KB2_DEFAULT_GEMM_MODE;
-    }();
-    return mode;
-}
-
-// keys[nq][ldk] <- contraction of Q[nq][d] with X[cols][d]; returns true if the tensor-core path ran
-inline bool
-launch_gemm_keys(cudaStream_t st, int mode, int metric, const float* Q, const float* X, const float* qn,
-                 const float* xn, int nq, int cols, int d, float* keys, int64_t ldk, const uint8_t* bitset,
-                 const int32_t* rows, int64_t row_base) {
-    if (mode == 1 && (ldk & 3) == 0) {
-        CUtensorMap tq, tx;
-        if (tc::make_tmap(&tq, Q, nq, d) && tc::make_tmap(&tx, X, cols, d)) {
-            static PerDeviceOnce once;
-            once.run([] {
-                cudaFuncSetAttribute((const void*)tc::gemm_keys_tc_kernel<KB2_METRIC_L2>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
-                cudaFuncSetAttribute((const void*)tc::gemm_keys_tc_kernel<KB2_METRIC_IP>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
-            });
-            dim3 g((unsigned)((cols + tc::BN - 1) / tc::BN), (unsigned)((nq + tc::BM - 1) / tc::BM));
-            if (metric == KB2_METRIC_L2)
-                tc::gemm_keys_tc_kernel<KB2_METRIC_L2><<<g, tc::THREADS, tc::SMEM_BYTES, st>>>(tq, tx, qn, xn, nq, cols, d, keys,
-                                                                                           ldk, bitset, rows, row_base);
-            else
-                tc::gemm_keys_tc_kernel<KB2_METRIC_IP><<<g, tc::THREADS, tc::SMEM_BYTES, st>>>(tq, tx, qn, xn, nq, cols, d, keys,
-                                                                                           ldk, bitset, rows, row_base);
-            return true;
-        }
-    }
-    dim3 g((unsigned)((cols + GK_BN - 1) / GK_BN), (unsigned)((nq + GK_BM - 1) / GK_BM));
-    if (metric == KB2_METRIC_L2)
-        gemm_keys_kernel<KB2_METRIC_L2><<<g, 256, 0, st>>>(Q, X, qn, xn, nq, cols, d, keys, ldk, bitset, rows, row_base);
-    else
-        gemm_keys_kernel<KB2_METRIC_IP><<<g, 256, 0, st>>>(Q, X, qn, xn, nq, cols, d, keys, ldk, bitset, rows, row_base);
-    return false;
 }
 
 struct Counters {
@@ -174,7 +128,8 @@ struct IndexBase {
     DevBuf<uint64_t> s_partial, s_partial2;
     DevBuf<int64_t> s_out_ids, s_probe_ids;
     DevBuf<uint8_t> s_bitset;
-    DevBuf<float> s_cos_in, s_cos_out;
+    DevBuf<float> s_cos_in, s_cos_out, s_typed_f32;
+    DevBuf<uint8_t> s_typed_raw;
 
     // L2-normalised device copy of n rows (COSINE)
     const float*
@@ -289,7 +244,7 @@ struct DensePlan {
 
 inline DensePlan
 dense_candidates(IndexBase& ix, const float* Q, int64_t nq, const float* X, const float* xn, int64_t n, int d,
-                 int metric, int k_need, const uint8_t* bitset, const int32_t* rows) {
+                 int metric, int k_need, const uint8_t* bitset, const int32_t* rows, int64_t bit_offset = 0) {
     cudaStream_t st = ix.stream;
     DensePlan pl;
     pl.Ksel = next_pow2(std::max(32, k_need));
@@ -322,7 +277,7 @@ dense_candidates(IndexBase& ix, const float* Q, int64_t nq, const float* X, cons
             pl.used = 1;
         }
         launch_gemm_keys(st, gemm_mode(), metric, Q, X + c0 * d, ix.s_qn.p, xn + c0, (int)nq, (int)cols, d, ix.s_keys.p, ldk,
-                         bitset, rows, c0);
+                         bitset, rows, c0 + bit_offset);
         const int per_slice = (int)(((cols + nsplit - 1) / nsplit + 31) / 32 * 32);
         const size_t hist_smem = (size_t)per_slice * 4 + 4160;
         if (pl.Ksel >= 64 && hist_smem <= (size_t)kMaxDynSmem) {
@@ -359,6 +314,9 @@ struct FlatIndex : IndexBase {
     size_t n_used = 0, norms_used = 0, labels_used = 0;
     bool custom_labels = false;
     int64_t n_global_added = 0;  // rows offered to add() over all calls (for sharding)
+    int n_add_calls = 0;
+    int64_t shard_lo = 0;        // first global row of this shard's slice (single add() call)
+    int64_t bitset_rows() const override { return shard_world > 1 ? n_global_added : count(); }
 
     void train(const float*, int64_t) override {}
     bool is_trained() const override { return true; }
@@ -377,6 +335,7 @@ struct FlatIndex : IndexBase {
         }
         const int64_t m = hi - lo;
         const int64_t first_label = n_global_added + lo;
+        if (n_add_calls++ == 0) shard_lo = lo;
         const bool need_labels = custom_labels || ids != nullptr || shard_world > 1;
         if (need_labels && !custom_labels) {
             // materialise identity labels for what is already stored
@@ -431,8 +390,12 @@ struct FlatIndex : IndexBase {
             d_dist = s_out_dist.p;
         }
         if (timing) KB2_CUDA_CHECK(cudaEventRecord(ev0, stream));
-        // bitset indexes internal rows == labels when labels are the identity (like BitsetView over segment offsets)
-        DensePlan pl = dense_candidates(*this, dq, nq, base.p, norms.p, n, dim, metric, k + 16, dbits, nullptr);
+        // bitset indexes internal rows == labels when labels are the identity (like BitsetView over segment offsets);
+        // a shard holds the contiguous slice [shard_lo, shard_lo + n) of ONE add() call, so bit = shard_lo + local row
+        KB2_REQUIRE(!(dbits && shard_world > 1 && n_add_calls > 1), KB2_NOT_IMPLEMENTED,
+                    "FLAT shard: bitset after several add() calls");
+        DensePlan pl = dense_candidates(*this, dq, nq, base.p, norms.p, n, dim, metric, k + 16, dbits, nullptr,
+                                        shard_world > 1 ? shard_lo : 0);
         if (timing) KB2_CUDA_CHECK(cudaEventRecord(ev1, stream));
         FinalizeParams fp{};
         fp.partial = s_partial.p;
@@ -803,7 +766,7 @@ struct IvfIndex : IndexBase {
     }
 
     // ---------------------------------------------------------------- list-major tensor-core engine (kb2_ivfpq_tc.cuh)
-    static constexpr int kTcCandCap = 1024;     // survivor slots per query (overflow -> LUT kernel redoes the query)
+    static constexpr int kTcCandCap = 2048;     // survivor slots per query (overflow -> LUT kernel redoes the query)
     DevBuf<uint16_t> tc_pqc16, s_qb16;
     DevBuf<float> tc_maxn2, s_qnorm, s_pair_base, s_lut, s_bound;
     DevBuf<int32_t> s_lcount, s_lstart, s_items, s_pair_q, s_plan_out, s_flaglist, s_resp;
@@ -816,9 +779,13 @@ struct IvfIndex : IndexBase {
     DevBuf<int64_t> s_loc_ids, s_g_ids;
     DevBuf<float> s_loc_dist, s_g_dist;
 
+    DevBuf<uint8_t> tc_codes_plain;   // un-rotated code bytes for the geometries whose decode assembles 16-byte chunks from several sub-quantizers
+    // engine instances: <G=1, dsub=8> (m16 d128: C3) and <G=3, dsub=2> (m48 d96: C5)
+    bool tc_geom_18() const { return G == 1 && M == 16 && dsub == 8; }
+    bool tc_geom_32() const { return G == 3 && M == 48 && dsub == 2; }
     bool
     use_tc_engine(int64_t nq, int nprobe, int Ksel) const {
-        if (!is_pq || G != 1 || M != 16 || dsub != 8 || dim != 128) return false;
+        if (!is_pq || !(tc_geom_18() || tc_geom_32())) return false;
         const char* e = getenv("KB2_PQ_ENGINE");
         if (e && !strcmp(e, "lut")) return false;
         if (nprobe < 8 || Ksel > kTcCandCap / 2) return false;
@@ -832,19 +799,24 @@ struct IvfIndex : IndexBase {
         cudaStream_t st = stream;
         const bool dist = distributed();
         if (!tc_ready) {
-            tc_pqc16.alloc_exact((size_t)16 * 256 * 8);
-            tc_maxn2.alloc_exact(20);
-            KB2_CUDA_CHECK(cudaMemsetAsync(tc_maxn2.p + 16, 0, 16, st));
-            pqtc::prepare_tables_kernel<<<16, 256, 0, st>>>(pqc.p, (__nv_bfloat16*)tc_pqc16.p, tc_maxn2.p);
+            tc_pqc16.alloc_exact((size_t)M * 256 * dsub);
+            tc_maxn2.alloc_exact(M + 4);
+            KB2_CUDA_CHECK(cudaMemsetAsync(tc_maxn2.p + M, 0, 16, st));
+            pqtc::prepare_tables_kernel<<<M, 256, 0, st>>>(pqc.p, dsub, (__nv_bfloat16*)tc_pqc16.p, tc_maxn2.p);
             if (metric == KB2_METRIC_L2 && npad > 0)
-                pqtc::max_abs_kernel<<<kNumSMs * 2, 256, 0, st>>>(t1.p, npad, (uint32_t*)(tc_maxn2.p + 16));
-            float h[20];
-            KB2_CUDA_CHECK(cudaMemcpyAsync(h, tc_maxn2.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+                pqtc::max_abs_kernel<<<kNumSMs * 2, 256, 0, st>>>(t1.p, npad, (uint32_t*)(tc_maxn2.p + M));
+            if (dsub < 8) {
+                tc_codes_plain.alloc_exact((size_t)G * npad * 16);
+                pqtc::unrotate_codes_kernel<<<grid1d((int64_t)G * npad * 16, 256), 256, 0, st>>>(codes.p, (int64_t)G * npad, npad,
+                                                                                            tc_codes_plain.p);
+            }
+            std::vector<float> h(M + 4);
+            KB2_CUDA_CHECK(cudaMemcpyAsync(h.data(), tc_maxn2.p, (M + 4) * 4, cudaMemcpyDeviceToHost, st));
             KB2_CUDA_CHECK(cudaStreamSynchronize(st));
             double acc = 0;
-            for (int i = 0; i < 16; i++) acc += h[i];
+            for (int i = 0; i < M; i++) acc += h[i];
             tc_rmax = (float)std::sqrt(acc) * 1.0001f;
-            tc_rowmax = 0.5f * h[16] * 1.0001f;   // max |t1| / 2: the largest row term of the admission test
+            tc_rowmax = 0.5f * h[M] * 1.0001f;   // max |t1| / 2: the largest row term of the admission test
             tc_ready = true;
         }
         const int64_t npairs = nq * nprobe;
@@ -867,6 +839,7 @@ struct IvfIndex : IndexBase {
         const int p0 = std::max(1, std::min((e_p0 ? atoi(e_p0) : 8) * std::max(1, shard_world), nprobe));   // at most this many lists
         const int a_codes = e_ac ? atoi(e_ac) : 3000;                                                        // ... until this many codes
         s_bound.ensure((size_t)nq);
+        if (tc_geom_18()) {
         s_lut.ensure((size_t)nq * 4096);
         const int32_t* qlist = nullptr;
         const uint32_t* qcount = nullptr;
@@ -899,6 +872,23 @@ struct IvfIndex : IndexBase {
             KB2_CUDA_CHECK(cudaGetLastError());
             last.launches += 2;
         }
+        } else {
+            // other geometries: the query-major LUT kernel over the first probes gives the exact k_base-th best key of those
+            // lists (any subset of the codes yields a valid bound)
+            int64_t avg_len = std::max<int64_t>(1, n_total / std::max<int64_t>(1, nlist));
+            const int pA = (int)std::min<int64_t>(nprobe, std::max<int64_t>(2, (a_codes + avg_len - 1) / avg_len + 1) * std::max(1, shard_world));
+            IvfScanParams a = sp;
+            a.nprobe = pA;
+            a.probe_stride = nprobe;
+            a.nsplit = 1;
+            a.partial = s_partial2.p;
+            a.partial_stride = 0;
+            a.counters = d_counter.p + 4;
+            a.qperm = nullptr;
+            launch_scan(a, (unsigned)nq, Ksel, pA, has_bits);
+            fltc::extract_bound_kernel<<<grid1d(nq, 256), 256, 0, st>>>(s_partial2.p, Ksel, k_base, nq, s_bound.p);
+            last.launches += 1;
+        }
         if (dist) comm->all_reduce_min_f32(s_bound.p, s_bound.p, (size_t)nq, st);
         mark("phaseA");
         // ---- plan: pairs grouped by list, work items
@@ -909,7 +899,7 @@ struct IvfIndex : IndexBase {
         s_plan_out.ensure(4);
         s_pair_q.ensure((size_t)npairs);
         s_pair_base.ensure((size_t)npairs);
-        s_qb16.ensure((size_t)nq * 128);
+        s_qb16.ensure((size_t)nq * dim);
         s_qnorm.ensure((size_t)nq);
         s_cand.ensure((size_t)nq * kTcCandCap);
         s_cand_cnt.ensure((size_t)2 * nq);
@@ -922,7 +912,7 @@ struct IvfIndex : IndexBase {
         pqtc::plan_kernel<<<1, 1024, 0, st>>>(s_lcount.p, (int)nlist, s_lstart.p, item_list, item_q0, item_nq, s_plan_out.p);
         pqtc::fill_pairs_kernel<<<grid1d(npairs, 256), 256, 0, st>>>(sp.probe_ids, sp.probe_dis, npairs, nprobe, metric, list_len.p,
                                                                      s_lstart.p, s_lcount.p + nlist, s_pair_q.p, s_pair_base.p);
-        pqtc::prepare_queries_kernel<<<grid1d(nq * 32, 256), 256, 0, st>>>(sp.queries, nq, (__nv_bfloat16*)s_qb16.p, s_qnorm.p);
+        pqtc::prepare_queries_kernel<<<grid1d(nq * 32, 256), 256, 0, st>>>(sp.queries, nq, dim, (__nv_bfloat16*)s_qb16.p, s_qnorm.p);
         mark("plan");
         // ---- tensor-core filter + exact re-evaluation of the survivors
         pqtc::Params tp{};
@@ -945,6 +935,7 @@ struct IvfIndex : IndexBase {
         tp.list_off = list_off.p;
         tp.list_len = list_len.p;
         tp.codes = (const uint4*)codes.p;
+        tp.codes_plain = (const uint4*)tc_codes_plain.p;
         tp.npad = npad;
         tp.t1 = t1.p;
         tp.pqc = pqc.p;
@@ -963,24 +954,30 @@ struct IvfIndex : IndexBase {
         tp.qflag = s_cand_cnt.p + nq;
         tp.counters = d_counter.p;
         if (timing) KB2_CUDA_CHECK(cudaEventRecord(ev2, st));
-        if (metric == KB2_METRIC_L2)
-            pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_L2><<<kNumSMs, pqtc::THREADS, pqtc::SMEM_BYTES, st>>>(tp);
-        else
-            pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_IP><<<kNumSMs, pqtc::THREADS, pqtc::SMEM_BYTES, st>>>(tp);
+#define KB2_TC_LAUNCH(GG, DD)                                                                                                         \
+    if (metric == KB2_METRIC_L2)                                                                                                     \
+        pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_L2, GG, DD><<<kNumSMs, pqtc::THREADS, pqtc::TcCfg<GG, DD>::SMEM_BYTES, st>>>(tp);    \
+    else                                                                                                                             \
+        pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_IP, GG, DD><<<kNumSMs, pqtc::THREADS, pqtc::TcCfg<GG, DD>::SMEM_BYTES, st>>>(tp);
+        if (tc_geom_18()) { KB2_TC_LAUNCH(1, 8) } else { KB2_TC_LAUNCH(3, 2) }
+#undef KB2_TC_LAUNCH
         if (timing) KB2_CUDA_CHECK(cudaEventRecord(ev3, st));
         KB2_CUDA_CHECK(cudaGetLastError());
         mark("tc_filter");
         // ---- survivors: group by query, exact fp32 keys (bit-identical to the LUT engine's)
         pqtc::scatter_survivors_kernel<<<dim3(16, n_logs + 1), 256, 0, st>>>(s_log.p, s_logcnt.p, log_cap, log_cap, s_cand.p, s_cand_cnt.p,
                                                                          kTcCandCap, tp.qflag, d_counter.p);
-        if (metric == KB2_METRIC_L2)
-            pqtc::exact_eval_kernel<KB2_METRIC_L2><<<(unsigned)nq, 128, 0, st>>>(
-                sp.queries, pqc.p, s_bound.p, (const uint4*)codes.p, t1.p, sp.bitset, rows.p, s_cand.p, s_cand_cnt.p, kTcCandCap,
-                tp.qflag, s_logcnt.p + n_logs + 1);
-        else
-            pqtc::exact_eval_kernel<KB2_METRIC_IP><<<(unsigned)nq, 128, 0, st>>>(
-                sp.queries, pqc.p, s_bound.p, (const uint4*)codes.p, t1.p, sp.bitset, rows.p, s_cand.p, s_cand_cnt.p, kTcCandCap,
-                tp.qflag, s_logcnt.p + n_logs + 1);
+#define KB2_TC_EVAL(MM, GG, DD)                                                                                                      \
+    pqtc::exact_eval_kernel<MM, GG, DD><<<(unsigned)nq, 128, 0, st>>>(sp.queries, pqc.p, eval_lut, s_bound.p, (const uint4*)codes.p, npad, t1.p,  \
+                                                                      sp.bitset, rows.p, s_cand.p, s_cand_cnt.p, kTcCandCap, tp.qflag,  \
+                                                                      s_logcnt.p + n_logs + 1);
+        const float* eval_lut = (tc_geom_18() && !dist) ? s_lut.p : nullptr;   // tables of the whole batch exist only without a communicator
+        if (tc_geom_18()) {
+            if (metric == KB2_METRIC_L2) { KB2_TC_EVAL(KB2_METRIC_L2, 1, 8) } else { KB2_TC_EVAL(KB2_METRIC_IP, 1, 8) }
+        } else {
+            if (metric == KB2_METRIC_L2) { KB2_TC_EVAL(KB2_METRIC_L2, 3, 2) } else { KB2_TC_EVAL(KB2_METRIC_IP, 3, 2) }
+        }
+#undef KB2_TC_EVAL
         KB2_CUDA_CHECK(cudaGetLastError());
         last.launches += 7;
         mark("scatter+eval");

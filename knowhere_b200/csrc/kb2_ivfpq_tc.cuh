@@ -47,24 +47,34 @@ namespace pqtc {
 
 constexpr int TM = 128;        // codes per tile (UMMA M)
 constexpr int NQT = 256;       // queries per item (UMMA N max)
-constexpr int KD = 128;        // dimensions — the engine is specialised to d=128, m=16, dsub=8
-constexpr int KSTEPS = KD / 16 + 1;   // K = 144: the 9th K-step carries the admission test (row term / column threshold)
-constexpr int CHUNKS = 2 * KSTEPS;    // 16-byte chunks per operand row
-constexpr int GRP_BYTES = CHUNKS * 128;   // one 8-row group of an operand: 18 core matrices of 128 B (UMMA SBO)
 constexpr int THREADS = 544;          // warps 0-7 decoders (2 groups), 8-15 epilogue (2 groups), 16 MMA
 constexpr int GROUP_THREADS = 128;
 constexpr int MMA_WARP = 16;
-constexpr int TAB_BYTES = 65536, A_BYTES = (TM / 8) * GRP_BYTES, B_BYTES = (NQT / 8) * GRP_BYTES;
 constexpr int META_BYTES = 3 * NQT * 4;   // h | base | qidx
-constexpr int OFF_TAB = 0;
-constexpr int OFF_A = TAB_BYTES;
-constexpr int OFF_B = OFF_A + 2 * A_BYTES;
-constexpr int OFF_META = OFF_B + B_BYTES;
-constexpr int OFF_BAR = OFF_META + 2 * META_BYTES;
-constexpr size_t SMEM_BYTES = OFF_BAR + 256 + 128 /*alignment slack*/;
-static_assert(SMEM_BYTES <= 227 * 1024, "filter kernel shared memory");
+// geometry of one engine instance: G groups of 16 sub-quantizers of DSUB dimensions (K = 16 G DSUB).
+// Instances: <1, 8> (m = 16, d = 128: BASELINE C3) and <3, 2> (m = 48, d = 96: BASELINE C5).
+template <int G, int DSUB>
+struct TcCfg {
+    static constexpr int M = 16 * G;
+    static constexpr int KD = M * DSUB;               // dimensions
+    static_assert(KD % 16 == 0 && (DSUB == 2 || DSUB == 4 || DSUB == 8), "unsupported PQ geometry");
+    static constexpr int XCHUNK = KD / 8;             // 16-byte chunk that carries the admission test (row term / column threshold)
+    static constexpr int KSTEPS = KD / 16 + 1;        // the last K-step holds the test chunk + a zero chunk
+    static constexpr int CHUNKS = 2 * KSTEPS;         // 16-byte chunks per operand row
+    static constexpr int GRP_BYTES = CHUNKS * 128;    // one 8-row group of an operand: core matrices of 128 B (UMMA SBO)
+    static constexpr int TAB_BYTES = M * 256 * DSUB * 2;   // bf16 codebooks
+    static constexpr int A_BYTES = (TM / 8) * GRP_BYTES, B_BYTES = (NQT / 8) * GRP_BYTES;
+    static constexpr int OFF_TAB = 0;
+    static constexpr int OFF_A = TAB_BYTES;
+    static constexpr int OFF_B = OFF_A + 2 * A_BYTES;
+    static constexpr int OFF_META = OFF_B + B_BYTES;
+    static constexpr int OFF_BAR = OFF_META + 2 * META_BYTES;
+    static constexpr size_t SMEM_BYTES = OFF_BAR + 256 + 128 /*alignment slack*/;
+    static_assert(SMEM_BYTES <= 227 * 1024, "filter kernel shared memory");
+};
+constexpr int KD = 128;                   // (phase-A kernels below are specific to the <1, 8> geometry)
 constexpr float kErrCoef = 0.0085f;       // (2u + u^2) for bf16 operands + fp32 accumulation slack
-constexpr float kAccCoef = 4e-5f;         // fp32 accumulation of the K=144 contraction incl. the threshold terms (x (|h| + max|r|))
+constexpr float kAccCoef = 4e-5f;         // fp32 accumulation of the contraction incl. the threshold terms (x (|h| + max|r|))
 
 struct Params {
     int metric;
@@ -87,7 +97,8 @@ struct Params {
     // index
     const int64_t* list_off;
     const int32_t* list_len;
-    const uint4* codes;            // [npad]
+    const uint4* codes;            // [G][npad] 16 code bytes per group, rotated by pos % 16 (kb2_ivf.cuh)
+    const uint4* codes_plain;      // [G][npad] un-rotated copy (byte b = sub-quantizer 16 g + b); used by the decode when DSUB < 8
     int64_t npad;
     const float* t1;               // [npad] (L2)
     const float* pqc;              // [16][256][8] fp32
@@ -135,11 +146,11 @@ bar_sync_epi() {
 // UMMA shared-memory descriptor, K-major, no swizzle: core matrix = 8 rows x 16 B (128 B contiguous);
 // LBO = distance between the two core matrices of one K=16 step (128 B), SBO = distance between 8-row groups (GRP_BYTES)
 __device__ __forceinline__ uint64_t
-make_desc_ns(uint32_t smem_addr) {
+make_desc_ns(uint32_t smem_addr, uint32_t grp_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
     d |= (uint64_t)(128 >> 4) << 16;
-    d |= (uint64_t)(GRP_BYTES >> 4) << 32;
+    d |= (uint64_t)(grp_bytes >> 4) << 32;
     d |= (uint64_t)1 << 46;
     return d;
 }
@@ -173,9 +184,13 @@ split3_bf16(float x, uint32_t& hi, uint32_t& mid, uint32_t& lo) {
     lo = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(r2));
 }
 
-template <int METRIC>
+template <int METRIC, int G, int DSUB>
 __global__ void __launch_bounds__(THREADS, 1)
 ivfpq_tc_filter_kernel(Params p) {
+    using C = TcCfg<G, DSUB>;
+    constexpr int KD = C::KD, XCHUNK = C::XCHUNK, KSTEPS = C::KSTEPS, GRP_BYTES = C::GRP_BYTES, TAB_BYTES = C::TAB_BYTES;
+    constexpr int A_BYTES = C::A_BYTES, OFF_TAB = C::OFF_TAB, OFF_A = C::OFF_A, OFF_B = C::OFF_B, OFF_META = C::OFF_META,
+                  OFF_BAR = C::OFF_BAR;
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t raw = tc::smem_u32(smem_dyn);
     const uint32_t base = (raw + 127u) & ~127u;
@@ -276,20 +291,27 @@ ivfpq_tc_filter_kernel(Params p) {
             const int ntiles = (len + TM - 1) / TM;
             const int par = it & 1;
             const int t_first = (int)((dg - (int)(g0 & 1u)) & 1);   // this group's first tile of the item
-            uint4 w_next = make_uint4(0, 0, 0, 0);
+            uint4 w_next[G];
+#pragma unroll
+            for (int g = 0; g < G; g++) w_next[g] = make_uint4(0, 0, 0, 0);
             float t_next = 0.f;
+            const uint4* code_src = (DSUB == 8) ? p.codes : p.codes_plain;
             if (t_first < ntiles && off + (int64_t)t_first * TM + tid < p.npad) {
-                w_next = ldg_stream_u4(p.codes + off + (int64_t)t_first * TM + tid);
+#pragma unroll
+                for (int g = 0; g < G; g++) w_next[g] = ldg_stream_u4(code_src + (int64_t)g * p.npad + off + (int64_t)t_first * TM + tid);
                 if (METRIC == KB2_METRIC_L2) t_next = __ldg(p.t1 + off + (int64_t)t_first * TM + tid);
             }
             auto decode_tile = [&](int t) {
                 const uint32_t g = g0 + (uint32_t)t;      // g & 1 == dg
-                const uint4 w = w_next;
+                uint4 w[G];
+#pragma unroll
+                for (int gg = 0; gg < G; gg++) w[gg] = w_next[gg];
                 const float tv = t_next;
                 {
                     const int64_t pn = off + (int64_t)(t + 2) * TM + tid;
                     if (t + 2 < ntiles && pn < p.npad) {
-                        w_next = ldg_stream_u4(p.codes + pn);
+#pragma unroll
+                        for (int gg = 0; gg < G; gg++) w_next[gg] = ldg_stream_u4(code_src + (int64_t)gg * p.npad + pn);
                         if (METRIC == KB2_METRIC_L2) t_next = __ldg(p.t1 + pn);
                     }
                 }
@@ -300,18 +322,55 @@ ivfpq_tc_filter_kernel(Params p) {
                 split3_bf16(-r, rh, rm, rl);
                 mbar_wait_g(bar_a_empty(dg), ((g >> 1) & 1u) ^ 1u);
                 unsigned char* A = sm + OFF_A + dg * A_BYTES + (tid >> 3) * GRP_BYTES + (tid & 7) * 16;
-                const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-                uint4 v[16];
+                if constexpr (DSUB == 8) {
+                    // chunk = one sub-quantizer (8 bf16): 16 gathers per group through the rotated code bytes.  The table is
+                    // laid out [code value][sub-quantizer] (16 B entries): the 8 lanes of a quarter-warp hold 8 consecutive
+                    // sub-quantizers, i.e. 8 different 16-byte bank groups whatever their code values => every LDS.128 is
+                    // conflict-free (a [sub-quantizer][code value] table costs ~3x the wavefronts with random codes).
 #pragma unroll
-                for (int s = 0; s < 16; s++) {           // all 16 gathers in flight before the first store
-                    const uint32_t byte = (ww[s >> 2] >> (8 * (s & 3))) & 255u;
-                    v[s] = tab[((s + tid) & 15) * 256 + byte];   // pos % 16 == tid % 16 (list_off, tile starts: multiples of 16)
+                    for (int gg = 0; gg < G; gg++) {
+                        const uint32_t ww[4] = {w[gg].x, w[gg].y, w[gg].z, w[gg].w};
+#pragma unroll
+                        for (int h0 = 0; h0 < 16; h0 += 8) {     // 8 gathers in flight, then 8 stores
+                            uint4 v[8];
+#pragma unroll
+                            for (int s = 0; s < 8; s++) {
+                                const uint32_t byte = (ww[(h0 + s) >> 2] >> (8 * ((h0 + s) & 3))) & 255u;
+                                v[s] = tab[byte * (16 * G) + gg * 16 + ((h0 + s + tid) & 15)];   // pos % 16 == tid % 16
+                            }
+#pragma unroll
+                            for (int s = 0; s < 8; s++) *reinterpret_cast<uint4*>(A + (gg * 16 + ((h0 + s + tid) & 15)) * 128) = v[s];
+                        }
+                    }
+                } else {
+                    // chunk = 8 / DSUB consecutive sub-quantizers, assembled from the un-rotated code bytes (static indices)
+                    constexpr int SPC = 8 / DSUB;              // sub-quantizers per 16-byte chunk
+                    constexpr int WPS = DSUB / 2;              // 32-bit words per sub-quantizer entry
+                    const uint32_t* tab32 = reinterpret_cast<const uint32_t*>(tab);
+#pragma unroll
+                    for (int c0 = 0; c0 < XCHUNK; c0 += 4) {   // 4 chunks (16 words) in flight
+                        uint32_t v[4][4];
+#pragma unroll
+                        for (int cc = 0; cc < 4; cc++) {
+#pragma unroll
+                            for (int j = 0; j < SPC; j++) {
+                                const int m = (c0 + cc) * SPC + j;
+                                const uint4 wg = w[m >> 4];
+                                const int b = m & 15;
+                                const uint32_t word = (b < 4) ? wg.x : (b < 8) ? wg.y : (b < 12) ? wg.z : wg.w;
+                                const uint32_t byte = (word >> (8 * (b & 3))) & 255u;
+#pragma unroll
+                                for (int x = 0; x < WPS; x++) v[cc][j * WPS + x] = tab32[(m * 256 + byte) * WPS + x];
+                            }
+                        }
+#pragma unroll
+                        for (int cc = 0; cc < 4; cc++)
+                            *reinterpret_cast<uint4*>(A + (c0 + cc) * 128) = make_uint4(v[cc][0], v[cc][1], v[cc][2], v[cc][3]);
+                    }
                 }
-#pragma unroll
-                for (int s = 0; s < 16; s++) *reinterpret_cast<uint4*>(A + ((s + tid) & 15) * 128) = v[s];
-                // chunk 16: [-r_hi, -r_mid, -r_lo, 1, 1, 1, 0, 0] (bf16 1.0 = 0x3F80); chunk 17: zeros
-                *reinterpret_cast<uint4*>(A + 16 * 128) = make_uint4(rh | (rm << 16), rl | (0x3F80u << 16), 0x3F803F80u, 0u);
-                *reinterpret_cast<uint4*>(A + 17 * 128) = make_uint4(0u, 0u, 0u, 0u);
+                // test chunk: [-r_hi, -r_mid, -r_lo, 1, 1, 1, 0, 0] (bf16 1.0 = 0x3F80); then a zero chunk
+                *reinterpret_cast<uint4*>(A + XCHUNK * 128) = make_uint4(rh | (rm << 16), rl | (0x3F80u << 16), 0x3F803F80u, 0u);
+                *reinterpret_cast<uint4*>(A + (XCHUNK + 1) * 128) = make_uint4(0u, 0u, 0u, 0u);
                 tc::fence_proxy_async();
                 tc::mbar_arrive(bar_a_full(dg));
             };
@@ -329,7 +388,7 @@ ivfpq_tc_filter_kernel(Params p) {
                 unsigned char* B = sm + OFF_B;
                 const int kc = tid >> 3;        // 16-byte chunk along K (0..15)
                 const int rsub = tid & 7;
-                for (int blk = dg; blk < nmma / 8; blk += 2) {
+                for (int blk = dg; blk < nmma / 8 && kc < XCHUNK; blk += 2) {
                     const int row = blk * 8 + rsub;
                     const int q = m_q[row];
                     const uint32_t dst = (uint32_t)(blk * GRP_BYTES + kc * 128 + rsub * 16);
@@ -344,8 +403,8 @@ ivfpq_tc_filter_kernel(Params p) {
                     uint32_t hh, hm, hl;
                     split3_bf16(m_h[dt], hh, hm, hl);
                     unsigned char* Bc = B + (dt >> 3) * GRP_BYTES + (dt & 7) * 16;
-                    *reinterpret_cast<uint4*>(Bc + 16 * 128) = make_uint4(0x3F803F80u, 0x3F80u | (hh << 16), hm | (hl << 16), 0u);
-                    *reinterpret_cast<uint4*>(Bc + 17 * 128) = make_uint4(0u, 0u, 0u, 0u);
+                    *reinterpret_cast<uint4*>(Bc + XCHUNK * 128) = make_uint4(0x3F803F80u, 0x3F80u | (hh << 16), hm | (hl << 16), 0u);
+                    *reinterpret_cast<uint4*>(Bc + (XCHUNK + 1) * 128) = make_uint4(0u, 0u, 0u, 0u);
                 }
                 asm volatile("cp.async.wait_all;" ::: "memory");
             }
@@ -379,7 +438,7 @@ ivfpq_tc_filter_kernel(Params p) {
                     const uint32_t d = tmem_base + (uint32_t)buf * 256u;
 #pragma unroll
                     for (int ks = 0; ks < KSTEPS; ks++)
-                        mma_bf16(d, make_desc_ns(a0 + ks * 256), make_desc_ns(b0 + ks * 256), idesc, ks > 0 ? 1u : 0u);
+                        mma_bf16(d, make_desc_ns(a0 + ks * 256, GRP_BYTES), make_desc_ns(b0 + ks * 256, GRP_BYTES), idesc, ks > 0 ? 1u : 0u);
                     tc::tc_commit(bar_a_empty(buf));
                     tc::tc_commit(bar_acc_full(buf));
                 }
@@ -592,31 +651,36 @@ fill_pairs_kernel(const int64_t* __restrict__ probe_ids, const float* __restrict
     pair_base[slot] = (metric == KB2_METRIC_L2) ? dv : -dv;
 }
 
-// bf16 copy + norm of the queries (warp per query, d = 128)
+// bf16 copy + norm of the queries (warp per query, d % 4 == 0)
 __global__ void
-prepare_queries_kernel(const float* __restrict__ q, int64_t nq, __nv_bfloat16* __restrict__ qb16, float* __restrict__ qnorm) {
+prepare_queries_kernel(const float* __restrict__ q, int64_t nq, int d, __nv_bfloat16* __restrict__ qb16, float* __restrict__ qnorm) {
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= nq) return;
-    const float4 v = __ldg(reinterpret_cast<const float4*>(q + w * KD) + lane);
-    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-    uint2 o;
-    o.x = *reinterpret_cast<uint32_t*>(&lo);
-    o.y = *reinterpret_cast<uint32_t*>(&hi);
-    reinterpret_cast<uint2*>(qb16 + w * KD)[lane] = o;
-    float s = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    float s = 0.f;
+    for (int j = lane * 4; j < d; j += 128) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(q + w * d + j));
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        uint2 o;
+        o.x = *reinterpret_cast<uint32_t*>(&lo);
+        o.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(qb16 + w * d + j) = o;
+        s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
     s = warp_sum(s);
     if (lane == 0) qnorm[w] = sqrtf(s) * 1.0001f;
 }
 
-// bf16 copy of the PQ codebooks [16][256][8] + max_j |c[m][j]|^2 per sub-quantizer (grid = 16, block = 256)
+// bf16 copy of the PQ codebooks + max_j |c[m][j]|^2 per sub-quantizer (grid = M, block = 256).  Layout: dsub == 8:
+// [code value j][sub-quantizer m] (conflict-free gathers in the filter kernel's decode); dsub < 8: [m][j].
 __global__ void __launch_bounds__(256)
-prepare_tables_kernel(const float* __restrict__ pqc, __nv_bfloat16* __restrict__ pqc16, float* __restrict__ maxn2) {
+prepare_tables_kernel(const float* __restrict__ pqc, int dsub, __nv_bfloat16* __restrict__ pqc16, float* __restrict__ maxn2) {
     const int m = blockIdx.x, j = threadIdx.x;
-    const float* c = pqc + ((size_t)m * 256 + j) * 8;
+    const int M = gridDim.x;
+    const float* c = pqc + ((size_t)m * 256 + j) * dsub;
     float n2 = 0.f;
-    __nv_bfloat16* o = pqc16 + ((size_t)m * 256 + j) * 8;
-    for (int t = 0; t < 8; t++) {
+    __nv_bfloat16* o = pqc16 + (dsub == 8 ? ((size_t)j * M + m) : ((size_t)m * 256 + j)) * dsub;
+    for (int t = 0; t < dsub; t++) {
         n2 = fmaf(c[t], c[t], n2);
         o[t] = __float2bfloat16_rn(c[t]);
     }
@@ -628,6 +692,16 @@ prepare_tables_kernel(const float* __restrict__ pqc, __nv_bfloat16* __restrict__
         __syncthreads();
     }
     if (j == 0) maxn2[m] = red[0];
+}
+// un-rotated copy of the code bytes: plain[g][pos] byte b = sub-quantizer 16 g + b   (rotated: byte s = sub-quantizer (s + pos) % 16)
+__global__ void
+unrotate_codes_kernel(const uint8_t* __restrict__ rot, int64_t total_words /* G * npad */, int64_t npad, uint8_t* __restrict__ plain) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total_words * 16) return;
+    const int s = (int)(t & 15);
+    const int64_t word = t >> 4;
+    const int64_t pos = word % npad;
+    plain[word * 16 + ((s + (int)(pos & 15)) & 15)] = rot[t];
 }
 
 // survivors of all CTA logs -> per-query rows (thread per log entry; grid = (x, number of logs))
@@ -703,13 +777,15 @@ lut_build_kernel(const float* __restrict__ queries, int64_t nq, const int32_t* _
 // produce bit-identical keys.  The entries are recomputed from the fp32 codebook (L1/L2 resident) instead of read from
 // a per-query table: no [nq][4096] table has to exist for the queries whose phase A ran on another rank.
 // grid = nq, block = 128.  Survivors above the bound become kEmpty.
-template <int METRIC>
+template <int METRIC, int G, int DSUB>
 __global__ void __launch_bounds__(128)
-exact_eval_kernel(const float* __restrict__ queries, const float* __restrict__ pqc, const float* __restrict__ bound_of,
-                  const uint4* __restrict__ codes, const float* __restrict__ t1, const uint8_t* __restrict__ bitset,
+exact_eval_kernel(const float* __restrict__ queries, const float* __restrict__ pqc, const float* __restrict__ lut,
+                  const float* __restrict__ bound_of,
+                  const uint4* __restrict__ codes, int64_t npad, const float* __restrict__ t1, const uint8_t* __restrict__ bitset,
                   const int32_t* __restrict__ rows, uint64_t* __restrict__ cand, const uint32_t* __restrict__ cand_cnt, int cap,
                   uint32_t* __restrict__ qflag, const uint32_t* __restrict__ log_over) {
-    __shared__ __align__(16) float s_q[KD];
+    constexpr int KDIM = 16 * G * DSUB;
+    __shared__ __align__(16) float s_q[KDIM];
     const int64_t q = blockIdx.x;
     if (*log_over) {
         if (threadIdx.x == 0) qflag[q] = 1u;
@@ -718,8 +794,14 @@ exact_eval_kernel(const float* __restrict__ queries, const float* __restrict__ p
     if (qflag[q]) return;
     const uint32_t n = min(cand_cnt[q], (uint32_t)cap);
     if (n == 0) return;
-    s_q[threadIdx.x] = queries[q * KD + threadIdx.x];
-    __syncthreads();
+    // lut != NULL (<1, 8> geometry, single GPU): the batch's tables [nq][256][16] from lut_build_kernel hold exactly these
+    // entries; otherwise they are recomputed from the codebook
+    const bool use_lut = (G == 1 && DSUB == 8) && lut != nullptr;
+    if (!use_lut) {
+        for (int j = threadIdx.x; j < KDIM; j += 128) s_q[j] = queries[q * KDIM + j];
+        __syncthreads();
+    }
+    const float* lq = lut + q * 4096;
     const float bound = bound_of[q];
     const float scale = (METRIC == KB2_METRIC_L2) ? -2.f : -1.f;
     uint64_t* row = cand + q * cap;
@@ -727,22 +809,28 @@ exact_eval_kernel(const float* __restrict__ queries, const float* __restrict__ p
         const uint64_t ent = row[i];
         const uint32_t pos = (uint32_t)ent;
         const float base = __uint_as_float((uint32_t)(ent >> 32));
-        const uint4 w = __ldg(codes + pos);
-        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
         float acc0 = (METRIC == KB2_METRIC_L2) ? __ldg(t1 + pos) : 0.f, acc1 = 0.f;
 #pragma unroll
-        for (int s = 0; s < 16; s++) {
-            const uint32_t byte = (ww[s >> 2] >> (8 * (s & 3))) & 255u;
-            const uint32_t m = (pos + s) & 15u;
-            const float4 c0 = __ldg(reinterpret_cast<const float4*>(pqc + ((size_t)m * 256 + byte) * 8));
-            const float4 c1 = __ldg(reinterpret_cast<const float4*>(pqc + ((size_t)m * 256 + byte) * 8) + 1);
-            const float4 qa = *reinterpret_cast<const float4*>(&s_q[m * 8]);
-            const float4 qb = *reinterpret_cast<const float4*>(&s_q[m * 8 + 4]);
-            float a = 0.f;
-            a = fmaf(qa.x, c0.x, a); a = fmaf(qa.y, c0.y, a); a = fmaf(qa.z, c0.z, a); a = fmaf(qa.w, c0.w, a);
-            a = fmaf(qb.x, c1.x, a); a = fmaf(qb.y, c1.y, a); a = fmaf(qb.z, c1.z, a); a = fmaf(qb.w, c1.w, a);
-            const float v = __fmul_rn(a, scale);
-            if (s & 1) acc1 = __fadd_rn(acc1, v); else acc0 = __fadd_rn(acc0, v);
+        for (int g = 0; g < G; g++) {
+            const uint4 w = __ldg(codes + (int64_t)g * npad + pos);
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int s = 0; s < 16; s++) {
+                const uint32_t byte = (ww[s >> 2] >> (8 * (s & 3))) & 255u;
+                const uint32_t m = g * 16 + ((pos + s) & 15u);
+                float v;
+                if (use_lut) {
+                    v = __ldg(lq + byte * 16 + m);
+                } else {
+                    const float* c = pqc + ((size_t)m * 256 + byte) * DSUB;
+                    const float* qs = &s_q[m * DSUB];
+                    float a = 0.f;
+#pragma unroll
+                    for (int t = 0; t < DSUB; t++) a = fmaf(qs[t], __ldg(c + t), a);
+                    v = __fmul_rn(a, scale);
+                }
+                if (s & 1) acc1 = __fadd_rn(acc1, v); else acc0 = __fadd_rn(acc0, v);
+            }
         }
         const float key = __fadd_rn(base, __fadd_rn(acc0, acc1));
         bool keep = key <= bound;

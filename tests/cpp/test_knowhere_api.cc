@@ -113,6 +113,72 @@ main() {
         REQUIRE(rr.has_value());
         REQUIRE(rr.value()->GetLims()[1] - rr.value()->GetLims()[0] == (size_t)(topk - 1));
     }
+    // AnnIterator, GetIndexMeta, DeserializeFromFile, BitsetView with an id offset, HNSW RangeSearch + filter
+    for (const char* name : {"IVF_FLAT", "HNSW"}) {
+        Json json = base;
+        json[indexparam::NLIST] = 16;
+        json[indexparam::NPROBE] = 16;
+        json[indexparam::HNSW_M] = 16;
+        json[indexparam::EFCONSTRUCTION] = 100;
+        json[indexparam::EF] = 64;
+        auto ix = IndexFactory::Instance().Create<fp32>(name, 0).value();
+        REQUIRE(ix.Build(train_ds, json) == Status::success);
+        auto meta_ds = ix.GetIndexMeta(json);
+        REQUIRE(meta_ds.has_value() && meta_ds.value()->GetJsonInfo().find(name) != std::string::npos);
+        // iterator: the first topk results equal Search's, distances are monotone, and it continues past topk
+        auto one = GenDataSet(1, dim, xq.data());
+        auto its = ix.AnnIterator(one, json, nullptr);
+        REQUIRE(its.has_value() && its.value().size() == 1);
+        auto sr = ix.Search(one, json, nullptr);
+        REQUIRE(sr.has_value());
+        float prev = -1.f;
+        int got = 0;
+        std::set<int64_t> uniq;
+        auto it = its.value()[0];
+        const bool exact_scan = std::string(name) == "IVF_FLAT";
+        while (got < 100 && it->HasNext().value()) {
+            auto nx = it->Next();
+            REQUIRE(nx.has_value());
+            if (got < (int)topk && exact_scan) REQUIRE(nx.value().first == sr.value()->GetIds()[got]);
+            if (exact_scan) REQUIRE(nx.value().second >= prev);
+            prev = nx.value().second;
+            uniq.insert(nx.value().first);
+            got++;
+        }
+        REQUIRE(got == 100 && (int)uniq.size() == 100);
+        // file round trip
+        BinarySet bs;
+        REQUIRE(ix.Serialize(bs) == Status::success);
+        auto bin = bs.GetByName(name);
+        REQUIRE(bin != nullptr);
+        const char* path = "/tmp/kb2_cpp_test_index.bin";
+        FILE* f = fopen(path, "wb");
+        REQUIRE(f && fwrite(bin->data.get(), 1, (size_t)bin->size, f) == (size_t)bin->size);
+        fclose(f);
+        auto ix2 = IndexFactory::Instance().Create<fp32>(name, 0).value();
+        REQUIRE(ix2.DeserializeFromFile(path, json) == Status::success);
+        auto sr2 = ix2.Search(one, json, nullptr);
+        REQUIRE(sr2.has_value());
+        for (int64_t i = 0; i < topk; i++) REQUIRE(sr.value()->GetIds()[i] == sr2.value()->GetIds()[i]);
+        // bitset over PUBLIC ids with an id offset: public id = internal id + 5 (bitsetview.h:131-175)
+        std::vector<uint8_t> bits((nb + 5 + 7) / 8, 0);
+        for (int64_t pub = 0; pub < nb + 5; pub += 2) bits[pub >> 3] |= (uint8_t)(1u << (pub & 7));   // even public ids filtered
+        BitsetView bv(bits.data(), (size_t)(nb + 5));
+        bv.set_id_offset(5);
+        bv.set_vector_count((size_t)nb);
+        auto fr = ix.Search(query_ds, json, bv);
+        REQUIRE(fr.has_value());
+        for (int64_t i = 0; i < nq * topk; i++) {
+            const int64_t id = fr.value()->GetIds()[i];
+            REQUIRE(id < 0 || ((id + 5) % 2) == 1);
+        }
+        // RangeSearch through the facade (HNSW: ef-bounded beam + closure, HnswSearcher.h:435-553)
+        Json rj = json;
+        rj[meta::RADIUS] = gt.value()->GetDistance()[topk - 1];
+        auto rr = ix.RangeSearch(query_ds, rj, nullptr);
+        REQUIRE(rr.has_value());
+        REQUIRE(rr.value()->GetLims()[1] - rr.value()->GetLims()[0] >= 1);
+    }
     printf("knowhere C++ API tests passed\n");
     return 0;
 }

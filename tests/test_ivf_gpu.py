@@ -367,3 +367,29 @@ def test_ivfflat_tc_engine_small_lists_and_fallback(kb):
     a = _with_env("KB2_FLAT_ENGINE", "tc", lambda: ix.search(xq, k, {"nprobe": 64}))
     b = _with_env("KB2_FLAT_ENGINE", "scan", lambda: ix.search(xq, k, {"nprobe": 64}))
     assert_topk_parity(a[0], a[1], b[0], b[1], rtol=2e-6, atol=1e-5, what="IVF_FLAT tc small lists", max_tie_rows=2)
+
+
+@pytest.mark.parametrize("np_dtype", [np.int8, np.float16])
+def test_typed_ingest_matches_widened_fp32(kb, np_dtype):
+    """int8 / fp16 data and queries (kb2_index_*_typed: widened to fp32 on the device like the reference's
+    index_node_data_mock_wrapper.cc:24-60) give exactly the answer of the same values passed as fp32."""
+    nb, d, nlist, m = 20000, 96, 32, 48
+    xb = datagen.clustered(nb, d, 42)
+    xq = datagen.clustered(64, d, 43)
+    if np_dtype == np.int8:
+        s = 127.0 / np.abs(xb).max()
+        xb_t, xq_t = np.clip(np.round(xb * s), -127, 127).astype(np.int8), np.clip(np.round(xq * s), -127, 127).astype(np.int8)
+    else:
+        xb_t, xq_t = xb.astype(np.float16), xq.astype(np.float16)
+    a = kb.Index("IVF_PQ", "IP", d, {"nlist": nlist, "m": m})
+    a.build(xb_t)
+    b = kb.Index("IVF_PQ", "IP", d, {"nlist": nlist, "m": m})
+    b.build(xb_t.astype(np.float32))
+    ra = a.search(xq_t, 10, {"nprobe": 8})
+    rb = b.search(xq_t.astype(np.float32), 10, {"nprobe": 8})
+    assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1])
+    f = kb.Index("FLAT", "L2", d)
+    f.add(xb_t)
+    ids, dist = f.search(xq_t, 5)
+    gi, gd = kb.brute_force_search(xb_t.astype(np.float32), xq_t.astype(np.float32), 5, "L2")
+    assert np.array_equal(ids, gi)

@@ -114,3 +114,40 @@ def test_ivfpq_tc_engine_on_shards(kb):
         ids.append(b[0]); dis.append(b[1])
     mi, md = kb.merge_topk(np.stack(ids), np.stack(dis), "L2")
     assert_topk_parity(mi, md, I0, D0, rtol=1e-6, atol=1e-6, what="sharded tc merge", max_tie_rows=nq // 10)
+
+
+@pytest.mark.parametrize("metric", ["IP", "L2"])
+def test_ivfpq_tc_engine_m48_dsub2(kb, ref, metric):
+    """The <G=3, dsub=2> instance of the engine (m = 48, d = 96: BASELINE C5's geometry, IP and L2): bit-identical to the LUT
+    engine, and the reference's IndexIVFPQ on the same imported index agrees (IVFPQScanner_impl.h:110-185)."""
+    nb, d, m, nlist, nprobe, nq, k = 60000, 96, 48, 64, 16, 3000, 10
+    xb = datagen.clustered(nb, d, 42)
+    xq = datagen.clustered(nq, d, 43)
+    mt = 0 if metric == "L2" else 1
+    r = ref.RefIvf("IVF_PQ", d, mt, nlist, m, 8)
+    r.train(xb)
+    r.add(xb)
+    ix = kb.Index("IVF_PQ", metric, d, {"nlist": nlist, "m": m, "nbits": 8})
+    ix.ivf_import(r.centroids(), r.pq_centroids(), list(r.lists()))
+    cfg = {"nprobe": nprobe}
+    ix.enable_kernel_timing(True)
+    i1, d1 = _search(ix, xq, k, cfg, "tc")
+    assert ix.last_stage_info()["engine"] == "tc" and ix.last_counters()["codes"] > 0
+    i0, d0 = _search(ix, xq, k, cfg, "lut")
+    assert np.array_equal(d0.view(np.uint32), d1.view(np.uint32)), f"distances differ in {(d0 != d1).any(axis=1).sum()} rows"
+    assert np.array_equal(i0, i1)
+    I0, D0 = r.search(xq, k, nprobe)
+    assert_topk_parity(i1, d1, I0, D0, rtol=1e-4, atol=1e-3, what=f"IVF_PQ m48 {metric} tc engine", max_tie_rows=nq // 10)
+    # int8-valued data (C5 is int8 widened to fp32) through the typed entry points, with a bitset
+    s = 127.0 / np.abs(xb).max()
+    xb8 = np.clip(np.round(xb * s), -127, 127).astype(np.int8)
+    xq8 = np.clip(np.round(xq * s), -127, 127).astype(np.int8)
+    ix8 = kb.Index("IVF_PQ", metric, d, {"nlist": nlist, "m": m, "nbits": 8})
+    ix8.build(xb8)
+    mask = np.zeros(nb, bool)
+    mask[::4] = True
+    bits = np.packbits(mask, bitorder="little")
+    a = _search(ix8, xq8, k, cfg, "lut", bitset=bits)
+    b = _search(ix8, xq8, k, cfg, "tc", bitset=bits)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+    assert not mask[b[0][b[0] >= 0]].any()
