@@ -569,6 +569,11 @@ def run_reference(args):
 
 
 def main():
+    # stdout carries exactly ONE JSON line: anything a library prints to fd 1 meanwhile (e.g. NCCL's version banner at
+    # communicator creation) is sent to stderr; the line itself goes to the saved descriptor
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(saved, "w", buffering=1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

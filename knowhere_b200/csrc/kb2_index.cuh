@@ -71,8 +71,10 @@ init_kernel_attributes() {
         set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_IP, 1, 8>);
         set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_L2, 3, 2>);
         set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_IP, 3, 2>);
-        set((const void*)pqtc::bound_kernel<KB2_METRIC_L2>);
-        set((const void*)pqtc::bound_kernel<KB2_METRIC_IP>);
+        set((const void*)pqtc::bound_kernel<KB2_METRIC_L2, 32>);
+        set((const void*)pqtc::bound_kernel<KB2_METRIC_IP, 32>);
+        set((const void*)pqtc::bound_kernel<KB2_METRIC_L2, 64>);
+        set((const void*)pqtc::bound_kernel<KB2_METRIC_IP, 64>);
         set((const void*)fltc::ivfflat_tc_kernel<KB2_METRIC_L2>);
         set((const void*)fltc::ivfflat_tc_kernel<KB2_METRIC_IP>);
         cudaGetLastError();
@@ -855,20 +857,21 @@ struct IvfIndex : IndexBase {
             last.launches += 2;
         }
         {
-            const size_t smem = pqtc::BOUND_SMEM;
+            const char* e_rw = getenv("KB2_BOUND_ROWW");
+            const int roww = (e_rw && atoi(e_rw) == 32) ? 32 : 64;
+            const size_t smem = pqtc::bound_smem(roww);
+#define KB2_BOUND_LAUNCH(MM, RW)                                                                                                    \
+    pqtc::lut_build_kernel<MM><<<kNumSMs, 256, 0, st>>>(sp.queries, nq, qlist, qcount, pqc.p, s_lut.p);                             \
+    mark("lut");                                                                                                                    \
+    pqtc::bound_kernel<MM, RW><<<bound_grid, 128, smem, st>>>(s_lut.p, qlist, qcount, nq, sp.probe_ids, sp.probe_dis, nprobe, p0,   \
+                                                             a_codes, k_base, list_off.p, list_len.p, (const uint4*)codes.p, t1.p, \
+                                                             sp.bitset, rows.p, s_bound.p, d_counter.p + 4);
             if (metric == KB2_METRIC_L2) {
-                pqtc::lut_build_kernel<KB2_METRIC_L2><<<kNumSMs, 256, 0, st>>>(sp.queries, nq, qlist, qcount, pqc.p, s_lut.p);
-                mark("lut");
-                pqtc::bound_kernel<KB2_METRIC_L2><<<bound_grid, 128, smem, st>>>(
-                    s_lut.p, qlist, qcount, nq, sp.probe_ids, sp.probe_dis, nprobe, p0, a_codes, k_base, list_off.p, list_len.p,
-                    (const uint4*)codes.p, t1.p, sp.bitset, rows.p, s_bound.p, d_counter.p + 4);
+                if (roww == 32) { KB2_BOUND_LAUNCH(KB2_METRIC_L2, 32) } else { KB2_BOUND_LAUNCH(KB2_METRIC_L2, 64) }
             } else {
-                pqtc::lut_build_kernel<KB2_METRIC_IP><<<kNumSMs, 256, 0, st>>>(sp.queries, nq, qlist, qcount, pqc.p, s_lut.p);
-                mark("lut");
-                pqtc::bound_kernel<KB2_METRIC_IP><<<bound_grid, 128, smem, st>>>(
-                    s_lut.p, qlist, qcount, nq, sp.probe_ids, sp.probe_dis, nprobe, p0, a_codes, k_base, list_off.p, list_len.p,
-                    (const uint4*)codes.p, t1.p, sp.bitset, rows.p, s_bound.p, d_counter.p + 4);
+                if (roww == 32) { KB2_BOUND_LAUNCH(KB2_METRIC_IP, 32) } else { KB2_BOUND_LAUNCH(KB2_METRIC_IP, 64) }
             }
+#undef KB2_BOUND_LAUNCH
             KB2_CUDA_CHECK(cudaGetLastError());
             last.launches += 2;
         }

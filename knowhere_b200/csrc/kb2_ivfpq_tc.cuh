@@ -896,14 +896,17 @@ compact_flags_kernel(const uint32_t* __restrict__ qflag, int64_t nq, int32_t* __
     {                                                                                         \
         const uint32_t _x = __byte_perm((WORD), lane4, 0x6504u | ((KB) << 4));                \
         float _v;                                                                             \
-        asm("ld.shared.f32 %0, [%1+%2];" : "=f"(_v) : "r"(_x >> 1), "n"(KB2_SMEM_BASE + 4 * (S))); \
+        asm("ld.shared.f32 %0, [%1+%2];" : "=f"(_v) : "r"(_x >> (ROWW == 32 ? 1 : 0)), "n"(KB2_SMEM_BASE + 4 * (S))); \
         ACC += _v;                                                                            \
     }
 constexpr int BOUND_KMAX = 6144;    // keys held per query (phase A looks at no more codes than this)
 constexpr int BOUND_BINS = 1024;
-constexpr size_t BOUND_SMEM = 32768 + BOUND_KMAX * 4 + BOUND_BINS * 4 + 64;
+// ROWW = words per code-value row of the skewed table: 32 (32 KB: lanes i and i+16 share a bank, 2 wavefronts per gather,
+// 3 CTAs/SM) or 64 (64 KB: conflict-free like the LUT kernel, 2 CTAs/SM)
+constexpr size_t bound_smem(int roww) { return (size_t)roww * 1024 + BOUND_KMAX * 4 + BOUND_BINS * 4 + 64; }
+constexpr size_t BOUND_SMEM = bound_smem(32);
 
-template <int METRIC>
+template <int METRIC, int ROWW>
 __global__ void __launch_bounds__(128)
 bound_kernel(const float* __restrict__ lut, const int32_t* __restrict__ qlist, const uint32_t* __restrict__ qcount, int64_t nq,
              const int64_t* __restrict__ probe_ids, const float* __restrict__ probe_dis,
@@ -913,8 +916,8 @@ bound_kernel(const float* __restrict__ lut, const int32_t* __restrict__ qlist, c
              unsigned long long* __restrict__ counters) {
     // work list: table i / query qlist[i] for i < *qcount (qlist == NULL: query i, i < nq); CTAs stride the list
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* s_lut = (float*)smem_raw;                              // [256][32]
-    float* s_keys = (float*)(smem_raw + 32768);                   // [BOUND_KMAX]
+    float* s_lut = (float*)smem_raw;                              // [256][ROWW]
+    float* s_keys = (float*)(smem_raw + ROWW * 1024);             // [BOUND_KMAX]
     uint32_t* s_hist = (uint32_t*)(s_keys + BOUND_KMAX);          // [BOUND_BINS]
     float* s_red = (float*)(s_hist + BOUND_BINS);                 // [16]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -933,15 +936,17 @@ bound_kernel(const float* __restrict__ lut, const int32_t* __restrict__ qlist, c
         for (int i = 0; i < 8; i++) {
             const int idx = threadIdx.x + i * 128;       // float4 index: j = idx / 4, m4 = (idx % 4) * 4
             const float4 v = __ldg(src + idx);
-            float4* dst = reinterpret_cast<float4*>(s_lut + (idx >> 2) * 32 + (idx & 3) * 4);
+            float4* dst = reinterpret_cast<float4*>(s_lut + (idx >> 2) * ROWW + (idx & 3) * 4);
             dst[0] = v;
             dst[4] = v;
+            if (ROWW == 64) { dst[8] = v; dst[12] = v; }
         }
     }
     for (int i = threadIdx.x; i < BOUND_BINS; i += 128) s_hist[i] = 0;
     __syncthreads();
     // PRMT builds (byte << 8) | (lane16 << 3) ; >> 1 = byte * 128 + lane16 * 4 (row pitch 128 B)
-    const uint32_t lane4 = (uint32_t)(lane & 15) << 3;
+    // ROWW = 64: (byte << 8) | (lane << 2) is the address itself (row pitch 256 B, word lane + s)
+    const uint32_t lane4 = (ROWW == 32) ? ((uint32_t)(lane & 15) << 3) : ((uint32_t)lane << 2);
     int seen = 0, n_tot = 0;
     float kmin = INFINITY, kmax = -INFINITY;
     for (int j = 0; j < p0_max && seen < min_codes && n_tot < BOUND_KMAX; j++) {
