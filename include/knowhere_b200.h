@@ -82,10 +82,13 @@ void kb2_index_destroy(kb2_index_t h);
 int kb2_index_set_stream(kb2_index_t h, void* cuda_stream);
 
 /* Multi-GPU list/row sharding.  Must be called before train/add/import.
- * IVF_*: inverted list l is kept by rank (l % world).  FLAT: row i is kept by rank
- * floor(i * world / n) at add time.  HNSW: replicas only (call is accepted, no effect).
- * Search then returns this shard's local top-k; merge shards with kb2_merge_topk after an
- * all-gather. */
+ * IVF_*: every inverted list lives on exactly one rank (greedy size-balanced packing over the global list sizes,
+ * identical on all ranks; KB2_SHARD_POLICY=mod selects l % world).  FLAT: row i is kept by rank
+ * floor(i * world / n) at add time.  HNSW: graph partitions — every rank builds an independent sub-graph over its
+ * contiguous row slice of the (single) add() call and all of them are searched with the same ef (SURVEY §8e option 2;
+ * recall >= the single graph's in practice, at world x the distance evaluations).
+ * Without a communicator Search returns this shard's local top-k (merge shards with kb2_merge_topk after an
+ * all-gather); with kb2_index_set_comm the gather + merge happen inside Search. */
 int kb2_index_set_shard(kb2_index_t h, int rank, int world);
 
 /* IndexNode::Train (reference: include/knowhere/index/index_node.h:131, ivf.cc:545-807):

@@ -6,6 +6,9 @@
 //   encoding  : residual to the assigned centroid, nearest sub-centroid per m (first minimum wins)
 //                                                                  F/IndexIVFPQ.cpp:178-200, ProductQuantizer.cpp:220-260
 #pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include <cub/cub.cuh>
 
 #include <algorithm>
@@ -300,6 +303,19 @@ gather_f32_kernel(const float* __restrict__ src, const int32_t* __restrict__ row
     out[t] = (r >= 0) ? src[r] : fill;
 }
 
+// fp32 -> fp16 (kind 1) / bf16 (kind 2) and back: refine stores of refine_type fp16 / bf16
+__global__ void
+narrow_kernel(const float* __restrict__ x, int64_t n, int kind, uint16_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = (kind == 1) ? __half_as_ushort(__float2half_rn(x[i])) : __bfloat16_as_ushort(__float2bfloat16_rn(x[i]));
+}
+__global__ void
+widen16_kernel(const uint16_t* __restrict__ x, int64_t n, int kind, float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = (kind == 1) ? __half2float(__ushort_as_half(x[i])) : __uint_as_float((uint32_t)x[i] << 16);
+}
 // out[i] = x[i] / |x[i]|  (rows of norm 0 are copied unchanged), warp per row — COSINE support
 __global__ void __launch_bounds__(256)
 normalize_rows_kernel(const float* __restrict__ x, int64_t n, int d, float* __restrict__ out) {

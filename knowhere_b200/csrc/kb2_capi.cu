@@ -158,9 +158,12 @@ kb2_index_create(const char* index_type, int metric, int dim, const char* json_c
                 KB2_REQUIRE(iv->nbits >= 1 && iv->nbits <= 24, KB2_OUT_OF_RANGE_IN_JSON, "nbits out of range");
                 iv->refine = cfg.get_bool("refine", false);
                 if (iv->refine) {
-                    const std::string rt = cfg.get_str("refine_type", "flat");
-                    KB2_REQUIRE(rt == "flat" || rt == "FLAT" || rt == "fp32" || rt == "FP32" || rt == "float32",
-                                KB2_NOT_IMPLEMENTED, "only refine_type=flat (fp32) is implemented");
+                    std::string rt = cfg.get_str("refine_type", "flat");
+                    for (auto& ch : rt) ch = (char)tolower((unsigned char)ch);
+                    if (rt == "flat" || rt == "fp32" || rt == "float32" || rt == "data_view") iv->refine_kind = 0;
+                    else if (rt == "fp16" || rt == "float16") iv->refine_kind = 1;
+                    else if (rt == "bf16" || rt == "bfloat16") iv->refine_kind = 2;
+                    else throw Error(KB2_NOT_IMPLEMENTED, "refine_type " + rt + " is not implemented (flat / fp16 / bf16 are)");
                 }
             }
         } else if (t == "HNSW") {
@@ -596,6 +599,7 @@ index_to_faiss(IndexBase& ix, FaissIndexData& o) {
         o.has_refine = iv->is_pq && iv->refine;
         if (o.has_refine) {
             KB2_REQUIRE(!iv->custom_labels, KB2_NOT_IMPLEMENTED, "faiss stream: refine store with custom ids");
+            KB2_REQUIRE(iv->refine_kind == 0, KB2_NOT_IMPLEMENTED, "faiss stream: only a flat fp32 refine store is written");
             // refine store in id order: row r lives at position pos_of_row[r]
             DevBuf<float> byrow;
             byrow.ensure((size_t)std::max<int64_t>(o.ntotal, 1) * o.d);

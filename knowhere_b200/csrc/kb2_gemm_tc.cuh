@@ -311,13 +311,13 @@ get_encode_fn() {
 
 // 2-D fp32 row-major [rows][d] -> box of 32 columns x 128 rows, 128-byte swizzle, zero fill out of bounds
 inline bool
-make_tmap(CUtensorMap* m, const float* ptr, int64_t rows, int d) {
+make_tmap(CUtensorMap* m, const float* ptr, int64_t rows, int d, int box_rows = 128) {
     PFN_encodeTiled fn = get_encode_fn();
     if (!fn) return false;
     if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (d & 3)) return false;
     cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)rows};
     cuuint64_t gstride[1] = {(cuuint64_t)d * 4};
-    cuuint32_t box[2] = {(cuuint32_t)BK, 128};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, gdim, gstride, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -47,7 +47,8 @@ struct HnswSearchParams {
     float* out_dist;
     unsigned long long* stats;  // [0] ndis, [1] nhops
     // filtered search / range search (hnsw_filtered_kernel)
-    const uint8_t* bitset;      // bit set => node filtered out (internal ids), or NULL
+    const uint8_t* bitset;      // bit set => node filtered out, bit index = internal id + bit_offset; or NULL
+    int64_t bit_offset;         // first global row of this shard (graph-partition sharding), else 0
     float k_alpha;              // filter_ratio * 0.7 (faiss_hnsw.cc:1425)
     int range_mode;             // 0: top-k, 1: range search
     float radius_key;           // range: keep key < radius_key (key = L2 distance, or -ip)
@@ -483,7 +484,7 @@ hnsw_filtered_kernel(HnswSearchParams p) {
         int v_size = 0, v_cur = 0, i_size = 0, logn = 0;
         bool log_overflow = false;
         {
-            const bool member = !(p.bitset && bit_is_set(p.bitset, nearest));
+            const bool member = !(p.bitset && bit_is_set(p.bitset, nearest + p.bit_offset));
             if (lane == 0) {
                 if (member) { v_dist[0] = d_nearest; v_id[0] = (uint32_t)nearest; }
                 else { i_dist[0] = d_nearest; i_id[0] = (uint32_t)nearest; }
@@ -538,7 +539,7 @@ hnsw_filtered_kernel(HnswSearchParams p) {
                     const uint32_t bit = 1u << (v & 31);
                     const uint32_t old = atomicOr(&vis[v >> 5], bit);
                     fresh = !(old & bit);
-                    if (fresh && p.bitset) member = !bit_is_set(p.bitset, v);
+                    if (fresh && p.bitset) member = !bit_is_set(p.bitset, v + p.bit_offset);
                 }
                 const unsigned fm = __ballot_sync(0xffffffffu, fresh);
                 const int nf = __popc(fm);
@@ -691,7 +692,7 @@ hnsw_filtered_kernel(HnswSearchParams p) {
                     const uint32_t bit = 1u << (v & 31);
                     const uint32_t old = atomicOr(&vis[v >> 5], bit);
                     fresh = !(old & bit);
-                    if (fresh && p.bitset) member = !bit_is_set(p.bitset, v);
+                    if (fresh && p.bitset) member = !bit_is_set(p.bitset, v + p.bit_offset);
                 }
                 const unsigned fm = __ballot_sync(0xffffffffu, fresh);
                 const int nf = __popc(fm);
@@ -755,6 +756,15 @@ bitset_count_kernel(const uint8_t* __restrict__ bits, int64_t nbits, unsigned lo
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
 }
+// set bits among bit positions [first, first + count)
+__global__ void __launch_bounds__(256)
+bitset_count_range_kernel(const uint8_t* __restrict__ bits, int64_t first, int64_t count, unsigned long long* __restrict__ out) {
+    unsigned long long acc = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+        acc += bit_is_set(bits, first + i) ? 1ull : 0ull;
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
 // queries whose result row holds fewer than min(k, n_valid) ids -> compact list (brute-force fallback, faiss_hnsw.cc:1464-1478)
 __global__ void __launch_bounds__(256)
 short_rows_kernel(const int64_t* __restrict__ ids, int64_t nq, int k, int64_t n_valid, int32_t* __restrict__ list,
@@ -796,6 +806,9 @@ struct HnswIndex : IndexBase {
     DevBuf<int> d_next;
     bool uploaded = false;
     int64_t last_ndis = 0, last_nhops = 0;
+    int64_t n_global = 0, shard_lo = 0;   // rows offered to add() / first global row of this shard
+    bool labels_are_offsets = false;      // labels = shard_lo + local row (sharded build without caller ids)
+    int64_t bitset_rows() const override { return shard_world > 1 ? n_global : n; }
 
     void train(const float*, int64_t) override {}
     bool is_trained() const override { return true; }
@@ -905,13 +918,31 @@ struct HnswIndex : IndexBase {
     add(const float* x, int64_t nadd, const int64_t* ids) override {
         KB2_REQUIRE(n == 0, KB2_NOT_IMPLEMENTED, "HNSW: incremental add after the first build is not implemented");
         KB2_REQUIRE(nadd > 0 && nadd < (1ll << 31), KB2_INVALID_ARGS, "bad row count");
-        h_vecs.resize((size_t)nadd * dim);
-        KB2_CUDA_CHECK(cudaMemcpy(h_vecs.data(), x, h_vecs.size() * 4, cudaMemcpyDefault));
-        if (ids) {
-            h_labels.resize(nadd);
-            KB2_CUDA_CHECK(cudaMemcpy(h_labels.data(), ids, nadd * 8, cudaMemcpyDefault));
-            custom_labels = true;
+        // graph-partition sharding (option 2): this rank builds an independent sub-graph over the contiguous row
+        // slice [lo, hi); every shard is searched with the same ef and the per-shard top-k are all-gathered and merged
+        int64_t lo = 0, hi = nadd;
+        if (shard_world > 1) {
+            lo = nadd * shard_rank / shard_world;
+            hi = nadd * (shard_rank + 1) / shard_world;
         }
+        n_global = nadd;
+        shard_lo = lo;
+        const int64_t nloc = hi - lo;
+        KB2_REQUIRE(nloc > 0, KB2_INVALID_ARGS, "HNSW shard without rows");
+        h_vecs.resize((size_t)nloc * dim);
+        KB2_CUDA_CHECK(cudaMemcpy(h_vecs.data(), x + lo * dim, h_vecs.size() * 4, cudaMemcpyDefault));
+        if (ids) {
+            h_labels.resize(nloc);
+            KB2_CUDA_CHECK(cudaMemcpy(h_labels.data(), ids + lo, nloc * 8, cudaMemcpyDefault));
+            custom_labels = true;
+            labels_are_offsets = false;
+        } else if (shard_world > 1) {
+            h_labels.resize(nloc);
+            for (int64_t i = 0; i < nloc; i++) h_labels[i] = lo + i;
+            custom_labels = true;
+            labels_are_offsets = true;
+        }
+        nadd = nloc;
         n = nadd;
         // levels: floor(-ln(U) / ln(M)), RNG seed 12345 (K/impl/HNSW.cpp:60-63,92-105)
         std::mt19937 rng(12345);
@@ -1085,7 +1116,8 @@ struct HnswIndex : IndexBase {
     // exact scan of the stored vectors (the reference's brute-force wrapper: IndexConditionalWrapper.cc:103-200)
     void
     brute_force(const float* dq, int64_t nq, int k, const uint8_t* dbits, int64_t* d_ids, float* d_dist) {
-        DensePlan pl = dense_candidates(*this, dq, nq, d_vecs.p, d_norms.p, n, dim, metric, k + 16, dbits, nullptr);
+        DensePlan pl = dense_candidates(*this, dq, nq, d_vecs.p, d_norms.p, n, dim, metric, k + 16, dbits, nullptr,
+                                        shard_world > 1 ? shard_lo : 0);
         FinalizeParams fp{};
         fp.partial = s_partial.p;
         fp.partial_stride = pl.stride();
@@ -1109,7 +1141,8 @@ struct HnswIndex : IndexBase {
     count_filtered(const uint8_t* dbits) {
         if (!dbits) return 0;
         KB2_CUDA_CHECK(cudaMemsetAsync(d_counter.p + 4, 0, 8, stream));
-        bitset_count_kernel<<<std::min<int64_t>(1024, (n / 8 + 255) / 256 + 1), 256, 0, stream>>>(dbits, n, d_counter.p + 4);
+        bitset_count_range_kernel<<<std::min<int64_t>(1024, (n + 255) / 256), 256, 0, stream>>>(dbits, shard_world > 1 ? shard_lo : 0, n,
+                                                                                         d_counter.p + 4);
         unsigned long long* hc = (unsigned long long*)h_counter.p;
         KB2_CUDA_CHECK(cudaMemcpyAsync(hc, d_counter.p + 4, 8, cudaMemcpyDeviceToHost, stream));
         KB2_CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -1188,6 +1221,16 @@ struct HnswIndex : IndexBase {
             d_ids = s_out_ids.p;
             d_dist = s_out_dist.p;
         }
+        // with a communicator the shard's top-k goes to a staging buffer; one all-gather + the merge kernel produce the result
+        const bool dist = distributed();
+        int64_t* const final_ids = d_ids;
+        float* const final_dist = d_dist;
+        if (dist) {
+            KB2_REQUIRE((int64_t)shard_world * k <= kMaxSortEntries, KB2_INVALID_ARGS, "world * k too large for the merge");
+            ensure_gather_buffers(nq, k);
+            d_ids = s_loc_ids.p;
+            d_dist = s_loc_dist.p;
+        }
         // WhetherPerformBruteForceSearch (IndexConditionalWrapper.cc:35-62): huge k or an almost-all-filtered bitset
         const int64_t n_filtered = count_filtered(dbits);
         const int64_t n_valid = n - n_filtered;
@@ -1211,6 +1254,7 @@ struct HnswIndex : IndexBase {
                     hnsw_search_kernel<KB2_METRIC_IP><<<L.grid, kHnswWarps * 32, L.smem, st>>>(p);
             } else {
                 p.bitset = dbits;
+                p.bit_offset = shard_world > 1 ? shard_lo : 0;
                 p.k_alpha = (float)((double)n_filtered / (double)n) * 0.7f;   // faiss_hnsw.cc:1425
                 if (metric == KB2_METRIC_L2)
                     hnsw_filtered_kernel<KB2_METRIC_L2><<<L.grid, kHnswWarps * 32, L.smem, st>>>(p);
@@ -1241,6 +1285,13 @@ struct HnswIndex : IndexBase {
                 KB2_CUDA_CHECK(cudaGetLastError());
                 last.flagged = ns;
             }
+        }
+        if (dist) {
+            comm->all_gather2(s_loc_ids.p, s_g_ids.p, (size_t)nq * k * 8, s_loc_dist.p, s_g_dist.p, (size_t)nq * k * 4, st);
+            launch_merge_topk(metric, shard_world, nq, k, s_g_ids.p, s_g_dist.p, final_ids, final_dist, st);
+            d_ids = final_ids;
+            d_dist = final_dist;
+            last.launches += 3;
         }
         unsigned long long* hs = (unsigned long long*)h_counter.p;
         KB2_CUDA_CHECK(cudaMemcpyAsync(hs, d_counter.p, 16, cudaMemcpyDeviceToHost, st));
@@ -1303,6 +1354,7 @@ struct HnswIndex : IndexBase {
                 KB2_CUDA_CHECK(cudaMemsetAsync(d_counter.p, 0, 16, st));
                 HnswSearchParams p = base_params(dq, nrun, ef, 1, L);
                 p.bitset = dbits;
+                p.bit_offset = shard_world > 1 ? shard_lo : 0;
                 p.k_alpha = (float)((double)n_filtered / (double)n) * 0.7f;
                 p.range_mode = 1;
                 p.radius_key = (metric == KB2_METRIC_L2) ? radius : -radius;

@@ -75,8 +75,10 @@ init_kernel_attributes() {
         set((const void*)pqtc::bound_kernel<KB2_METRIC_IP, 32>);
         set((const void*)pqtc::bound_kernel<KB2_METRIC_L2, 64>);
         set((const void*)pqtc::bound_kernel<KB2_METRIC_IP, 64>);
-        set((const void*)fltc::ivfflat_tc_kernel<KB2_METRIC_L2>);
-        set((const void*)fltc::ivfflat_tc_kernel<KB2_METRIC_IP>);
+        set((const void*)fltc::ivfflat_tc_kernel<KB2_METRIC_L2, 32>);
+        set((const void*)fltc::ivfflat_tc_kernel<KB2_METRIC_IP, 32>);
+        set((const void*)fltc::ivfflat_tc_kernel<KB2_METRIC_L2, 128>);
+        set((const void*)fltc::ivfflat_tc_kernel<KB2_METRIC_IP, 128>);
         cudaGetLastError();
     });
 }
@@ -131,6 +133,16 @@ struct IndexBase {
     DevBuf<int64_t> s_out_ids, s_probe_ids;
     DevBuf<uint8_t> s_bitset;
     DevBuf<float> s_cos_in, s_cos_out, s_typed_f32;
+    // multi-GPU (kb2_index_set_comm): staging of the local top-k and of the gathered per-shard candidates
+    DevBuf<int64_t> s_loc_ids, s_g_ids;
+    DevBuf<float> s_loc_dist, s_g_dist;
+    void
+    ensure_gather_buffers(int64_t nq, int k) {
+        s_loc_ids.ensure((size_t)nq * k);
+        s_loc_dist.ensure((size_t)nq * k);
+        s_g_ids.ensure((size_t)shard_world * nq * k);
+        s_g_dist.ensure((size_t)shard_world * nq * k);
+    }
     DevBuf<uint8_t> s_typed_raw;
 
     // L2-normalised device copy of n rows (COSINE)
@@ -453,6 +465,7 @@ struct IvfIndex : IndexBase {
     int64_t nlist = 128;
     int M = 0, nbits = 8, dsub = 0;
     bool refine = false;
+    int refine_kind = 0;       // refine store element type: 0 fp32 ("flat"), 1 fp16, 2 bf16 (ivf_config.h:97-128)
     bool trained = false;
     // trained state
     DevBuf<float> centroids, cnorms, pqc;
@@ -469,10 +482,12 @@ struct IvfIndex : IndexBase {
     int64_t npad = 0;
     int G = 0;                 // 16-sub-quantizer groups when the skewed kernel applies, else 0
     std::vector<int64_t> h_list_off;
-    std::vector<int32_t> h_list_len, h_list_cnt_all;
+    std::vector<int32_t> h_list_len, h_list_cnt_all, h_list_owner;
+    DevBuf<int32_t> list_owner;   // [nlist] rank that holds each list (size-balanced packing, identical on every rank)
     DevBuf<int64_t> list_off;
     DevBuf<int32_t> list_len, rows, pos_of_row;
     DevBuf<uint8_t> codes;     // [G][npad][16] or [npad][M]
+    DevBuf<uint16_t> vecs16;          // refine store when refine_kind != 0 (vecs is released after seal)
     DevBuf<float> t1, vecs, vnorm2;   // vnorm2[pos] = |x|^2 (IVF_FLAT: row term of the list-major tensor-core engine)
     DevBuf<int64_t> labels;    // row -> label (sealed copy of f_labels)
     DevBuf<int32_t> s_qkey, s_qkey2, s_qidx, s_qperm;
@@ -480,11 +495,19 @@ struct IvfIndex : IndexBase {
 
     bool keeps_vecs() const { return !is_pq || refine; }
     bool is_trained() const override { return trained; }
-    bool has_raw() const override { return keeps_vecs(); }
+    bool has_raw() const override { return keeps_vecs() && refine_kind == 0; }
+    // fp32 view of the list-order vector store (decoded into tmp when it is kept in 16 bits)
+    const float*
+    vecs_f32(DevBuf<float>& tmp) {
+        if (!refine_kind || !is_pq) return vecs.p;
+        tmp.ensure((size_t)npad * dim);
+        widen16_kernel<<<grid1d(npad * dim, 256), 256, 0, stream>>>(vecs16.p, npad * dim, refine_kind, tmp.p);
+        return tmp.p;
+    }
     int64_t count() const override { return n_total; }
     int64_t
     size_bytes() const override {
-        return (int64_t)(centroids.bytes() + pqc.bytes() + codes.bytes() + t1.bytes() + vecs.bytes() + rows.bytes() +
+        return (int64_t)(centroids.bytes() + pqc.bytes() + codes.bytes() + t1.bytes() + vecs.bytes() + vecs16.bytes() + rows.bytes() +
                          pos_of_row.bytes() + f_codes.bytes() + f_vecs.bytes() + f_assign.bytes());
     }
 
@@ -615,10 +638,32 @@ struct IvfIndex : IndexBase {
         h_list_len.assign(nlist, 0);
         std::vector<int64_t> first_rank(nlist, 0);
         int64_t cur = 0, rank = 0;
+        // list -> shard: greedy size-balanced packing (longest list first onto the lightest shard), computed from
+        // the global list sizes, which every rank holds, so all ranks derive the same table.  KB2_SHARD_POLICY=mod: l % world.
+        h_list_owner.assign(nlist, 0);
+        if (shard_world > 1) {
+            const char* pol = getenv("KB2_SHARD_POLICY");
+            if (pol && !strcmp(pol, "mod")) {
+                for (int64_t l = 0; l < nlist; l++) h_list_owner[l] = (int32_t)(l % shard_world);
+            } else {
+                std::vector<int64_t> order(nlist), load(shard_world, 0);
+                for (int64_t l = 0; l < nlist; l++) order[l] = l;
+                std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return h_list_cnt_all[a] > h_list_cnt_all[b]; });
+                for (int64_t l : order) {
+                    int best = 0;
+                    for (int r = 1; r < shard_world; r++)
+                        if (load[r] < load[best]) best = r;
+                    h_list_owner[l] = best;
+                    load[best] += h_list_cnt_all[l];
+                }
+            }
+        }
+        list_owner.alloc_exact(nlist);
+        KB2_CUDA_CHECK(cudaMemcpyAsync(list_owner.p, h_list_owner.data(), nlist * 4, cudaMemcpyHostToDevice, st));
         for (int64_t l = 0; l < nlist; l++) {
             first_rank[l] = rank;
             rank += h_list_cnt_all[l];
-            const bool owned = (l % shard_world) == shard_rank;
+            const bool owned = h_list_owner[l] == shard_rank;
             h_list_len[l] = owned ? h_list_cnt_all[l] : 0;
             h_list_off[l] = cur;
             cur += round_up(h_list_len[l], 32);
@@ -680,6 +725,11 @@ struct IvfIndex : IndexBase {
             if (!is_pq) {
                 vnorm2.alloc_exact(npad);
                 row_norms_kernel<<<grid1d(npad * 32, 256), 256, 0, st>>>(vecs.p, npad, dim, vnorm2.p);
+            } else if (refine_kind) {
+                vecs16.alloc_exact((size_t)npad * dim);
+                narrow_kernel<<<grid1d(npad * dim, 256), 256, 0, st>>>(vecs.p, npad * dim, refine_kind, vecs16.p);
+                KB2_CUDA_CHECK(cudaStreamSynchronize(st));
+                vecs.release();
             }
         }
         if (custom_labels) {
@@ -707,9 +757,12 @@ struct IvfIndex : IndexBase {
             f_codes_used = (size_t)n * M;
         }
         if (keeps_vecs()) {
+            DevBuf<float> dec;
+            const float* v32 = vecs_f32(dec);
             f_vecs.alloc_exact((size_t)std::max<int64_t>(n, 1) * dim);
-            gather_rows_kernel<<<grid1d(n * 32, 256), 256, 0, st>>>(vecs.p, pos_of_row.p, n, dim, dim, f_vecs.p);
+            gather_rows_kernel<<<grid1d(n * 32, 256), 256, 0, st>>>(v32, pos_of_row.p, n, dim, dim, f_vecs.p);
             f_vecs_used = (size_t)n * dim;
+            KB2_CUDA_CHECK(cudaStreamSynchronize(st));
         }
         KB2_CUDA_CHECK(cudaStreamSynchronize(st));
         sealed = false;
@@ -777,9 +830,6 @@ struct IvfIndex : IndexBase {
     DevBuf<uint4> s_log;
     float tc_rmax = 0.f, tc_rowmax = 0.f;
     bool tc_ready = false;
-    // multi-GPU (kb2_index_set_comm): every rank holds the lists l % world == rank and sees the whole batch
-    DevBuf<int64_t> s_loc_ids, s_g_ids;
-    DevBuf<float> s_loc_dist, s_g_dist;
 
     DevBuf<uint8_t> tc_codes_plain;   // un-rotated code bytes for the geometries whose decode assembles 16-byte chunks from several sub-quantizers
     // engine instances: <G=1, dsub=8> (m16 d128: C3) and <G=3, dsub=2> (m48 d96: C5)
@@ -848,7 +898,7 @@ struct IvfIndex : IndexBase {
         unsigned bound_grid = (unsigned)nq;
         if (dist) {
             s_resp.ensure((size_t)nq + 1);
-            pqtc::compact_resp_kernel<<<1, 1024, 0, st>>>(sp.probe_ids, nprobe, nq, shard_world, shard_rank, s_resp.p + 1,
+            pqtc::compact_resp_kernel<<<1, 1024, 0, st>>>(sp.probe_ids, nprobe, nq, list_owner.p, shard_rank, s_resp.p + 1,
                                                           (uint32_t*)s_resp.p);
             pqtc::fill_f32_kernel<<<grid1d(nq, 256), 256, 0, st>>>(s_bound.p, nq, INFINITY);
             qlist = s_resp.p + 1;
@@ -858,7 +908,7 @@ struct IvfIndex : IndexBase {
         }
         {
             const char* e_rw = getenv("KB2_BOUND_ROWW");
-            const int roww = (e_rw && atoi(e_rw) == 32) ? 32 : 64;
+            const int roww = (e_rw && atoi(e_rw) == 64) ? 64 : 32;   // measured at C3: 0.37 ms (32, 3 CTAs/SM) vs 0.52 ms (64, 2 CTAs/SM)
             const size_t smem = pqtc::bound_smem(roww);
 #define KB2_BOUND_LAUNCH(MM, RW)                                                                                                    \
     pqtc::lut_build_kernel<MM><<<kNumSMs, 256, 0, st>>>(sp.queries, nq, qlist, qcount, pqc.p, s_lut.p);                             \
@@ -1040,6 +1090,8 @@ struct IvfIndex : IndexBase {
         cudaStream_t st = stream;
         const int64_t npairs = nq * nprobe;
         const int64_t npairs_pad = npairs + fltc::NQ_ITEM;
+        // items of <= 32 queries (small B tiles, 5 stages in flight) while a list is probed by few queries, else <= 128
+        const int item_cap = ((double)npairs / (double)std::max<int64_t>(1, nlist) <= 40.0) ? 32 : 128;
         // ---- phase A: exact k-th best key over the query's nearest probed lists (query-major kernel) = admission bound
         const int pA = std::min(nprobe, std::max(1, 2 * shard_world));
         s_bound.ensure((size_t)nq);
@@ -1058,7 +1110,7 @@ struct IvfIndex : IndexBase {
             last.launches += 1;
         }
         // ---- plan: pairs grouped by list, items of <= 128 queries
-        const int64_t max_items = nlist + npairs / fltc::NQ_ITEM + 2;
+        const int64_t max_items = nlist + npairs / item_cap + 2;
         s_lcount.ensure((size_t)2 * nlist);
         s_lstart.ensure((size_t)nlist);
         s_items.ensure((size_t)3 * max_items);
@@ -1076,7 +1128,7 @@ struct IvfIndex : IndexBase {
         int32_t* item_list = s_items.p;
         int32_t* item_q0 = s_items.p + max_items;
         int32_t* item_nq = s_items.p + 2 * max_items;
-        fltc::plan_kernel<<<1, 1024, 0, st>>>(s_lcount.p, (int)nlist, s_lstart.p, item_list, item_q0, item_nq, s_plan_out.p);
+        fltc::plan_kernel<<<1, 1024, 0, st>>>(s_lcount.p, (int)nlist, item_cap, s_lstart.p, item_list, item_q0, item_nq, s_plan_out.p);
         pqtc::fill_pairs_kernel<<<grid1d(npairs, 256), 256, 0, st>>>(sp.probe_ids, sp.probe_dis, npairs, nprobe, metric, list_len.p,
                                                                      s_lstart.p, s_lcount.p + nlist, s_pair_q.p, s_pair_base.p);
         // pairs of lists owned by other shards leave holes at the end of the pair array: point them at no query
@@ -1084,8 +1136,8 @@ struct IvfIndex : IndexBase {
                                                                                      s_qhi.p, s_qlo.p);
         row_norms_kernel<<<grid1d(nq * 32, 256), 256, 0, st>>>(sp.queries, nq, dim, s_qnorm.p);
         CUtensorMap tx, thi, tlo;
-        KB2_REQUIRE(tc::make_tmap(&tx, vecs.p, npad, dim) && tc::make_tmap(&thi, s_qhi.p, npairs_pad, dim) &&
-                        tc::make_tmap(&tlo, s_qlo.p, npairs_pad, dim),
+        KB2_REQUIRE(tc::make_tmap(&tx, vecs.p, npad, dim) && tc::make_tmap(&thi, s_qhi.p, npairs_pad, dim, item_cap) &&
+                        tc::make_tmap(&tlo, s_qlo.p, npairs_pad, dim, item_cap),
                     KB2_INTERNAL_ERROR, "IVF_FLAT tensor-core engine: tensor map encoding failed");
         fltc::Params fpar{};
         fpar.metric = metric;
@@ -1111,10 +1163,14 @@ struct IvfIndex : IndexBase {
         fpar.log_cap = log_cap;
         fpar.counters = d_counter.p;
         if (timing) KB2_CUDA_CHECK(cudaEventRecord(ev2, st));
-        if (metric == KB2_METRIC_L2)
-            fltc::ivfflat_tc_kernel<KB2_METRIC_L2><<<kNumSMs, fltc::THREADS, fltc::SMEM_BYTES, st>>>(tx, thi, tlo, fpar);
-        else
-            fltc::ivfflat_tc_kernel<KB2_METRIC_IP><<<kNumSMs, fltc::THREADS, fltc::SMEM_BYTES, st>>>(tx, thi, tlo, fpar);
+#define KB2_FL_LAUNCH(MM, BR) \
+    fltc::ivfflat_tc_kernel<MM, BR><<<kNumSMs, fltc::THREADS, fltc::FlCfg<BR>::SMEM_BYTES, st>>>(tx, thi, tlo, fpar);
+        if (metric == KB2_METRIC_L2) {
+            if (item_cap == 32) { KB2_FL_LAUNCH(KB2_METRIC_L2, 32) } else { KB2_FL_LAUNCH(KB2_METRIC_L2, 128) }
+        } else {
+            if (item_cap == 32) { KB2_FL_LAUNCH(KB2_METRIC_IP, 32) } else { KB2_FL_LAUNCH(KB2_METRIC_IP, 128) }
+        }
+#undef KB2_FL_LAUNCH
         if (timing) KB2_CUDA_CHECK(cudaEventRecord(ev3, st));
         KB2_CUDA_CHECK(cudaGetLastError());
         uint32_t* qflag = s_cand_cnt.p + nq;
@@ -1279,12 +1335,7 @@ struct IvfIndex : IndexBase {
 
         // ---- finalize: merge CTA lists, optional exact refine, labels.  With a communicator the local top-k goes to a
         //      staging buffer, ONE fused all-gather ships ids + distances of every shard, and the merge kernel writes the result.
-        if (dist) {
-            s_loc_ids.ensure((size_t)nq * k);
-            s_loc_dist.ensure((size_t)nq * k);
-            s_g_ids.ensure((size_t)shard_world * nq * k);
-            s_g_dist.ensure((size_t)shard_world * nq * k);
-        }
+        if (dist) ensure_gather_buffers(nq, k);
         {
             FinalizeParams fp{};
             fp.partial = fin_partial;
@@ -1298,6 +1349,8 @@ struct IvfIndex : IndexBase {
             fp.labels = custom_labels ? labels.p : nullptr;
             fp.rerank = (use_refine || flat_tc) ? 1 : 0;
             fp.raw = vecs.p;
+            fp.raw16 = (is_pq && refine_kind) ? vecs16.p : nullptr;
+            fp.raw16_kind = refine_kind;
             fp.raw_by_pos = 1;
             fp.queries = dq;
             fp.d = dim;

@@ -26,15 +26,23 @@ namespace kb2 {
 namespace fltc {
 
 constexpr int TM = 128;         // list rows per tile (UMMA M)
-constexpr int NQ_ITEM = 128;    // queries per item (UMMA N max)
+constexpr int NQ_ITEM = 128;    // most queries per item (UMMA N max)
 constexpr int BK = 32;          // floats per k-block (one 128-byte swizzle row)
-constexpr int STAGES = 3;
-constexpr int TILE_BYTES = 128 * BK * 4;        // 16 KB
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;     // A_hi | A_lo | B_hi | B_lo
+constexpr int TILE_BYTES = 128 * BK * 4;        // 16 KB: 128 rows of one k-block
 constexpr int THREADS = 320;
-constexpr int OFF_META = STAGES * STAGE_BYTES;             // thr[128] | base[128] | qidx[128]
-constexpr int OFF_BAR = OFF_META + 3 * NQ_ITEM * 4;
-constexpr size_t SMEM_BYTES = OFF_BAR + 256 + 1024 /*alignment slack*/;
+// BROWS = query rows per item the instance is built for (its B tiles are BROWS x 128 B): 32 -> 40 KB stages, 5 in flight
+// (few queries per list: C2 has ~31); 128 -> 64 KB stages, 3 in flight.  The kernel is bound by the latency of the
+// TMA -> convert -> MMA -> release chain of a stage, so the number of stages in flight sets the HBM rate it reaches.
+template <int BROWS>
+struct FlCfg {
+    static constexpr int B_TILE_BYTES = BROWS * BK * 4;
+    static constexpr int STAGE_BYTES = 2 * TILE_BYTES + 2 * B_TILE_BYTES;     // A_hi | A_lo | B_hi | B_lo
+    static constexpr int STAGES = BROWS <= 32 ? 5 : 3;
+    static constexpr int OFF_META = STAGES * STAGE_BYTES;                     // thr[128] | base[128] | qidx[128]
+    static constexpr int OFF_BAR = OFF_META + 3 * NQ_ITEM * 4;
+    static constexpr size_t SMEM_BYTES = OFF_BAR + 256 + 1024 /*alignment slack*/;
+    static_assert(SMEM_BYTES <= 227 * 1024, "IVF_FLAT tensor-core kernel shared memory");
+};
 constexpr float kSlack = 3e-5f;   // 3xTF32 contraction error, relative to |q|^2 + |x|^2 (measured 5e-6, tests/test_gemm_tc_gpu.py)
 
 struct Params {
@@ -84,7 +92,7 @@ extract_bound_kernel(const uint64_t* __restrict__ partial, int64_t stride, int k
 
 // plan for 128-query items (the IVF_PQ engine's plan kernel cuts at 256)
 __global__ void __launch_bounds__(1024)
-plan_kernel(const int32_t* __restrict__ lcount, int nlist, int32_t* __restrict__ lstart, int32_t* __restrict__ item_list,
+plan_kernel(const int32_t* __restrict__ lcount, int nlist, int item_cap, int32_t* __restrict__ lstart, int32_t* __restrict__ item_list,
             int32_t* __restrict__ item_q0, int32_t* __restrict__ item_nq, int32_t* __restrict__ n_items) {
     typedef cub::BlockScan<int, 1024> Scan;
     __shared__ typename Scan::TempStorage tmp_a, tmp_b;
@@ -94,7 +102,7 @@ plan_kernel(const int32_t* __restrict__ lcount, int nlist, int32_t* __restrict__
     for (int b0 = 0; b0 < nlist; b0 += 1024) {
         const int l = b0 + threadIdx.x;
         const int c = l < nlist ? lcount[l] : 0;
-        const int nch = (c + NQ_ITEM - 1) / NQ_ITEM;
+        const int nch = (c + item_cap - 1) / item_cap;
         int ex_a, ex_b, tot_a, tot_b;
         Scan(tmp_a).ExclusiveSum(c, ex_a, tot_a);
         Scan(tmp_b).ExclusiveSum(nch, ex_b, tot_b);
@@ -103,7 +111,7 @@ plan_kernel(const int32_t* __restrict__ lcount, int nlist, int32_t* __restrict__
             lstart[l] = ca + ex_a;
             if (nch > 0) {
                 int per = ((c + nch - 1) / nch + 15) & ~15;
-                if ((nch - 1) * per >= c) per = NQ_ITEM;
+                if ((nch - 1) * per >= c || per > item_cap) per = item_cap;
                 for (int ch = 0; ch < nch; ch++) {
                     const int i = cb + ex_b + ch;
                     item_list[i] = l;
@@ -127,10 +135,13 @@ make_idesc_tf32(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 }
 
-template <int METRIC>
+template <int METRIC, int BROWS>
 __global__ void __launch_bounds__(THREADS, 1)
 ivfflat_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_qhi,
                   const __grid_constant__ CUtensorMap tmap_qlo, Params p) {
+    using C = FlCfg<BROWS>;
+    constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, B_TILE_BYTES = C::B_TILE_BYTES, OFF_META = C::OFF_META,
+                  OFF_BAR = C::OFF_BAR;
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t raw = tc::smem_u32(smem_dyn);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -186,10 +197,10 @@ ivfflat_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                         const int s = it % STAGES;
                         pqtc::mbar_wait_g(bar_empty(s), ((it / STAGES) & 1u) ^ 1u);
                         const uint32_t st = base + (uint32_t)s * STAGE_BYTES;
-                        tc::mbar_expect_tx(bar_full_raw(s), 3 * TILE_BYTES);
+                        tc::mbar_expect_tx(bar_full_raw(s), TILE_BYTES + 2 * B_TILE_BYTES);
                         tc::tma_load_2d(st, &tmap_x, kb * BK, (int)(off + (int64_t)t * TM), bar_full_raw(s));
                         tc::tma_load_2d(st + 2 * TILE_BYTES, &tmap_qhi, kb * BK, q0, bar_full_raw(s));
-                        tc::tma_load_2d(st + 3 * TILE_BYTES, &tmap_qlo, kb * BK, q0, bar_full_raw(s));
+                        tc::tma_load_2d(st + 2 * TILE_BYTES + B_TILE_BYTES, &tmap_qlo, kb * BK, q0, bar_full_raw(s));
                     }
                 }
             }
@@ -218,7 +229,7 @@ ivfflat_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                             const uint64_t a_hi = tc::make_desc(st + ko);
                             const uint64_t a_lo = tc::make_desc(st + TILE_BYTES + ko);
                             const uint64_t b_hi = tc::make_desc(st + 2 * TILE_BYTES + ko);
-                            const uint64_t b_lo = tc::make_desc(st + 3 * TILE_BYTES + ko);
+                            const uint64_t b_lo = tc::make_desc(st + 2 * TILE_BYTES + B_TILE_BYTES + ko);
                             tc::tc_mma_tf32(d_t, a_hi, b_hi, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
                             tc::tc_mma_tf32(d_t, a_hi, b_lo, idesc, 1u);
                             tc::tc_mma_tf32(d_t, a_lo, b_hi, idesc, 1u);

@@ -498,14 +498,24 @@ ivfpq_tc_filter_kernel(Params p) {
                 const uint32_t taddr0 = tmem_base + ((uint32_t)(we * 32) << 16) + (uint32_t)(eg * 256);
                 uint32_t masks[8];
                 uint32_t va[32], vb[32];
+                // D >= 0  <=>  sign bit clear.  Two-level test with short dependency chains (the serial OR-chain of a naive
+                // mask build was the epilogue's critical path): 8 independent 4-way ANDs, a 3-deep AND tree over them for the
+                // common "nothing passes" exit, and on a hit only the groups whose AND has a clear sign bit are expanded.
                 auto scan_chunk = [&](const uint32_t (&v)[32]) -> uint32_t {
-                    uint32_t a = v[0];
+                    uint32_t g[8];
 #pragma unroll
-                    for (int u = 1; u < 32; u++) a &= v[u];
-                    if ((int32_t)a < 0) return 0u;   // all 32 sign bits set: nothing passes
+                    for (int i = 0; i < 8; i++) g[i] = (v[4 * i] & v[4 * i + 1]) & (v[4 * i + 2] & v[4 * i + 3]);
+                    const uint32_t all = ((g[0] & g[1]) & (g[2] & g[3])) & ((g[4] & g[5]) & (g[6] & g[7]));
+                    if ((int32_t)all < 0) return 0u;   // all 32 sign bits set: nothing passes
                     uint32_t m = 0;
 #pragma unroll
-                    for (int u = 0; u < 32; u++) m |= ((~v[u]) >> 31) << u;
+                    for (int i = 0; i < 8; i++) {
+                        if ((int32_t)g[i] >= 0) {
+                            const uint32_t b0 = (~v[4 * i]) >> 31, b1 = (~v[4 * i + 1]) >> 31;
+                            const uint32_t b2 = (~v[4 * i + 2]) >> 31, b3 = (~v[4 * i + 3]) >> 31;
+                            m |= ((b0 | (b1 << 1)) | ((b2 << 2) | (b3 << 3))) << (4 * i);
+                        }
+                    }
                     return m;
                 };
                 // software pipeline over the chunks: the TMEM load of chunk ci+1 is in flight while chunk ci is tested
@@ -839,17 +849,16 @@ exact_eval_kernel(const float* __restrict__ queries, const float* __restrict__ p
     }
 }
 
-// queries whose nearest list is owned by this rank (list l lives on rank l % world) -> compact list: this rank runs their
-// phase A (one CTA; order is irrelevant)
+// queries whose nearest list is owned by this rank -> compact list: this rank runs their phase A (one CTA; order is irrelevant)
 __global__ void __launch_bounds__(1024)
-compact_resp_kernel(const int64_t* __restrict__ probe_ids, int nprobe, int64_t nq, int world, int rank, int32_t* __restrict__ list,
-                    uint32_t* __restrict__ count) {
+compact_resp_kernel(const int64_t* __restrict__ probe_ids, int nprobe, int64_t nq, const int32_t* __restrict__ list_owner, int rank,
+                    int32_t* __restrict__ list, uint32_t* __restrict__ count) {
     __shared__ uint32_t s_n;
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
     for (int64_t q = threadIdx.x; q < nq; q += 1024) {
         const int64_t l = probe_ids[q * nprobe];
-        if (l >= 0 && (int)(l % world) == rank) list[atomicAdd(&s_n, 1u)] = (int32_t)q;
+        if (l >= 0 && list_owner[l] == rank) list[atomicAdd(&s_n, 1u)] = (int32_t)q;
     }
     __syncthreads();
     if (threadIdx.x == 0) *count = s_n;

@@ -404,7 +404,10 @@ serialize_index(IndexBase& ix, std::vector<uint8_t>& blob) {
         w.put<int64_t>(iv->nlist);
         w.put<int32_t>(iv->M);
         w.put<int32_t>(iv->nbits);
-        w.put<int32_t>(iv->refine ? 1 : 0);
+        w.put<int32_t>(iv->refine ? 1 + iv->refine_kind : 0);   // 0 none, 1 fp32, 2 fp16, 3 bf16 refine store
+        DevBuf<float> dec;
+        const float* v32 = (iv->is_pq && iv->refine) ? iv->vecs_f32(dec) : nullptr;
+        if (v32) KB2_CUDA_CHECK(cudaStreamSynchronize(iv->stream));
         std::vector<float> c((size_t)iv->nlist * ix.dim);
         KB2_CUDA_CHECK(cudaMemcpy(c.data(), iv->centroids.p, c.size() * 4, cudaMemcpyDeviceToHost));
         w.put_bytes(c.data(), c.size() * 4);
@@ -425,8 +428,7 @@ serialize_index(IndexBase& ix, std::vector<uint8_t>& blob) {
             w.put_bytes(cd.data(), cd.size());
             if (iv->is_pq && iv->refine) {
                 std::vector<float> rv((size_t)len * ix.dim);
-                KB2_CUDA_CHECK(cudaMemcpy(rv.data(), iv->vecs.p + iv->h_list_off[l] * ix.dim, rv.size() * 4,
-                                          cudaMemcpyDeviceToHost));
+                KB2_CUDA_CHECK(cudaMemcpy(rv.data(), v32 + iv->h_list_off[l] * ix.dim, rv.size() * 4, cudaMemcpyDeviceToHost));
                 w.put_bytes(rv.data(), rv.size() * 4);
             }
         }
@@ -475,7 +477,12 @@ deserialize_index(const uint8_t* blob, size_t size, int device) {
         const int64_t nlist = r.get<int64_t>();
         iv->M = r.get<int32_t>();
         iv->nbits = r.get<int32_t>();
-        iv->refine = r.get<int32_t>() != 0;
+        {
+            const int rf = r.get<int32_t>();
+            KB2_REQUIRE(rf >= 0 && rf <= 3, KB2_INVALID_BINARY_SET, "bad refine field in blob");
+            iv->refine = rf != 0;
+            iv->refine_kind = rf ? rf - 1 : 0;
+        }
         KB2_REQUIRE(nlist >= 1 && (uint64_t)nlist <= size / ((size_t)dim * 4), KB2_INVALID_BINARY_SET, "bad nlist in blob");
         if (iv->is_pq)
             KB2_REQUIRE(iv->M > 0 && dim % iv->M == 0 && iv->nbits == 8, KB2_INVALID_BINARY_SET, "bad m / nbits in blob");

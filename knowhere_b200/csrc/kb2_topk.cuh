@@ -7,6 +7,7 @@
 // with the k-th distance; the final ordering (distance, then id) is identical
 // (heap_reorder, F/utils/Heap.h; F/IndexIVF.cpp:484-494).
 #pragma once
+#include <cuda_fp16.h>
 #include <float.h>
 
 #include "kb2_common.cuh"
@@ -226,6 +227,8 @@ struct FinalizeParams {
     const int64_t* labels;     // row -> label (NULL: identity)
     int rerank;                // 1: recompute keys exactly from `raw`
     const float* raw;          // [*][d] fp32
+    const uint16_t* raw16;     // or [*][d] fp16 / bf16 (refine_type fp16 / bf16: src/index/refine/refine_utils.cc:99-160); NULL: use raw
+    int raw16_kind;            // 1 fp16, 2 bf16
     int raw_by_pos;            // 1: raw indexed by pos, 0: by row
     const float* queries;      // [nq][d]
     int d;
@@ -284,15 +287,29 @@ finalize_kernel(FinalizeParams p) {
             uint32_t pos = s_pos[i];
             if (pos == kNoPos) continue;
             int64_t r = p.raw_by_pos ? (int64_t)pos : (p.rows ? (int64_t)p.rows[pos] : (int64_t)pos);
-            const float* x = p.raw + r * (int64_t)p.d;
             float acc = 0.f;
-            if (p.metric == KB2_METRIC_L2) {
+            if (p.raw16) {
+                const uint16_t* x16 = p.raw16 + r * (int64_t)p.d;
                 for (int j = lane; j < p.d; j += kWarp) {
-                    float t = s_q[j] - x[j];
-                    acc = fmaf(t, t, acc);
+                    const float xv = (p.raw16_kind == 1) ? __half2float(__ushort_as_half(x16[j]))
+                                                         : __uint_as_float((uint32_t)x16[j] << 16);
+                    if (p.metric == KB2_METRIC_L2) {
+                        const float t = s_q[j] - xv;
+                        acc = fmaf(t, t, acc);
+                    } else {
+                        acc = fmaf(s_q[j], xv, acc);
+                    }
                 }
             } else {
-                for (int j = lane; j < p.d; j += kWarp) acc = fmaf(s_q[j], x[j], acc);
+                const float* x = p.raw + r * (int64_t)p.d;
+                if (p.metric == KB2_METRIC_L2) {
+                    for (int j = lane; j < p.d; j += kWarp) {
+                        float t = s_q[j] - x[j];
+                        acc = fmaf(t, t, acc);
+                    }
+                } else {
+                    for (int j = lane; j < p.d; j += kWarp) acc = fmaf(s_q[j], x[j], acc);
+                }
             }
             acc = warp_sum(acc);
             if (lane == 0) s_key[i] = (p.metric == KB2_METRIC_L2) ? acc : -acc;

@@ -59,6 +59,22 @@ for (d, nlist, m, nq, nprobe, tag) in [(64, 128, 16, 500, 16, "lut engine"), (12
     print(f"rank {rank} [{tag}, engine {eng}]: merged==unsharded rows {same_rows:.4f} ok={ok}", flush=True)
     ok_all = ok_all and ok
     del sh, ref_ix, full
+# HNSW graph-partition sharding: every rank builds a sub-graph over its row slice; the collective search merges the shards
+n, d, M, k = 20000, 64, 16, 10
+xb, xq = datagen.clustered(n, d, 5), datagen.clustered(200, d, 6)
+hs = kb.Index("HNSW", "L2", d, {"M": M, "efConstruction": 100}, device=rank)
+hs.set_shard(rank, world)
+hs.add(xb)
+assert hs.count() == n // world
+hs.set_comm(comm)
+hi, hd = hs.search(xq, k, {"ef": 64})
+gt, _ = kb.brute_force_search(xb, xq, k, "L2", device=rank)
+rec = np.mean([len(set(a) & set(b)) / k for a, b in zip(hi, gt)])
+mask = np.zeros(n, bool); mask[::3] = True
+fi, _ = hs.search(xq, k, {"ef": 64}, bitset=np.packbits(mask, bitorder="little"))
+ok_h = rec > 0.9 and not mask[fi[fi >= 0]].any() and (np.diff(hd, axis=1) >= 0).all()
+print(f"rank {rank} [hnsw graph partitions]: recall {rec:.3f} ok={ok_h}", flush=True)
+ok_all = ok_all and ok_h
 dist.barrier(); dist.destroy_process_group()
 sys.exit(0 if ok_all else 3)
 '''
