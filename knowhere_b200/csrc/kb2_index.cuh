@@ -183,8 +183,8 @@ struct IndexBase {
         KB2_CUDA_CHECK(cudaEventCreate(&ev3));
         KB2_CUDA_CHECK(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
         for (cudaEvent_t* e : {&ev_c0, &ev_c1, &ev_c2, &ev_c3}) KB2_CUDA_CHECK(cudaEventCreate(e));
-        d_counter.ensure(8);
-        h_counter.ensure(64);
+        d_counter.ensure(16);
+        h_counter.ensure(128);
     }
     void
     set_stream(cudaStream_t s) {
@@ -835,6 +835,30 @@ struct IvfIndex : IndexBase {
     // engine instances: <G=1, dsub=8> (m16 d128: C3) and <G=3, dsub=2> (m48 d96: C5)
     bool tc_geom_18() const { return G == 1 && M == 16 && dsub == 8; }
     bool tc_geom_32() const { return G == 3 && M == 48 && dsub == 2; }
+    DevBuf<int32_t> s_items2, s_bal_idx, s_bal_idx2;
+    DevBuf<uint32_t> s_bal_key, s_bal_key2;
+    // sort the items by descending cost and deal them to the G persistent CTAs in snake order; returns the new item arrays
+    int32_t*
+    balance_items(int32_t* items, int64_t max_items, int G_ctas, int tile_cost, int col_cost) {
+        cudaStream_t st = stream;
+        const char* e = getenv("KB2_TC_BALANCE");
+        if (e && atoi(e) == 0) return items;
+        s_items2.ensure((size_t)3 * max_items);
+        s_bal_key.ensure((size_t)max_items); s_bal_key2.ensure((size_t)max_items);
+        s_bal_idx.ensure((size_t)max_items); s_bal_idx2.ensure((size_t)max_items);
+        pqtc::item_cost_kernel<<<grid1d(max_items, 256), 256, 0, st>>>(s_plan_out.p, items, items + 2 * max_items, list_len.p, max_items,
+                                                                     tile_cost, col_cost, s_bal_key.p, s_bal_idx.p);
+        size_t tmp_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, s_bal_key.p, s_bal_key2.p, s_bal_idx.p, s_bal_idx2.p, (int)max_items, 0, 32, st);
+        s_sort_tmp.ensure(tmp_bytes);
+        cub::DeviceRadixSort::SortPairs(s_sort_tmp.p, tmp_bytes, s_bal_key.p, s_bal_key2.p, s_bal_idx.p, s_bal_idx2.p, (int)max_items, 0, 32, st);
+        pqtc::deal_items_kernel<<<grid1d(max_items, 256), 256, 0, st>>>(s_plan_out.p, s_bal_idx2.p, G_ctas, items, items + max_items,
+                                                                      items + 2 * max_items, s_items2.p, s_items2.p + max_items,
+                                                                      s_items2.p + 2 * max_items);
+        last.launches += 4;
+        return s_items2.p;
+    }
+
     bool
     use_tc_engine(int64_t nq, int nprobe, int Ksel) const {
         if (!is_pq || !(tc_geom_18() || tc_geom_32())) return false;
@@ -963,6 +987,13 @@ struct IvfIndex : IndexBase {
         int32_t* item_q0 = s_items.p + max_items;
         int32_t* item_nq = s_items.p + 2 * max_items;
         pqtc::plan_kernel<<<1, 1024, 0, st>>>(s_lcount.p, (int)nlist, s_lstart.p, item_list, item_q0, item_nq, s_plan_out.p);
+        {
+            // per tile: decode ~ constant, contraction ~ columns (+ the test K-step)
+            int32_t* bal = balance_items(s_items.p, max_items, kNumSMs, 600, 5);
+            item_list = bal;
+            item_q0 = bal + max_items;
+            item_nq = bal + 2 * max_items;
+        }
         pqtc::fill_pairs_kernel<<<grid1d(npairs, 256), 256, 0, st>>>(sp.probe_ids, sp.probe_dis, npairs, nprobe, metric, list_len.p,
                                                                      s_lstart.p, s_lcount.p + nlist, s_pair_q.p, s_pair_base.p);
         pqtc::prepare_queries_kernel<<<grid1d(nq * 32, 256), 256, 0, st>>>(sp.queries, nq, dim, (__nv_bfloat16*)s_qb16.p, s_qnorm.p);
@@ -1129,6 +1160,12 @@ struct IvfIndex : IndexBase {
         int32_t* item_q0 = s_items.p + max_items;
         int32_t* item_nq = s_items.p + 2 * max_items;
         fltc::plan_kernel<<<1, 1024, 0, st>>>(s_lcount.p, (int)nlist, item_cap, s_lstart.p, item_list, item_q0, item_nq, s_plan_out.p);
+        {
+            int32_t* bal = balance_items(s_items.p, max_items, kNumSMs, 1000, 2);   // a tile is bound by its HBM stream
+            item_list = bal;
+            item_q0 = bal + max_items;
+            item_nq = bal + 2 * max_items;
+        }
         pqtc::fill_pairs_kernel<<<grid1d(npairs, 256), 256, 0, st>>>(sp.probe_ids, sp.probe_dis, npairs, nprobe, metric, list_len.p,
                                                                      s_lstart.p, s_lcount.p + nlist, s_pair_q.p, s_pair_base.p);
         // pairs of lists owned by other shards leave holes at the end of the pair array: point them at no query
@@ -1186,10 +1223,131 @@ struct IvfIndex : IndexBase {
 
     // coarse quantizer for queries [q_lo, q_hi): top-nprobe centroids with exact dis0 (F/IndexIVF.cpp:336-342) into rows
     // [q_lo, q_hi) of s_probe_ids / s_probe_dis
+    // Coarse stage on the list-major tensor-core kernel: the centroid table is ONE pseudo-list scanned by every query, i.e. an
+    // IVF_FLAT search with k = nprobe + 16.  The admission bound comes from a sample (the first nlist/8 centroids through the
+    // dense path: its k'-th best key, k' = 2x the expected share + 8), so the kernel logs ~2(nprobe+16) candidates per query
+    // instead of writing the [nq][nlist] key matrix that a separate selection kernel had to read back.  The bound is a
+    // heuristic, so it is CHECKED: a query with fewer than nprobe + 16 candidates raises a counter and the caller repeats
+    // the search with the dense path (counter slot 8; never observed on the benchmark shapes).
+    bool coarse_tc_disabled = false;
+    DevBuf<float> s_cbound;
+    DevBuf<int64_t> s_coff;
+    DevBuf<int32_t> s_clen;
+    bool
+    use_coarse_tc(int64_t m, int nprobe) const {
+        const char* e = getenv("KB2_COARSE");
+        if (coarse_tc_disabled || (e && !strcmp(e, "dense"))) return false;
+        if (dim % fltc::BK != 0 || nlist < 1024 || nprobe + 16 > 256 || nprobe + 16 > nlist / 8) return false;
+        if (e && !strcmp(e, "tc")) return m >= 296;
+        return m >= 1024;
+    }
+    void
+    coarse_probes_tc(const float* Q, int64_t m, int nprobe, int64_t* out_ids, float* out_dis) {
+        cudaStream_t st = stream;
+        const int need = nprobe + 16;
+        // ---- sample bound
+        const int64_t ns = std::max<int64_t>(512, (nlist / 8 + 127) / 128 * 128);
+        const int k_sample = (int)std::min<int64_t>(ns, 2 * ((int64_t)need * ns + nlist - 1) / nlist + 8);
+        DensePlan pl = dense_candidates(*this, Q, m, centroids.p, cnorms.p, ns, dim, metric, std::max(k_sample, 17) - 16 + 16, nullptr, nullptr);
+        KB2_REQUIRE(k_sample <= pl.Ksel, KB2_INTERNAL_ERROR, "coarse sample selection too small");
+        s_cbound.ensure((size_t)m);
+        fltc::extract_bound_kernel<<<grid1d(m, 256), 256, 0, st>>>(s_partial.p, pl.stride(), k_sample, m, s_cbound.p);
+        // ---- items: chunks of consecutive queries over the single pseudo-list [0, nlist)
+        const int item_cap = (m / 128 < 2 * kNumSMs) ? 32 : 128;
+        const int64_t n_it = (m + item_cap - 1) / item_cap;
+        const int64_t npairs_pad = m + fltc::NQ_ITEM;
+        s_items.ensure((size_t)3 * n_it);
+        s_plan_out.ensure(4);
+        s_pair_q.ensure((size_t)m);
+        s_qnorm.ensure((size_t)m);
+        s_cand.ensure((size_t)m * kTcCandCap);
+        s_cand_cnt.ensure((size_t)2 * m + 4);
+        s_qhi.ensure((size_t)npairs_pad * dim);
+        s_qlo.ensure((size_t)npairs_pad * dim);
+        if (s_coff.n < 1) {
+            s_coff.ensure(1);
+            s_clen.ensure(1);
+        }
+        const int64_t h_off = 0;
+        const int32_t h_len = (int32_t)nlist;
+        KB2_CUDA_CHECK(cudaMemcpyAsync(s_coff.p, &h_off, 8, cudaMemcpyHostToDevice, st));
+        KB2_CUDA_CHECK(cudaMemcpyAsync(s_clen.p, &h_len, 4, cudaMemcpyHostToDevice, st));
+        KB2_CUDA_CHECK(cudaMemsetAsync(s_cand_cnt.p, 0, ((size_t)2 * m + 4) * 4, st));
+        int32_t* item_list = s_items.p;
+        int32_t* item_q0 = s_items.p + n_it;
+        int32_t* item_nq = s_items.p + 2 * n_it;
+        fltc::uniform_items_kernel<<<grid1d(std::max<int64_t>(m, n_it), 256), 256, 0, st>>>(m, item_cap, item_list, item_q0, item_nq,
+                                                                                         s_plan_out.p, s_pair_q.p);
+        fltc::gather_split_queries_kernel<<<grid1d(npairs_pad * 32, 256), 256, 0, st>>>(Q, s_pair_q.p, m, npairs_pad, dim, s_qhi.p, s_qlo.p);
+        row_norms_kernel<<<grid1d(m * 32, 256), 256, 0, st>>>(Q, m, dim, s_qnorm.p);
+        CUtensorMap tx, thi, tlo;
+        KB2_REQUIRE(tc::make_tmap(&tx, centroids.p, nlist, dim) && tc::make_tmap(&thi, s_qhi.p, npairs_pad, dim, item_cap) &&
+                        tc::make_tmap(&tlo, s_qlo.p, npairs_pad, dim, item_cap),
+                    KB2_INTERNAL_ERROR, "coarse tensor-core stage: tensor map encoding failed");
+        fltc::Params fpar{};
+        fpar.metric = metric;
+        fpar.d = dim;
+        fpar.n_items = s_plan_out.p;
+        fpar.item_list = item_list;
+        fpar.item_q0 = item_q0;
+        fpar.item_nq = item_nq;
+        fpar.pair_q = s_pair_q.p;
+        fpar.qnorm2 = s_qnorm.p;
+        fpar.bound = s_cbound.p;
+        fpar.list_off = s_coff.p;
+        fpar.list_len = s_clen.p;
+        fpar.xnorm2 = cnorms.p;
+        fpar.bitset = nullptr;
+        fpar.rows = nullptr;
+        const int grid = (int)std::min<int64_t>(kNumSMs, n_it);
+        const uint32_t log_cap = (uint32_t)std::min<int64_t>(std::max<int64_t>(m * 1024 / grid, 32768), 1 << 20);
+        s_log.ensure((size_t)kNumSMs * log_cap);
+        s_logcnt.ensure(kNumSMs + 8);
+        KB2_CUDA_CHECK(cudaMemsetAsync(s_logcnt.p, 0, (kNumSMs + 8) * 4, st));
+        fpar.log = s_log.p;
+        fpar.log_cnt = s_logcnt.p;
+        fpar.log_cap = log_cap;
+        fpar.counters = nullptr;
+#define KB2_FL_LAUNCH(MM, BR) \
+    fltc::ivfflat_tc_kernel<MM, BR><<<grid, fltc::THREADS, fltc::FlCfg<BR>::SMEM_BYTES, st>>>(tx, thi, tlo, fpar);
+        if (metric == KB2_METRIC_L2) {
+            if (item_cap == 32) { KB2_FL_LAUNCH(KB2_METRIC_L2, 32) } else { KB2_FL_LAUNCH(KB2_METRIC_L2, 128) }
+        } else {
+            if (item_cap == 32) { KB2_FL_LAUNCH(KB2_METRIC_IP, 32) } else { KB2_FL_LAUNCH(KB2_METRIC_IP, 128) }
+        }
+#undef KB2_FL_LAUNCH
+        KB2_CUDA_CHECK(cudaGetLastError());
+        uint32_t* qflag = s_cand_cnt.p + m;
+        fltc::scatter_kernel<<<dim3(16, grid), 256, 0, st>>>(s_log.p, s_logcnt.p, log_cap, s_cand.p, s_cand_cnt.p, kTcCandCap, qflag);
+        fltc::check_counts_kernel<<<grid1d(m, 256), 256, 0, st>>>(s_cand_cnt.p, qflag, m, (uint32_t)std::min<int64_t>(need, nlist),
+                                                                s_logcnt.p + grid, d_counter.p + 8);
+        last.launches += 8;
+        FinalizeParams fp{};
+        fp.partial = s_cand.p;
+        fp.partial_stride = kTcCandCap;
+        fp.n_partial = kTcCandCap;
+        fp.counts = s_cand_cnt.p;
+        fp.k_sel = (int)std::min<int64_t>(need, nlist);
+        fp.k_out = nprobe;
+        fp.rerank = 1;
+        fp.raw = centroids.p;
+        fp.raw_by_pos = 1;
+        fp.queries = Q;
+        fp.d = dim;
+        fp.metric = metric;
+        fp.out_ids = out_ids;
+        fp.out_dist = out_dis;
+        launch_finalize(*this, fp, m);
+    }
+
     void
     coarse_probes(const float* dq, int64_t q_lo, int64_t q_hi, int nprobe) {
         const int64_t m = q_hi - q_lo;
         if (m <= 0) return;
+        if (!distributed() && use_coarse_tc(m, nprobe)) {
+            coarse_probes_tc(dq + q_lo * dim, m, nprobe, s_probe_ids.p + q_lo * nprobe, s_probe_dis.p + q_lo * nprobe);
+            return;
+        }
         DensePlan pl = dense_candidates(*this, dq + q_lo * dim, m, centroids.p, cnorms.p, nlist, dim, metric, nprobe + 16, nullptr,
                                         nullptr);
         FinalizeParams fp{};
@@ -1240,6 +1398,7 @@ struct IvfIndex : IndexBase {
             d_dist = s_out_dist.p;
         }
 
+        KB2_CUDA_CHECK(cudaMemsetAsync(d_counter.p + 8, 0, 8, st));
         // ---- coarse quantizer.  With a communicator every rank ranks the centroids for its slice of the batch only and the
         //      probe lists are all-gathered (in place; slices padded to the same length).
         const int64_t per = dist ? (nq + shard_world - 1) / shard_world : nq;
@@ -1367,9 +1526,23 @@ struct IvfIndex : IndexBase {
             last.launches += 3;
         }
         unsigned long long* hc = (unsigned long long*)h_counter.p;
-        KB2_CUDA_CHECK(cudaMemcpyAsync(hc, d_counter.p, 64, cudaMemcpyDeviceToHost, st));
+        KB2_CUDA_CHECK(cudaMemcpyAsync(hc, d_counter.p, 72, cudaMemcpyDeviceToHost, st));
         results_out(nq, k, out_ids, out_dist, d_ids, d_dist);
         KB2_REQUIRE(hc[1] == 0 && hc[5] == 0, KB2_INTERNAL_ERROR, "ivfpq_scan_kernel: unexpected shared-memory window base");
+        if (hc[8] != 0 && !coarse_tc_disabled) {
+            // the sampled admission bound of the tensor-core coarse stage left some query short of candidates: repeat the
+            // whole search with the dense coarse path (results of this pass are discarded)
+            coarse_tc_disabled = true;
+            try {
+                search(q, nq, k, cfg, bitset, nbits, out_ids, out_dist);
+            } catch (...) {
+                coarse_tc_disabled = false;
+                throw;
+            }
+            coarse_tc_disabled = false;
+            last.flagged += (int64_t)hc[8];
+            return;
+        }
         last.survivors = (int64_t)hc[2];
         last.flagged = (int64_t)hc[7];
         const unsigned long long scanned = hc[0];

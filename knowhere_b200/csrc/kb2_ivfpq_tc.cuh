@@ -647,6 +647,41 @@ plan_kernel(const int32_t* __restrict__ lcount, int nlist, int32_t* __restrict__
     if (threadIdx.x == 0) *n_items = carry_b;
 }
 
+// ---- static load balancing of the persistent kernels.  CTA b processes items b, b + G, b + 2G, ...; in list order the per-CTA
+// totals differ by +-30 % (list length x queries per list has a heavy tail), and the launch lasts as long as its slowest CTA.
+// Items are therefore sorted by descending cost estimate and dealt out in snake order (round r forwards, round r+1
+// backwards), the classic longest-processing-time deal.
+__global__ void
+item_cost_kernel(const int32_t* __restrict__ n_items, const int32_t* __restrict__ item_list, const int32_t* __restrict__ item_nq,
+                 const int32_t* __restrict__ list_len, int64_t max_items, int tile_cost, int col_cost, uint32_t* __restrict__ key,
+                 int32_t* __restrict__ idx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= max_items) return;
+    uint32_t k = 0xffffffffu;   // unused slots sort to the end
+    if (i < *n_items) {
+        const long long tiles = (list_len[item_list[i]] + TM - 1) / TM;
+        const long long c = tiles * (tile_cost + (long long)col_cost * ((item_nq[i] + 15) & ~15));
+        k = 0xfffffffeu - (uint32_t)min(c, 0xfffffff0ll);   // ascending key = descending cost
+    }
+    key[i] = k;
+    idx[i] = (int32_t)i;
+}
+__global__ void
+deal_items_kernel(const int32_t* __restrict__ n_items, const int32_t* __restrict__ sorted_idx, int G, const int32_t* __restrict__ in_list,
+                  const int32_t* __restrict__ in_q0, const int32_t* __restrict__ in_nq, int32_t* __restrict__ out_list,
+                  int32_t* __restrict__ out_q0, int32_t* __restrict__ out_nq) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;   // rank by descending cost
+    const int n = *n_items;
+    if (j >= n) return;
+    const int r = j / G, b = j % G;
+    const bool full_round = (r + 1) * G <= n;
+    const int dst = r * G + (((r & 1) && full_round) ? (G - 1 - b) : b);
+    const int src = sorted_idx[j];
+    out_list[dst] = in_list[src];
+    out_q0[dst] = in_q0[src];
+    out_nq[dst] = in_nq[src];
+}
+
 __global__ void
 fill_pairs_kernel(const int64_t* __restrict__ probe_ids, const float* __restrict__ probe_dis, int64_t npairs, int nprobe,
                   int metric, const int32_t* __restrict__ list_len, const int32_t* __restrict__ lstart,

@@ -283,7 +283,42 @@ finalize_kernel(FinalizeParams p) {
 
     if (p.rerank) {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        for (int i = warp; i < ksel; i += (blockDim.x >> 5)) {
+        const int nwarps = blockDim.x >> 5;
+        if (!p.raw16 && (p.d & 3) == 0 && (reinterpret_cast<uintptr_t>(p.raw) & 15) == 0) {
+            // four candidates per warp at a time (8 lanes each, 128 B per candidate and step): the re-rank is a chain of
+            // dependent random-row round trips (L2 / HBM), so candidates in flight per warp are what sets its duration
+            const int sub = lane & 7, grp = lane >> 3;
+            const float4* q4 = reinterpret_cast<const float4*>(s_q);
+            for (int i0 = warp * 4; i0 < ksel; i0 += nwarps * 4) {
+                const int i = i0 + grp;
+                const uint32_t pos = (i < ksel) ? s_pos[i] : kNoPos;
+                float acc = 0.f;
+                if (pos != kNoPos) {
+                    const int64_t r = p.raw_by_pos ? (int64_t)pos : (p.rows ? (int64_t)p.rows[pos] : (int64_t)pos);
+                    const float4* x4 = reinterpret_cast<const float4*>(p.raw + r * (int64_t)p.d);
+                    for (int j = sub; j < (p.d >> 2); j += 8) {
+                        const float4 xv = __ldg(x4 + j);
+                        const float4 qv = q4[j];
+                        if (p.metric == KB2_METRIC_L2) {
+                            float t;
+                            t = qv.x - xv.x; acc = fmaf(t, t, acc);
+                            t = qv.y - xv.y; acc = fmaf(t, t, acc);
+                            t = qv.z - xv.z; acc = fmaf(t, t, acc);
+                            t = qv.w - xv.w; acc = fmaf(t, t, acc);
+                        } else {
+                            acc = fmaf(qv.x, xv.x, acc); acc = fmaf(qv.y, xv.y, acc);
+                            acc = fmaf(qv.z, xv.z, acc); acc = fmaf(qv.w, xv.w, acc);
+                        }
+                    }
+                }
+                acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                if (sub == 0 && pos != kNoPos) s_key[i] = (p.metric == KB2_METRIC_L2) ? acc : -acc;
+            }
+            __syncthreads();
+        } else {
+        for (int i = warp; i < ksel; i += nwarps) {
             uint32_t pos = s_pos[i];
             if (pos == kNoPos) continue;
             int64_t r = p.raw_by_pos ? (int64_t)pos : (p.rows ? (int64_t)p.rows[pos] : (int64_t)pos);
@@ -315,6 +350,7 @@ finalize_kernel(FinalizeParams p) {
             if (lane == 0) s_key[i] = (p.metric == KB2_METRIC_L2) ? acc : -acc;
         }
         __syncthreads();
+        }
     }
 
     // rank by (key, label, slot)
