@@ -59,6 +59,9 @@ struct HnswSearchParams {
     int queue_cap;
     uint32_t* q_overflow;       // range: [nq] 1 = the BFS queue overflowed (host reruns that query with a larger queue)
     const int32_t* q_list;      // optional: indices of the queries to run (second pass), nq = its length
+    // construction (hnsw_search_kernel as the candidate generator of the batched GPU build)
+    int beam_level;             // level the beam runs on (0 for searches); the greedy descent stops above it
+    const int32_t* q_nodes;     // optional: query i is the stored vector of node q_nodes[i]
 };
 
 constexpr int kHnswWarps = 4;  // warps (queries in flight) per CTA
@@ -181,7 +184,7 @@ template <int METRIC>
 __device__ __forceinline__ void
 hnsw_descend(const HnswSearchParams& p, const float* s_q, int lane, int32_t& nearest, float& d_nearest,
              unsigned long long& ndis_tot, unsigned long long& nhops_tot) {
-    for (int level = p.max_level; level >= 1; level--) {
+    for (int level = p.max_level; level > p.beam_level; level--) {
         for (;;) {
             const int32_t prev = nearest;
             const int64_t begin = p.offsets[prev] + p.cum[level];
@@ -249,7 +252,10 @@ hnsw_search_kernel(HnswSearchParams p) {
         if (lane == 0) q = atomicAdd(p.next_query, 1);
         q = __shfl_sync(0xffffffffu, q, 0);
         if (q >= p.nq) break;
-        for (int j = lane; j < p.d; j += kWarp) s_q[j] = p.queries[(int64_t)q * p.d + j];
+        {
+            const float* qsrc = p.q_nodes ? p.vecs + (int64_t)p.q_nodes[q] * p.d : p.queries + (int64_t)q * p.d;
+            for (int j = lane; j < p.d; j += kWarp) s_q[j] = qsrc[j];
+        }
         __syncwarp();
 
         // ---- greedy descent on the upper levels (HnswSearcher.h:116-170,334-356)
@@ -281,8 +287,8 @@ hnsw_search_kernel(HnswSearchParams p) {
             while (cursor < size && (s_id[cursor] & 0x80000000u)) cursor++;
             nhops_tot++;
 
-            const int64_t begin = p.offsets[cur_id] + p.cum[0];
-            const int64_t end = p.offsets[cur_id] + p.cum[1];
+            const int64_t begin = p.offsets[cur_id] + p.cum[p.beam_level];
+            const int64_t end = p.offsets[cur_id] + p.cum[p.beam_level + 1];
             bool done = false;
             for (int64_t b = begin; b < end && !done; b += kWarp) {
                 const int32_t v = (b + lane < end) ? p.neighbors[b + lane] : -1;
@@ -740,6 +746,182 @@ hnsw_filtered_kernel(HnswSearchParams p) {
     if (p.stats && lane == 0) {
         atomicAdd(&p.stats[0], ndis_tot);
         atomicAdd(&p.stats[1], nhops_tot);
+    }
+}
+
+
+// ============================================================================================
+// GPU construction (reference: K/IndexHNSW.cpp:83-215 hnsw_add_vertices, K/impl/HNSW.cpp:231-300
+// shrink_neighbor_list, :302-420 add_links_starting_from).  The reference inserts one node at a time under per-node locks;
+// here every level is built by BATCHED insertion in the reference's order (levels descending): for a batch of new nodes
+//   1. hnsw_search_kernel (beam on that level, ef = efConstruction, entry from the finished upper levels) -> candidates
+//   2. hnsw_select_kernel: the heuristic of shrink_neighbor_list (keep c unless some kept s has dist(c,s) < dist(c,q))
+//   3. hnsw_link_kernel: reverse links under a per-node spin lock; a full row is re-shrunk with the same heuristic
+// Nodes of one batch do not see each other; batches grow with the graph (<= 1/4 of it), so the effect is that of a few
+// concurrent inserters in the reference.  Graphs are not bit-identical to the reference's (they are not reproducible
+// run-to-run there either); recall parity is what the tests hold.
+// ============================================================================================
+struct HnswBuildParams {
+    const float* vecs;
+    int d, metric, level;
+    int32_t* neighbors;
+    const int64_t* offsets;
+    const int32_t* cum;
+    const int32_t* batch;        // [nb] node ids being inserted
+    int nb, ef;
+    const int64_t* cand_ids;     // [nb][ef] ascending by key (from the search kernel), -1 padded
+    const float* cand_dist;      // [nb][ef] distances as Search reports them (IP un-negated)
+    int32_t* sel_ids;            // [nb][64] selected neighbours of each new node (for the link pass)
+    int32_t* sel_cnt;            // [nb]
+    int32_t* locks;              // [n]
+};
+constexpr int kBuildWarps = 4;
+
+// keep candidate c (key kc to the centre) unless an already kept s is closer to c than the centre is
+template <int METRIC>
+__device__ __forceinline__ bool
+hnsw_heuristic_keep(const float* __restrict__ vecs, int d, const float* s_c /* vector of c in smem */, float kc, const int32_t* s_sel,
+                    int nsel, int lane) {
+    int j = 0;
+    if ((d & 3) == 0) {
+        for (; j + 4 <= nsel; j += 4) {
+            float k0, k1, k2, k3;
+            hnsw_key4<METRIC>(vecs, d, s_c, s_sel[j], s_sel[j + 1], s_sel[j + 2], s_sel[j + 3], lane, k0, k1, k2, k3);
+            if (k0 < kc || k1 < kc || k2 < kc || k3 < kc) return false;
+        }
+    }
+    for (; j < nsel; j++)
+        if (hnsw_key<METRIC>(vecs, d, s_c, s_sel[j], lane) < kc) return false;
+    return true;
+}
+
+// dynamic smem per warp: d floats (candidate vector) + 64 ints
+template <int METRIC>
+__global__ void __launch_bounds__(kBuildWarps * 32)
+hnsw_select_kernel(HnswBuildParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int dpad = (p.d + 3) & ~3;
+    unsigned char* mine = smem_raw + (size_t)warp * ((size_t)dpad * 4 + 256);
+    float* s_c = (float*)mine;
+    int32_t* s_sel = (int32_t*)(mine + (size_t)dpad * 4);
+    const int w = blockIdx.x * kBuildWarps + warp;
+    if (w >= p.nb) return;
+    const int32_t q = p.batch[w];
+    const int maxn = p.cum[p.level + 1] - p.cum[p.level];
+    int nsel = 0;
+    for (int ci = 0; ci < p.ef && nsel < maxn; ci++) {
+        const int64_t c = p.cand_ids[(int64_t)w * p.ef + ci];
+        if (c < 0) break;
+        if (c == q) continue;
+        const float dc = p.cand_dist[(int64_t)w * p.ef + ci];
+        const float kc = (METRIC == KB2_METRIC_L2) ? dc : -dc;
+        __syncwarp();
+        for (int j = lane; j < p.d; j += kWarp) s_c[j] = p.vecs[c * p.d + j];
+        __syncwarp();
+        if (hnsw_heuristic_keep<METRIC>(p.vecs, p.d, s_c, kc, s_sel, nsel, lane)) {
+            if (lane == 0) s_sel[nsel] = (int32_t)c;
+            nsel++;
+            __syncwarp();
+        }
+    }
+    int32_t* row = p.neighbors + p.offsets[q] + p.cum[p.level];
+    for (int j = lane; j < maxn; j += kWarp) row[j] = j < nsel ? s_sel[j] : -1;
+    for (int j = lane; j < nsel; j += kWarp) p.sel_ids[(int64_t)w * 64 + j] = s_sel[j];
+    if (lane == 0) p.sel_cnt[w] = nsel;
+}
+
+// reverse links: for every selected neighbour s of the new node q, add q to s's row (under s's lock); a full row is
+// re-selected among its members + q with the heuristic, centre s.  dynamic smem per warp: 2 * d floats + 3 * 64 words
+template <int METRIC>
+__global__ void __launch_bounds__(kBuildWarps * 32)
+hnsw_link_kernel(HnswBuildParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int dpad = (p.d + 3) & ~3;
+    unsigned char* mine = smem_raw + (size_t)warp * ((size_t)dpad * 8 + 768);
+    float* s_s = (float*)mine;                       // vector of the centre s
+    float* s_c = s_s + dpad;                         // vector of the candidate being tested
+    int32_t* s_id = (int32_t*)(s_c + dpad);          // [64] candidate ids (sorted by key to s)
+    float* s_key = (float*)(s_id + 64);              // [64]
+    int32_t* s_sel = (int32_t*)(s_key + 64);         // [64] kept ids
+    const int w = blockIdx.x * kBuildWarps + warp;
+    if (w >= p.nb) return;
+    const int32_t q = p.batch[w];
+    const int cap = p.cum[p.level + 1] - p.cum[p.level];   // <= 64 (M <= 32)
+    const int nq_sel = p.sel_cnt[w];
+    for (int si = 0; si < nq_sel; si++) {
+        const int32_t s = p.sel_ids[(int64_t)w * 64 + si];
+        if (lane == 0) {
+            while (atomicCAS(&p.locks[s], 0, 1) != 0) {}
+        }
+        __syncwarp();
+        __threadfence();
+        volatile int32_t* row = p.neighbors + p.offsets[s] + p.cum[p.level];
+        // current members (compact, -1 terminated)
+        int cnt = 0;
+        for (int j0 = 0; j0 < cap; j0 += kWarp) {
+            const int32_t v = (j0 + lane < cap) ? row[j0 + lane] : -1;
+            const unsigned m = __ballot_sync(0xffffffffu, v >= 0);
+            if (v >= 0) s_id[j0 + lane] = v;
+            cnt += __popc(m);
+        }
+        __syncwarp();
+        if (cnt < cap) {
+            if (lane == 0) row[cnt] = q;
+        } else {
+            // full: candidates = members + q, keys to s, sort, heuristic, rewrite
+            for (int j = lane; j < p.d; j += kWarp) s_s[j] = p.vecs[(int64_t)s * p.d + j];
+            if (lane == 0) s_id[cnt] = q;
+            __syncwarp();
+            const int nc = cnt + 1;
+            for (int j = 0; j < nc; j++) {
+                const float kj = hnsw_key<METRIC>(p.vecs, p.d, s_s, s_id[j], lane);
+                if (lane == 0) s_key[j] = kj;
+            }
+            __syncwarp();
+            // rank by (key, id): nc <= 65 elements, two per lane at most three
+            int32_t my_id[3];
+            float my_key[3];
+            int my_rank[3];
+            for (int t = 0; t < 3; t++) {
+                const int j = lane + 32 * t;
+                my_rank[t] = -1;
+                if (j < nc) {
+                    my_id[t] = s_id[j];
+                    my_key[t] = s_key[j];
+                    int r = 0;
+                    for (int x = 0; x < nc; x++) {
+                        const float kx = s_key[x];
+                        const int32_t ix = s_id[x];
+                        r += (kx < my_key[t]) || (kx == my_key[t] && ix < my_id[t]);
+                    }
+                    my_rank[t] = r;
+                }
+            }
+            __syncwarp();
+            for (int t = 0; t < 3; t++)
+                if (my_rank[t] >= 0) { s_id[my_rank[t]] = my_id[t]; s_key[my_rank[t]] = my_key[t]; }
+            __syncwarp();
+            int nsel = 0;
+            for (int ci = 0; ci < nc && nsel < cap; ci++) {
+                const int32_t c = s_id[ci];
+                const float kc = s_key[ci];
+                __syncwarp();
+                for (int j = lane; j < p.d; j += kWarp) s_c[j] = p.vecs[(int64_t)c * p.d + j];
+                __syncwarp();
+                if (hnsw_heuristic_keep<METRIC>(p.vecs, p.d, s_c, kc, s_sel, nsel, lane)) {
+                    if (lane == 0) s_sel[nsel] = c;
+                    nsel++;
+                    __syncwarp();
+                }
+            }
+            for (int j = lane; j < cap; j += kWarp) row[j] = j < nsel ? s_sel[j] : -1;
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicExch(&p.locks[s], 0);
+        __syncwarp();
     }
 }
 

@@ -859,6 +859,11 @@ struct IvfIndex : IndexBase {
         return s_items2.p;
     }
 
+    static bool
+    tc_dynamic_sched() {
+        static const bool dyn = [] { const char* e = getenv("KB2_TC_SCHED"); return !(e && !strcmp(e, "static")); }();
+        return dyn;
+    }
     bool
     use_tc_engine(int64_t nq, int nprobe, int Ksel) const {
         if (!is_pq || !(tc_geom_18() || tc_geom_32())) return false;
@@ -973,7 +978,7 @@ struct IvfIndex : IndexBase {
         s_lcount.ensure((size_t)2 * nlist);
         s_lstart.ensure((size_t)nlist);
         s_items.ensure((size_t)3 * max_items);
-        s_plan_out.ensure(4);
+        s_plan_out.ensure(8);
         s_pair_q.ensure((size_t)npairs);
         s_pair_base.ensure((size_t)npairs);
         s_qb16.ensure((size_t)nq * dim);
@@ -989,7 +994,9 @@ struct IvfIndex : IndexBase {
         pqtc::plan_kernel<<<1, 1024, 0, st>>>(s_lcount.p, (int)nlist, s_lstart.p, item_list, item_q0, item_nq, s_plan_out.p);
         {
             // per tile: decode ~ constant, contraction ~ columns (+ the test K-step)
-            int32_t* bal = balance_items(s_items.p, max_items, kNumSMs, 600, 5);
+            // dynamic draw (default): items in descending cost order, CTAs take the next one when free; KB2_TC_SCHED=static
+            // keeps the fixed round-robin assignment with the snake deal
+            int32_t* bal = balance_items(s_items.p, max_items, tc_dynamic_sched() ? 0 : kNumSMs, 600, 5);
             item_list = bal;
             item_q0 = bal + max_items;
             item_nq = bal + 2 * max_items;
@@ -1007,6 +1014,10 @@ struct IvfIndex : IndexBase {
         tp.qb16 = (const __nv_bfloat16*)s_qb16.p;
         tp.qnorm = s_qnorm.p;
         tp.n_items = s_plan_out.p;
+        if (tc_dynamic_sched()) {
+            tp.ticket = s_plan_out.p + 4;
+            KB2_CUDA_CHECK(cudaMemsetAsync(tp.ticket, 0, 4, st));
+        }
         tp.item_list = item_list;
         tp.item_q0 = item_q0;
         tp.item_nq = item_nq;
@@ -1238,8 +1249,9 @@ struct IvfIndex : IndexBase {
         const char* e = getenv("KB2_COARSE");
         if (coarse_tc_disabled || (e && !strcmp(e, "dense"))) return false;
         if (dim % fltc::BK != 0 || nlist < 1024 || nprobe + 16 > 256 || nprobe + 16 > nlist / 8) return false;
-        if (e && !strcmp(e, "tc")) return m >= 296;
-        return m >= 1024;
+        // opt-in (KB2_COARSE=tc): measured at C3 (10000 x 4096 centroids) the list-major kernel + its sample bound cost
+        // 0.75 ms against 0.43 ms of the dense GEMM + select it would replace (profiles/r2_summary.md)
+        return e && !strcmp(e, "tc") && m >= 296;
     }
     void
     coarse_probes_tc(const float* Q, int64_t m, int nprobe, int64_t* out_ids, float* out_dis) {

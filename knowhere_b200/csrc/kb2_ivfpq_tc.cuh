@@ -69,7 +69,7 @@ struct TcCfg {
     static constexpr int OFF_B = OFF_A + 2 * A_BYTES;
     static constexpr int OFF_META = OFF_B + B_BYTES;
     static constexpr int OFF_BAR = OFF_META + 2 * META_BYTES;
-    static constexpr size_t SMEM_BYTES = OFF_BAR + 256 + 128 /*alignment slack*/;
+    static constexpr size_t SMEM_BYTES = OFF_BAR + 256 + 128 /*alignment slack*/;   // barriers 0..135, scheduler ring 144..239
     static_assert(SMEM_BYTES <= 227 * 1024, "filter kernel shared memory");
 };
 constexpr int KD = 128;                   // (phase-A kernels below are specific to the <1, 8> geometry)
@@ -84,6 +84,8 @@ struct Params {
     const float* qnorm;            // [nq]
     // plan
     const int32_t* n_items;        // device scalar
+    int32_t* ticket;               // optional work counter (zeroed before the launch): CTAs draw items from it in order, so a
+                                   // CTA that got short items simply draws more (NULL: item = blockIdx.x + seq * gridDim.x)
     const int32_t* item_list;      // [items]
     const int32_t* item_q0;        // [items] first pair of the chunk
     const int32_t* item_nq;        // [items]
@@ -211,6 +213,38 @@ ivfpq_tc_filter_kernel(Params p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_items = *p.n_items;
 
+    // ---- item sequence of this CTA.  The three roles walk the same sequence independently (at most ~3 items apart), so the
+    // seq-th draw is published through a small ring in shared memory: whoever needs it first claims the slot, takes a ticket
+    // from the global counter and publishes it; the others read it.
+    constexpr int SCHED_R = 8;
+    int* sch_claim = (int*)(sm + OFF_BAR + 144);
+    int* sch_item = sch_claim + SCHED_R;
+    volatile int* sch_ready = (volatile int*)(sch_item + SCHED_R);
+    if (threadIdx.x < SCHED_R) {
+        sch_claim[threadIdx.x] = (int)threadIdx.x - SCHED_R;
+        sch_ready[threadIdx.x] = -1;
+    }
+    auto item_at = [&](int seq) -> int {   // warp-uniform call
+        if (!p.ticket) return (int)blockIdx.x + seq * (int)gridDim.x;
+        int v = 0;
+        if (lane == 0) {
+            const int sl = seq & (SCHED_R - 1);
+            if (sch_ready[sl] != seq) {
+                if (atomicCAS(sch_claim + sl, seq - SCHED_R, seq) == seq - SCHED_R) {
+                    const int t = atomicAdd(p.ticket, 1);
+                    ((volatile int*)sch_item)[sl] = t;
+                    __threadfence_block();
+                    sch_ready[sl] = seq;
+                } else {
+                    while (sch_ready[sl] != seq) {}
+                }
+            }
+            __threadfence_block();
+            v = ((volatile int*)sch_item)[sl];
+        }
+        return __shfl_sync(0xffffffffu, v, 0);
+    };
+
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; i++) {
             tc::mbar_init(bar_a_full(i), GROUP_THREADS);
@@ -281,8 +315,10 @@ ivfpq_tc_filter_kernel(Params p) {
         };
         uint32_t g0 = 0;   // global tile counter at the start of the item
         int it = 0;
-        if ((int)blockIdx.x < n_items) write_meta(blockIdx.x, 0);
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
+        int item = item_at(0);
+        if (item < n_items) write_meta(item, 0);
+        for (; item < n_items; it++) {
+            const int item_next = item_at(it + 1);
             const int l = p.item_list[item];
             const int nqi = p.item_nq[item];
             const int nmma = (nqi + 15) & ~15;
@@ -411,16 +447,17 @@ ivfpq_tc_filter_kernel(Params p) {
             tc::fence_proxy_async();
             tc::mbar_arrive(bar_b_full);
             // thresholds of the NEXT item (other meta buffer)
-            if (item + (int)gridDim.x < n_items) write_meta(item + gridDim.x, it + 1);
+            if (item_next < n_items) write_meta(item_next, it + 1);
             // ---- this group's remaining tiles
             for (int t = t_first + 2; t < ntiles; t += 2) decode_tile(t);
             g0 += (uint32_t)ntiles;
+            item = item_next;
         }
     } else if (warp == MMA_WARP) {
         // =========================== MMA issuer ===========================
         uint32_t g = 0;
         int it = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
+        for (int item = item_at(0); item < n_items; item = item_at(++it)) {
             const int l = p.item_list[item];
             const int nqi = p.item_nq[item];
             const int nmma = (nqi + 15) & ~15;
@@ -475,7 +512,7 @@ ivfpq_tc_filter_kernel(Params p) {
           "=r"(V[17]), "=r"(V[18]), "=r"(V[19]), "=r"(V[20]), "=r"(V[21]), "=r"(V[22]), "=r"(V[23]), "=r"(V[24]),        \
           "=r"(V[25]), "=r"(V[26]), "=r"(V[27]), "=r"(V[28]), "=r"(V[29]), "=r"(V[30]), "=r"(V[31])                      \
         : "r"(TADDR))
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
+        for (int item = item_at(0); item < n_items; item = item_at(++it)) {
             const int l = p.item_list[item];
             const int nqi = p.item_nq[item];
             const int nmma = (nqi + 15) & ~15;
@@ -673,9 +710,12 @@ deal_items_kernel(const int32_t* __restrict__ n_items, const int32_t* __restrict
     const int j = blockIdx.x * blockDim.x + threadIdx.x;   // rank by descending cost
     const int n = *n_items;
     if (j >= n) return;
-    const int r = j / G, b = j % G;
-    const bool full_round = (r + 1) * G <= n;
-    const int dst = r * G + (((r & 1) && full_round) ? (G - 1 - b) : b);
+    int dst = j;   // G == 0: plain descending-cost order (drawn dynamically through Params::ticket)
+    if (G > 0) {
+        const int r = j / G, b = j % G;
+        const bool full_round = (r + 1) * G <= n;
+        dst = r * G + (((r & 1) && full_round) ? (G - 1 - b) : b);
+    }
     const int src = sorted_idx[j];
     out_list[dst] = in_list[src];
     out_q0[dst] = in_q0[src];

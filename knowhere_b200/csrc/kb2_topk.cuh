@@ -284,7 +284,9 @@ finalize_kernel(FinalizeParams p) {
     if (p.rerank) {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         const int nwarps = blockDim.x >> 5;
-        if (!p.raw16 && (p.d & 3) == 0 && (reinterpret_cast<uintptr_t>(p.raw) & 15) == 0) {
+        const bool vec4 = (p.d & 3) == 0 && (p.raw16 ? (reinterpret_cast<uintptr_t>(p.raw16) & 7) == 0
+                                                      : (reinterpret_cast<uintptr_t>(p.raw) & 15) == 0);
+        if (vec4) {
             // four candidates per warp at a time (8 lanes each, 128 B per candidate and step): the re-rank is a chain of
             // dependent random-row round trips (L2 / HBM), so candidates in flight per warp are what sets its duration
             const int sub = lane & 7, grp = lane >> 3;
@@ -295,9 +297,25 @@ finalize_kernel(FinalizeParams p) {
                 float acc = 0.f;
                 if (pos != kNoPos) {
                     const int64_t r = p.raw_by_pos ? (int64_t)pos : (p.rows ? (int64_t)p.rows[pos] : (int64_t)pos);
-                    const float4* x4 = reinterpret_cast<const float4*>(p.raw + r * (int64_t)p.d);
+                    // a 16-bit store (refine_type fp16 / bf16) is decoded to fp32 and summed in the same order as the fp32
+                    // store, so it answers exactly like a flat store holding the rounded rows
+                    const float4* x4 = p.raw16 ? nullptr : reinterpret_cast<const float4*>(p.raw + r * (int64_t)p.d);
+                    const uint2* h4 = p.raw16 ? reinterpret_cast<const uint2*>(p.raw16 + r * (int64_t)p.d) : nullptr;
                     for (int j = sub; j < (p.d >> 2); j += 8) {
-                        const float4 xv = __ldg(x4 + j);
+                        float4 xv;
+                        if (x4) {
+                            xv = __ldg(x4 + j);
+                        } else {
+                            const uint2 h = __ldg(h4 + j);
+                            if (p.raw16_kind == 1) {
+                                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h.x));
+                                const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+                                xv = make_float4(a.x, a.y, b.x, b.y);
+                            } else {
+                                xv = make_float4(__uint_as_float(h.x << 16), __uint_as_float(h.x & 0xffff0000u),
+                                                 __uint_as_float(h.y << 16), __uint_as_float(h.y & 0xffff0000u));
+                            }
+                        }
                         const float4 qv = q4[j];
                         if (p.metric == KB2_METRIC_L2) {
                             float t;
