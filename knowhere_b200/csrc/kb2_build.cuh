@@ -45,18 +45,26 @@ launch_gemm_keys(cudaStream_t st, int mode, int metric, const float* Q, const fl
         if (tc::make_tmap(&tq, Q, nq, d) && tc::make_tmap(&tx, X, cols, d)) {
             static PerDeviceOnce once;
             once.run([] {
-                cudaFuncSetAttribute((const void*)tc::gemm_keys_tc_kernel<KB2_METRIC_L2>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
-                cudaFuncSetAttribute((const void*)tc::gemm_keys_tc_kernel<KB2_METRIC_IP>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
+                cudaFuncSetAttribute((const void*)tc::gemm_keys_tc_kernel<KB2_METRIC_L2, 3>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::smem_bytes(3));
+                cudaFuncSetAttribute((const void*)tc::gemm_keys_tc_kernel<KB2_METRIC_IP, 3>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::smem_bytes(3));
+                cudaFuncSetAttribute((const void*)tc::gemm_keys_tc_kernel<KB2_METRIC_L2, 1>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::smem_bytes(1));
+                cudaFuncSetAttribute((const void*)tc::gemm_keys_tc_kernel<KB2_METRIC_IP, 1>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::smem_bytes(1));
             });
             dim3 g((unsigned)((cols + tc::BN - 1) / tc::BN), (unsigned)((nq + tc::BM - 1) / tc::BM));
-            if (metric == KB2_METRIC_L2)
-                tc::gemm_keys_tc_kernel<KB2_METRIC_L2><<<g, tc::THREADS, tc::SMEM_BYTES, st>>>(tq, tx, qn, xn, nq, cols, d, keys,
-                                                                                           ldk, bitset, rows, row_base);
-            else
-                tc::gemm_keys_tc_kernel<KB2_METRIC_IP><<<g, tc::THREADS, tc::SMEM_BYTES, st>>>(tq, tx, qn, xn, nq, cols, d, keys,
-                                                                                           ldk, bitset, rows, row_base);
+            static const int short_k = [] { const char* e = getenv("KB2_GEMM_SHORTK"); return e ? atoi(e) : 192; }();
+#define KB2_GEMM_LAUNCH(MM, NST)                                                                                                  \
+    tc::gemm_keys_tc_kernel<MM, NST><<<g, tc::THREADS, tc::smem_bytes(NST), st>>>(tq, tx, qn, xn, nq, cols, d, keys, ldk, bitset, \
+                                                                                  rows, row_base)
+            if (d <= short_k) {
+                if (metric == KB2_METRIC_L2) KB2_GEMM_LAUNCH(KB2_METRIC_L2, 1); else KB2_GEMM_LAUNCH(KB2_METRIC_IP, 1);
+            } else {
+                if (metric == KB2_METRIC_L2) KB2_GEMM_LAUNCH(KB2_METRIC_L2, 3); else KB2_GEMM_LAUNCH(KB2_METRIC_IP, 3);
+            }
+#undef KB2_GEMM_LAUNCH
             return true;
         }
     }

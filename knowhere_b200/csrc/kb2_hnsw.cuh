@@ -62,6 +62,8 @@ struct HnswSearchParams {
     // construction (hnsw_search_kernel as the candidate generator of the batched GPU build)
     int beam_level;             // level the beam runs on (0 for searches); the greedy descent stops above it
     const int32_t* q_nodes;     // optional: query i is the stored vector of node q_nodes[i]
+    const int32_t* node_rank;   // optional: insertion rank of every node; the descent only moves to nodes of rank < rank_limit
+    int rank_limit;             //           (= nodes already linked on the beam level)
 };
 
 constexpr int kHnswWarps = 4;  // warps (queries in flight) per CTA
@@ -208,6 +210,7 @@ hnsw_descend(const HnswSearchParams& p, const float* s_q, int lane, int32_t& nea
                     if (lane == j + 1) myk = kb;
                 }
                 ndis_tot += cnt;
+                if (p.node_rank && lane < cnt && p.node_rank[v] >= p.rank_limit) myk = INFINITY;
                 // sequential "if (dis < d_nearest)" over the slots == first strict minimum
                 float bk = myk;
                 int bl = lane;
@@ -1147,10 +1150,14 @@ struct HnswIndex : IndexBase {
         std::vector<int32_t> order(n);
         for (int64_t i = 0; i < n; i++) order[i] = (int32_t)i;
         std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return h_levels[a] > h_levels[b]; });
-        std::vector<omp_lock_t> locks(n);
-        for (auto& l : locks) omp_init_lock(&l);
         entry_point = order[0];
         max_level = h_levels[order[0]] - 1;
+        if (gpu_build_wanted(n, M)) {
+            build_graph_gpu(order);
+            return;
+        }
+        std::vector<omp_lock_t> locks(n);
+        for (auto& l : locks) omp_init_lock(&l);
         // host threads: the affinity / OpenMP default, capped by the cgroup CPU quota (a 128-thread box leased with a 16-CPU
         // quota runs 128 threads 8x oversubscribed otherwise)
         int nthreads = omp_get_max_threads();
@@ -1227,6 +1234,112 @@ struct HnswIndex : IndexBase {
         uploaded = false;
     }
 
+    // ------------------------------------------------------------ device-side construction (see hnsw_select_kernel)
+    static bool
+    gpu_build_wanted(int64_t n_rows, int M_) {
+        if (2 * M_ > 64) return false;   // the link kernel keeps a row in 64 slots
+        const char* e = getenv("KB2_HNSW_BUILD");
+        if (e && !strcmp(e, "host")) return false;
+        if (e && !strcmp(e, "gpu")) return true;
+        return n_rows >= 20000;
+    }
+    void
+    build_graph_gpu(const std::vector<int32_t>& order) {
+        init_attrs();
+        cudaStream_t st = stream;
+        const int ef = std::max(efConstruction, 2 * M);
+        d_vecs.alloc_exact(h_vecs.size());
+        d_neighbors.alloc_exact(h_neighbors.size());
+        d_offsets.alloc_exact(h_offsets.size());
+        d_cum.alloc_exact(h_cum.size() + 1);
+        KB2_CUDA_CHECK(cudaMemcpyAsync(d_vecs.p, h_vecs.data(), h_vecs.size() * 4, cudaMemcpyHostToDevice, st));
+        KB2_CUDA_CHECK(cudaMemsetAsync(d_neighbors.p, 0xff, h_neighbors.size() * 4, st));
+        KB2_CUDA_CHECK(cudaMemcpyAsync(d_offsets.p, h_offsets.data(), h_offsets.size() * 8, cudaMemcpyHostToDevice, st));
+        KB2_CUDA_CHECK(cudaMemcpyAsync(d_cum.p, h_cum.data(), h_cum.size() * 4, cudaMemcpyHostToDevice, st));
+        std::vector<int32_t> rank(n);
+        for (int64_t i = 0; i < n; i++) rank[order[i]] = (int32_t)i;
+        DevBuf<int32_t> d_order, d_rank, d_locks, d_sel, d_selcnt;
+        DevBuf<int64_t> d_cand_ids;
+        DevBuf<float> d_cand_dist;
+        d_order.alloc_exact((size_t)n);
+        d_rank.alloc_exact((size_t)n);
+        d_locks.alloc_exact((size_t)n);
+        KB2_CUDA_CHECK(cudaMemcpyAsync(d_order.p, order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        KB2_CUDA_CHECK(cudaMemcpyAsync(d_rank.p, rank.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        KB2_CUDA_CHECK(cudaMemsetAsync(d_locks.p, 0, (size_t)n * 4, st));
+        int64_t maxb = 16384;
+        if (const char* e = getenv("KB2_HNSW_BUILD_BATCH")) maxb = std::max<int64_t>(1, atoll(e));
+        maxb = std::min<int64_t>(maxb, n);
+        d_cand_ids.alloc_exact((size_t)maxb * ef);
+        d_cand_dist.alloc_exact((size_t)maxb * ef);
+        d_sel.alloc_exact((size_t)maxb * 64);
+        d_selcnt.alloc_exact((size_t)maxb);
+        d_next.ensure(1);
+        const int dpad = (dim + 3) & ~3;
+        const size_t smem_sel = (size_t)kBuildWarps * ((size_t)dpad * 4 + 256);
+        const size_t smem_link = (size_t)kBuildWarps * ((size_t)dpad * 8 + 768);
+        KB2_REQUIRE(smem_link <= (size_t)kMaxDynSmem, KB2_INVALID_ARGS, "HNSW GPU build: dim too large");
+        int64_t level_count[64] = {0};   // nodes with (levels - 1) >= L
+        for (int L = 0; L <= max_level && L < 64; L++) {
+            int64_t c = 0;
+            while (c < n && h_levels[order[c]] - 1 >= L) c++;
+            level_count[L] = c;
+        }
+        int64_t n_batches = 0;
+        for (int L = max_level; L >= 0; L--) {
+            const int64_t cntL = level_count[L];
+            int64_t inserted = 1;   // the entry point (order[0]) is on every level
+            while (inserted < cntL) {
+                const int64_t nb = std::min<int64_t>(std::min<int64_t>(maxb, std::max<int64_t>(1, inserted / 4)), cntL - inserted);
+                const Launch La = plan_launch(nb, ef, false);
+                KB2_CUDA_CHECK(cudaMemsetAsync(d_next.p, 0, 4, st));
+                HnswSearchParams p = base_params(nullptr, nb, ef, ef, La);
+                p.labels = nullptr;
+                p.q_nodes = d_order.p + inserted;
+                p.beam_level = L;
+                p.node_rank = d_rank.p;
+                p.rank_limit = (int)inserted;
+                p.out_ids = d_cand_ids.p;
+                p.out_dist = d_cand_dist.p;
+                HnswBuildParams b{};
+                b.vecs = d_vecs.p;
+                b.d = dim;
+                b.metric = metric;
+                b.level = L;
+                b.neighbors = d_neighbors.p;
+                b.offsets = d_offsets.p;
+                b.cum = d_cum.p;
+                b.batch = d_order.p + inserted;
+                b.nb = (int)nb;
+                b.ef = ef;
+                b.cand_ids = d_cand_ids.p;
+                b.cand_dist = d_cand_dist.p;
+                b.sel_ids = d_sel.p;
+                b.sel_cnt = d_selcnt.p;
+                b.locks = d_locks.p;
+                const int gb = (int)((nb + kBuildWarps - 1) / kBuildWarps);
+                if (metric == KB2_METRIC_L2) {
+                    hnsw_search_kernel<KB2_METRIC_L2><<<La.grid, kHnswWarps * 32, La.smem, st>>>(p);
+                    hnsw_select_kernel<KB2_METRIC_L2><<<gb, kBuildWarps * 32, smem_sel, st>>>(b);
+                    hnsw_link_kernel<KB2_METRIC_L2><<<gb, kBuildWarps * 32, smem_link, st>>>(b);
+                } else {
+                    hnsw_search_kernel<KB2_METRIC_IP><<<La.grid, kHnswWarps * 32, La.smem, st>>>(p);
+                    hnsw_select_kernel<KB2_METRIC_IP><<<gb, kBuildWarps * 32, smem_sel, st>>>(b);
+                    hnsw_link_kernel<KB2_METRIC_IP><<<gb, kBuildWarps * 32, smem_link, st>>>(b);
+                }
+                inserted += nb;
+                n_batches++;
+            }
+        }
+        KB2_CUDA_CHECK(cudaGetLastError());
+        KB2_CUDA_CHECK(cudaMemcpyAsync(h_neighbors.data(), d_neighbors.p, h_neighbors.size() * 4, cudaMemcpyDeviceToHost, st));
+        KB2_CUDA_CHECK(cudaStreamSynchronize(st));
+        last.launches = 3 * n_batches;
+        // rows are compact (-1 only at the tail) by construction of the two kernels; validate the structure once
+        validate_graph();
+        uploaded = false;
+    }
+
     void
     import_graph(int64_t nn, const float* vectors, const int32_t* levels, const int64_t* offsets, const int32_t* neighbors,
                  const int32_t* cum, int n_cum, int32_t ep, int32_t ml) {
@@ -1290,7 +1403,9 @@ struct HnswIndex : IndexBase {
         static PerDeviceOnce once;
         once.run([] {
             for (const void* f : {(const void*)hnsw_search_kernel<KB2_METRIC_L2>, (const void*)hnsw_search_kernel<KB2_METRIC_IP>,
-                                  (const void*)hnsw_filtered_kernel<KB2_METRIC_L2>, (const void*)hnsw_filtered_kernel<KB2_METRIC_IP>})
+                                  (const void*)hnsw_filtered_kernel<KB2_METRIC_L2>, (const void*)hnsw_filtered_kernel<KB2_METRIC_IP>,
+                                  (const void*)hnsw_select_kernel<KB2_METRIC_L2>, (const void*)hnsw_select_kernel<KB2_METRIC_IP>,
+                                  (const void*)hnsw_link_kernel<KB2_METRIC_L2>, (const void*)hnsw_link_kernel<KB2_METRIC_IP>})
                 cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
         });
     }

@@ -849,9 +849,9 @@ struct IvfIndex : IndexBase {
         pqtc::item_cost_kernel<<<grid1d(max_items, 256), 256, 0, st>>>(s_plan_out.p, items, items + 2 * max_items, list_len.p, max_items,
                                                                      tile_cost, col_cost, s_bal_key.p, s_bal_idx.p);
         size_t tmp_bytes = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, s_bal_key.p, s_bal_key2.p, s_bal_idx.p, s_bal_idx2.p, (int)max_items, 0, 32, st);
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, s_bal_key.p, s_bal_key2.p, s_bal_idx.p, s_bal_idx2.p, (int)max_items, 0, 16, st);
         s_sort_tmp.ensure(tmp_bytes);
-        cub::DeviceRadixSort::SortPairs(s_sort_tmp.p, tmp_bytes, s_bal_key.p, s_bal_key2.p, s_bal_idx.p, s_bal_idx2.p, (int)max_items, 0, 32, st);
+        cub::DeviceRadixSort::SortPairs(s_sort_tmp.p, tmp_bytes, s_bal_key.p, s_bal_key2.p, s_bal_idx.p, s_bal_idx2.p, (int)max_items, 0, 16, st);
         pqtc::deal_items_kernel<<<grid1d(max_items, 256), 256, 0, st>>>(s_plan_out.p, s_bal_idx2.p, G_ctas, items, items + max_items,
                                                                       items + 2 * max_items, s_items2.p, s_items2.p + max_items,
                                                                       s_items2.p + 2 * max_items);
@@ -1156,7 +1156,7 @@ struct IvfIndex : IndexBase {
         s_lcount.ensure((size_t)2 * nlist);
         s_lstart.ensure((size_t)nlist);
         s_items.ensure((size_t)3 * max_items);
-        s_plan_out.ensure(4);
+        s_plan_out.ensure(8);
         s_pair_q.ensure((size_t)npairs);
         s_pair_base.ensure((size_t)npairs);
         s_qnorm.ensure((size_t)nq);
@@ -1172,7 +1172,7 @@ struct IvfIndex : IndexBase {
         int32_t* item_nq = s_items.p + 2 * max_items;
         fltc::plan_kernel<<<1, 1024, 0, st>>>(s_lcount.p, (int)nlist, item_cap, s_lstart.p, item_list, item_q0, item_nq, s_plan_out.p);
         {
-            int32_t* bal = balance_items(s_items.p, max_items, kNumSMs, 1000, 2);   // a tile is bound by its HBM stream
+            int32_t* bal = balance_items(s_items.p, max_items, tc_dynamic_sched() ? 0 : kNumSMs, 1000, 2);   // a tile is bound by its HBM stream
             item_list = bal;
             item_q0 = bal + max_items;
             item_nq = bal + 2 * max_items;
@@ -1191,6 +1191,10 @@ struct IvfIndex : IndexBase {
         fpar.metric = metric;
         fpar.d = dim;
         fpar.n_items = s_plan_out.p;
+        if (tc_dynamic_sched()) {
+            fpar.ticket = s_plan_out.p + 4;
+            KB2_CUDA_CHECK(cudaMemsetAsync(fpar.ticket, 0, 4, st));
+        }
         fpar.item_list = item_list;
         fpar.item_q0 = item_q0;
         fpar.item_nq = item_nq;
@@ -1269,7 +1273,7 @@ struct IvfIndex : IndexBase {
         const int64_t n_it = (m + item_cap - 1) / item_cap;
         const int64_t npairs_pad = m + fltc::NQ_ITEM;
         s_items.ensure((size_t)3 * n_it);
-        s_plan_out.ensure(4);
+        s_plan_out.ensure(8);
         s_pair_q.ensure((size_t)m);
         s_qnorm.ensure((size_t)m);
         s_cand.ensure((size_t)m * kTcCandCap);
@@ -1300,6 +1304,10 @@ struct IvfIndex : IndexBase {
         fpar.metric = metric;
         fpar.d = dim;
         fpar.n_items = s_plan_out.p;
+        if (tc_dynamic_sched()) {
+            fpar.ticket = s_plan_out.p + 4;
+            KB2_CUDA_CHECK(cudaMemsetAsync(fpar.ticket, 0, 4, st));
+        }
         fpar.item_list = item_list;
         fpar.item_q0 = item_q0;
         fpar.item_nq = item_nq;

@@ -40,7 +40,7 @@ struct FlCfg {
     static constexpr int STAGES = BROWS <= 32 ? 5 : 3;
     static constexpr int OFF_META = STAGES * STAGE_BYTES;                     // thr[128] | base[128] | qidx[128]
     static constexpr int OFF_BAR = OFF_META + 3 * NQ_ITEM * 4;
-    static constexpr size_t SMEM_BYTES = OFF_BAR + 256 + 1024 /*alignment slack*/;
+    static constexpr size_t SMEM_BYTES = OFF_BAR + 256 + 384 /*item ring*/ + 1024 /*alignment slack*/;
     static_assert(SMEM_BYTES <= 227 * 1024, "IVF_FLAT tensor-core kernel shared memory");
 };
 constexpr float kSlack = 3e-5f;   // 3xTF32 contraction error, relative to |q|^2 + |x|^2 (measured 5e-6, tests/test_gemm_tc_gpu.py)
@@ -48,6 +48,7 @@ constexpr float kSlack = 3e-5f;   // 3xTF32 contraction error, relative to |q|^2
 struct Params {
     int metric, d;
     const int32_t* n_items;
+    int32_t* ticket;              // optional work counter (see pqtc::Params::ticket)
     const int32_t* item_list;
     const int32_t* item_q0;       // first pair of the item
     const int32_t* item_nq;
@@ -161,6 +162,38 @@ ivfflat_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const int n_items = *p.n_items;
     const int nkb = p.d / BK;
 
+    // item sequence of this CTA, drawn from a global counter and shared by the four roles (same scheme as the IVF_PQ filter
+    // kernel; the roles are < 16 items apart: the producer leads by at most STAGES k-blocks, the epilogue trails by 2 tiles)
+    constexpr int SCHED_R = 32;
+    int* sch_claim = (int*)(sm + OFF_BAR + 256);
+    int* sch_item = sch_claim + SCHED_R;
+    volatile int* sch_ready = (volatile int*)(sch_item + SCHED_R);
+    if (threadIdx.x < SCHED_R) {
+        sch_claim[threadIdx.x] = (int)threadIdx.x - SCHED_R;
+        sch_ready[threadIdx.x] = -1;
+    }
+    auto item_at_thread = [&](int seq) -> int {
+        if (!p.ticket) return (int)blockIdx.x + seq * (int)gridDim.x;
+        const int sl = seq & (SCHED_R - 1);
+        if (sch_ready[sl] != seq) {
+            if (atomicCAS(sch_claim + sl, seq - SCHED_R, seq) == seq - SCHED_R) {
+                const int t = atomicAdd(p.ticket, 1);
+                ((volatile int*)sch_item)[sl] = t;
+                __threadfence_block();
+                sch_ready[sl] = seq;
+            } else {
+                while (sch_ready[sl] != seq) {}
+            }
+        }
+        __threadfence_block();
+        return ((volatile int*)sch_item)[sl];
+    };
+    auto item_at = [&](int seq) -> int {   // warp-uniform call
+        int v = 0;
+        if (lane == 0) v = item_at_thread(seq);
+        return __shfl_sync(0xffffffffu, v, 0);
+    };
+
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) {
             tc::mbar_init(bar_full_raw(s), 1);
@@ -187,7 +220,8 @@ ivfflat_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         // ================= TMA producer: per (item, tile, k-block) one stage = raw A tile + B_hi + B_lo =================
         if (lane == 0) {
             uint32_t it = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int seq = 0;
+            for (int item = item_at_thread(0); item < n_items; item = item_at_thread(++seq)) {
                 const int l = p.item_list[item];
                 const int q0 = p.item_q0[item];
                 const int64_t off = p.list_off[l];
@@ -208,7 +242,8 @@ ivfflat_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     } else if (warp == 1) {
         // ================= MMA issuer =================
         uint32_t it = 0, g = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int seq = 0;
+        for (int item = item_at(0); item < n_items; item = item_at(++seq)) {
             const int l = p.item_list[item];
             const int nmma = (p.item_nq[item] + 15) & ~15;
             const int ntiles = (p.list_len[l] + TM - 1) / TM;
@@ -245,7 +280,8 @@ ivfflat_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         // ================= converters: split the raw A tile into hi (in place) and lo =================
         const int t128 = threadIdx.x - 64;   // 0..127
         uint32_t it = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int seq = 0;
+        for (int item = item_at(0); item < n_items; item = item_at(++seq)) {
             const int l = p.item_list[item];
             const int ntiles = (p.list_len[l] + TM - 1) / TM;
             for (int t = 0; t < ntiles; t++) {
@@ -282,7 +318,8 @@ ivfflat_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         bool log_over = false;
         unsigned long long n_rows = 0;
         uint32_t g = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int seq = 0;
+        for (int item = item_at(0); item < n_items; item = item_at(++seq)) {
             const int l = p.item_list[item];
             const int q0 = p.item_q0[item];
             const int nqi = p.item_nq[item];

@@ -694,11 +694,11 @@ item_cost_kernel(const int32_t* __restrict__ n_items, const int32_t* __restrict_
                  int32_t* __restrict__ idx) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= max_items) return;
-    uint32_t k = 0xffffffffu;   // unused slots sort to the end
+    uint32_t k = 0xffffu;   // unused slots sort to the end; 16-bit keys = two radix passes
     if (i < *n_items) {
         const long long tiles = (list_len[item_list[i]] + TM - 1) / TM;
-        const long long c = tiles * (tile_cost + (long long)col_cost * ((item_nq[i] + 15) & ~15));
-        k = 0xfffffffeu - (uint32_t)min(c, 0xfffffff0ll);   // ascending key = descending cost
+        const long long c = (tiles * (tile_cost + (long long)col_cost * ((item_nq[i] + 15) & ~15))) >> 5;
+        k = 0xfffeu - (uint32_t)min(c, 0xfff0ll);   // ascending key = descending cost
     }
     key[i] = k;
     idx[i] = (int32_t)i;
@@ -1033,13 +1033,14 @@ bound_kernel(const float* __restrict__ lut, const int32_t* __restrict__ qlist, c
     const uint32_t lane4 = (ROWW == 32) ? ((uint32_t)(lane & 15) << 3) : ((uint32_t)lane << 2);
     int seen = 0, n_tot = 0;
     float kmin = INFINITY, kmax = -INFINITY;
-    for (int j = 0; j < p0_max && seen < min_codes && n_tot < BOUND_KMAX; j++) {
+    const int code_cap = min(BOUND_KMAX, max(min_codes, k_need));   // scan no more than the requested number of codes
+    for (int j = 0; j < p0_max && seen < min_codes && n_tot < code_cap; j++) {
         const int64_t l = probe_ids[q * probe_stride + j];
         if (l < 0) continue;
         const int len_all = list_len[l];
         if (len_all == 0) continue;
         seen += len_all;
-        const int len = min(len_all, BOUND_KMAX - n_tot);   // any subset of the codes still yields a valid upper bound
+        const int len = min(len_all, code_cap - n_tot);   // any subset of the codes still yields a valid upper bound
         const int64_t off = list_off[l];
         const float dv = probe_dis[q * probe_stride + j];
         const float base = (METRIC == KB2_METRIC_L2) ? dv : -dv;

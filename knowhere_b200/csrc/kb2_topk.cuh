@@ -262,7 +262,24 @@ finalize_kernel(FinalizeParams p) {
     if (p.rerank)
         for (int i = threadIdx.x; i < p.d; i += blockDim.x) s_q[i] = p.queries[q * p.d + i];
     __syncthreads();
-    block_bitonic_sort(s_sort, p.n_sort);
+    if (p.n_sort <= (int)blockDim.x) {
+        // small candidate sets (IVF coarse, tensor-core PQ survivors): rank by counting, one entry per thread.  The bitonic
+        // network costs log^2(n) CTA barriers with most warps idle; this is n broadcast reads per thread and two barriers.
+        const int i = threadIdx.x;
+        const uint64_t mine = (i < p.n_sort) ? s_sort[i] : kEmpty;
+        int rank = 0;
+        if (i < p.n_partial) {
+            for (int j = 0; j < p.n_partial; j++) {
+                const uint64_t e = s_sort[j];
+                rank += (e < mine) || (e == mine && j < i);
+            }
+        }
+        __syncthreads();
+        if (i < p.n_partial) s_sort[rank] = mine;   // a permutation of [0, n_partial); the kEmpty tail stays in place
+        __syncthreads();
+    } else {
+        block_bitonic_sort(s_sort, p.n_sort);
+    }
 
     const int ksel = p.k_sel;
     for (int i = threadIdx.x; i < ksel; i += blockDim.x) {
