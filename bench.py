@@ -435,8 +435,10 @@ def run_ours(args):
                                f", batch={nq}, k={k}",
                    "recall_at_10": recall, "recall_queries": n_gt, "refine_k": cfg.get("refine_k"),
                    "data": "clustered low-rank gaussian mixture, seeds base 42 / query 43 (SURVEY 8d)",
-                   "l2_policy": "inputs larger than L2 (codes 200 MB + refine vectors 5 GB per pass)",
-                   "sharding": ("inverted lists sharded l % N, collectives inside libknowhere_b200.so (kb2_comm_*): probe "
+                   "l2_policy": ("inputs larger than L2: every step streams the probed lists' codes (the whole code array, "
+                                 f"{n * wl['build'].get('m', d * 4) / 1e6:.0f} MB, is touched at this nprobe) and gathers refine rows "
+                                 f"from a {n * d * 4 / 1e9:.1f} GB store; L2 is 126 MB"),
+                   "sharding": ("inverted lists packed onto the ranks by size, collectives inside libknowhere_b200.so (kb2_comm_*): probe "
                                 "all-gather, bound all-reduce, one all-gather of per-shard top-k + merge kernel")
                    if world > 1 else "single GPU",
                    "build_s": round(t_build, 2), "datagen_s": round(t_gen, 2)},

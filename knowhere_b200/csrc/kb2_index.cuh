@@ -313,6 +313,21 @@ launch_finalize(IndexBase& ix, FinalizeParams fp, int64_t nq) {
     fp.n_sort = next_pow2(std::max(fp.n_partial, 2));
     KB2_REQUIRE(fp.n_sort <= kMaxSortEntries, KB2_INTERNAL_ERROR, "finalize: too many partial candidates");
     KB2_REQUIRE(fp.k_sel <= kMaxK && fp.k_out <= fp.k_sel, KB2_INVALID_ARGS, "k too large");
+    static const bool warp_path = [] { const char* e = getenv("KB2_FINALIZE"); return !(e && !strcmp(e, "cta")); }();
+    if (warp_path && fp.k_sel <= 128 && fp.d <= 1024 && (fp.n_partial <= 256 || fp.counts)) {
+        // one warp per query (see finalize_warp_kernel); variable-length rows longer than 256 entries fall through to the
+        // CTA kernel below, which then skips the short ones
+        const size_t smem_w = (size_t)kFinWarps * ((size_t)((fp.d + 3) & ~3) * 4 + 128 * 24);
+        const unsigned g = (unsigned)((nq + kFinWarps - 1) / kFinWarps);
+        if (fp.n_partial <= 128)
+            finalize_warp_kernel<4><<<g, kFinWarps * 32, smem_w, ix.stream>>>(fp, nq);
+        else
+            finalize_warp_kernel<8><<<g, kFinWarps * 32, smem_w, ix.stream>>>(fp, nq);
+        ix.last.launches++;
+        KB2_CUDA_CHECK(cudaGetLastError());
+        if (fp.n_partial <= 256) return;
+        fp.split_small = 256;
+    }
     const size_t smem = (size_t)fp.n_sort * 8 + (size_t)fp.k_sel * 16 + (size_t)fp.d * 4 + 16;
     finalize_kernel<<<(unsigned)nq, 256, smem, ix.stream>>>(fp);
     ix.last.launches++;

@@ -238,6 +238,7 @@ struct FinalizeParams {
     int32_t* out_pos;          // optional [nq][k_out] positions (NULL: skip)
     const uint32_t* counts;    // optional [nq]: only the first min(counts[q], n_partial) entries of a row are valid ...
     const uint32_t* count_flags;   // ... unless count_flags[q] != 0 (then all n_partial are)
+    int split_small;           // > 0: rows with at most this many valid entries were handled by finalize_warp_kernel: skip them
 };
 
 // dynamic smem: n_sort*8 + k_sel*(4+8+4) + d*4
@@ -255,6 +256,7 @@ finalize_kernel(FinalizeParams p) {
     if (p.counts && !(p.count_flags && p.count_flags[q])) {
         // variable-length row (tensor-core PQ engine): sort only what is there
         const int c = (int)min(p.counts[q], (uint32_t)p.n_partial);
+        if (p.split_small > 0 && c <= p.split_small) return;
         p.n_partial = c;
         p.n_sort = c <= 2 ? 2 : (1 << (32 - __clz(c - 1)));
     }
@@ -412,6 +414,233 @@ finalize_kernel(FinalizeParams p) {
         }
     }
     // k_out > k_sel cannot happen (host guarantees k_sel >= k_out)
+}
+
+// ------------------------------------------------------------------------------------------
+// Finalize, small case (n_partial <= 128 candidates): ONE WARP per query, four queries per CTA.  Same contract and the same
+// results as finalize_kernel; the CTA version spends its time in barriers and O(n^2) ranking loops (ncu r2: 12 k warp
+// instructions per query, 75 % issue-active), this one sorts in registers (element i of the warp = lane * 4 + r):
+//   1. bitonic sort of the packed (key, position) entries, 4 per lane
+//   2. exact keys of the best k_sel from the raw rows, four candidates at a time (8 lanes each)
+//   3. bitonic sort of (exact key, label) and the k_out best written out
+// dynamic smem per warp: d floats + 128 * (8 + 4 + 8 + 4) bytes
+// ------------------------------------------------------------------------------------------
+struct FinEntry {
+    float key;
+    int64_t label;
+    uint32_t pos;
+};
+__device__ __forceinline__ bool
+fin_less(const FinEntry& a, const FinEntry& b) {
+    return a.key < b.key || (a.key == b.key && a.label < b.label);
+}
+__device__ __forceinline__ FinEntry
+fin_shfl_xor(const FinEntry& a, int m) {
+    FinEntry o;
+    o.key = __shfl_xor_sync(0xffffffffu, a.key, m);
+    o.label = __shfl_xor_sync(0xffffffffu, a.label, m);
+    o.pos = __shfl_xor_sync(0xffffffffu, a.pos, m);
+    return o;
+}
+__device__ __forceinline__ uint64_t
+fin_shfl_xor(uint64_t a, int m) {
+    return __shfl_xor_sync(0xffffffffu, a, m);
+}
+__device__ __forceinline__ bool
+fin_less(uint64_t a, uint64_t b) {
+    return a < b;
+}
+// ascending bitonic sort of 32 * EPL elements held EPL per lane (index = lane * EPL + r)
+template <typename T, int EPL>
+__device__ __forceinline__ void
+warp_bitonic(T (&v)[EPL], int lane) {
+#pragma unroll
+    for (int k2 = 2; k2 <= 32 * EPL; k2 <<= 1) {
+#pragma unroll
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            if (j < EPL) {
+#pragma unroll
+                for (int r = 0; r < EPL; r++) {
+                    if ((r ^ j) > r) {
+                        const bool asc = (((lane * EPL + r) & k2) == 0);
+                        const bool sw = fin_less(v[r ^ j], v[r]) == asc;   // out of order for this direction
+                        const T a = v[r], b = v[r ^ j];
+                        v[r] = sw ? b : a;
+                        v[r ^ j] = sw ? a : b;
+                    }
+                }
+            } else {
+                const int m = j / EPL;
+                const bool lower = (lane & m) == 0;
+#pragma unroll
+                for (int r = 0; r < EPL; r++) {
+                    const bool asc = (((lane * EPL + r) & k2) == 0);
+                    const T o = fin_shfl_xor(v[r], m);
+                    const bool take_min = (lower == asc);
+                    // equal elements: each side keeps its own copy
+                    const bool take_o = take_min ? fin_less(o, v[r]) : fin_less(v[r], o);
+                    v[r] = take_o ? o : v[r];
+                }
+            }
+        }
+    }
+}
+
+constexpr int kFinWarps = 4;
+template <int EPL>   // candidates per lane in step 1: 4 (<= 128 candidates) or 8 (<= 256)
+__global__ void __launch_bounds__(kFinWarps * 32)
+finalize_warp_kernel(FinalizeParams p, int64_t nq) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int dpad = (p.d + 3) & ~3;
+    const size_t per_warp = (size_t)dpad * 4 + 128 * 24;
+    unsigned char* mine = smem_raw + (size_t)warp * per_warp;
+    float* s_q = (float*)mine;
+    int64_t* s_label = (int64_t*)(mine + (size_t)dpad * 4);
+    uint64_t* s_e = (uint64_t*)(s_label + 128);
+    float* s_key = (float*)(s_e + 128);
+    uint32_t* s_pos = (uint32_t*)(s_key + 128);
+    const int64_t q = (int64_t)blockIdx.x * kFinWarps + warp;
+    if (q >= nq) return;
+
+    // ---- 1. approximate order
+    int n = p.n_partial;
+    if (p.counts && !(p.count_flags && p.count_flags[q])) n = (int)min(p.counts[q], (uint32_t)p.n_partial);
+    if (n > 32 * EPL) return;   // (only with p.split_small) left to finalize_kernel
+    const uint64_t* src = p.partial + q * p.partial_stride;
+    uint64_t e[EPL];
+#pragma unroll
+    for (int r = 0; r < EPL; r++) {
+        const int i = lane * EPL + r;
+        e[r] = (i < n) ? src[i] : kEmpty;
+    }
+    if (p.rerank)
+        for (int j = lane; j < p.d; j += kWarp) s_q[j] = p.queries[q * p.d + j];
+    warp_bitonic<uint64_t, EPL>(e, lane);
+    const int ksel = p.k_sel;
+#pragma unroll
+    for (int r = 0; r < EPL; r++) {
+        const int i = lane * EPL + r;
+        if (i < 128) {
+            const uint64_t v = e[r];
+            uint32_t pos = kNoPos;
+            float key = INFINITY;
+            int64_t label = INT64_MAX;
+            if (i < ksel && v != kEmpty) {
+                pos = unpack_pos(v);
+                key = unpack_key(v);
+                const int64_t row = p.rows ? (int64_t)p.rows[pos] : (int64_t)pos;
+                label = p.labels ? p.labels[row] : row;
+            }
+            s_pos[i] = pos;
+            s_key[i] = key;
+            s_label[i] = label;
+        }
+    }
+    __syncwarp();
+
+    // ---- 2. exact keys (same arithmetic and summation order as finalize_kernel)
+    if (p.rerank) {
+        const bool vec4 = (p.d & 3) == 0 && (p.raw16 ? (reinterpret_cast<uintptr_t>(p.raw16) & 7) == 0
+                                                      : (reinterpret_cast<uintptr_t>(p.raw) & 15) == 0);
+        if (vec4) {
+            const int sub = lane & 7, grp = lane >> 3;
+            const float4* q4 = reinterpret_cast<const float4*>(s_q);
+            for (int i0 = 0; i0 < ksel; i0 += 4) {
+                const int i = i0 + grp;
+                const uint32_t pos = (i < ksel) ? s_pos[i] : kNoPos;
+                float acc = 0.f;
+                if (pos != kNoPos) {
+                    const int64_t r = p.raw_by_pos ? (int64_t)pos : (p.rows ? (int64_t)p.rows[pos] : (int64_t)pos);
+                    const float4* x4 = p.raw16 ? nullptr : reinterpret_cast<const float4*>(p.raw + r * (int64_t)p.d);
+                    const uint2* h4 = p.raw16 ? reinterpret_cast<const uint2*>(p.raw16 + r * (int64_t)p.d) : nullptr;
+                    for (int j = sub; j < (p.d >> 2); j += 8) {
+                        float4 xv;
+                        if (x4) {
+                            xv = __ldg(x4 + j);
+                        } else {
+                            const uint2 h = __ldg(h4 + j);
+                            if (p.raw16_kind == 1) {
+                                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h.x));
+                                const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+                                xv = make_float4(a.x, a.y, b.x, b.y);
+                            } else {
+                                xv = make_float4(__uint_as_float(h.x << 16), __uint_as_float(h.x & 0xffff0000u),
+                                                 __uint_as_float(h.y << 16), __uint_as_float(h.y & 0xffff0000u));
+                            }
+                        }
+                        const float4 qv = q4[j];
+                        if (p.metric == KB2_METRIC_L2) {
+                            float t;
+                            t = qv.x - xv.x; acc = fmaf(t, t, acc);
+                            t = qv.y - xv.y; acc = fmaf(t, t, acc);
+                            t = qv.z - xv.z; acc = fmaf(t, t, acc);
+                            t = qv.w - xv.w; acc = fmaf(t, t, acc);
+                        } else {
+                            acc = fmaf(qv.x, xv.x, acc); acc = fmaf(qv.y, xv.y, acc);
+                            acc = fmaf(qv.z, xv.z, acc); acc = fmaf(qv.w, xv.w, acc);
+                        }
+                    }
+                }
+                acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                if (sub == 0 && pos != kNoPos) s_key[i] = (p.metric == KB2_METRIC_L2) ? acc : -acc;
+            }
+        } else {
+            for (int i = 0; i < ksel; i++) {
+                const uint32_t pos = s_pos[i];
+                if (pos == kNoPos) continue;
+                const int64_t r = p.raw_by_pos ? (int64_t)pos : (p.rows ? (int64_t)p.rows[pos] : (int64_t)pos);
+                float acc = 0.f;
+                for (int j = lane; j < p.d; j += kWarp) {
+                    float xv;
+                    if (p.raw16) {
+                        const uint16_t h = p.raw16[r * (int64_t)p.d + j];
+                        xv = (p.raw16_kind == 1) ? __half2float(__ushort_as_half(h)) : __uint_as_float((uint32_t)h << 16);
+                    } else {
+                        xv = p.raw[r * (int64_t)p.d + j];
+                    }
+                    if (p.metric == KB2_METRIC_L2) {
+                        const float t = s_q[j] - xv;
+                        acc = fmaf(t, t, acc);
+                    } else {
+                        acc = fmaf(s_q[j], xv, acc);
+                    }
+                }
+                acc = warp_sum(acc);
+                if (lane == 0) s_key[i] = (p.metric == KB2_METRIC_L2) ? acc : -acc;
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- 3. final order by (key, label); empty slots (key inf, label max) go last
+    FinEntry f[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int i = lane * 4 + r;
+        f[r].key = s_key[i];
+        f[r].label = s_label[i];
+        f[r].pos = s_pos[i];
+    }
+    warp_bitonic<FinEntry, 4>(f, lane);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int i = lane * 4 + r;
+        if (i < p.k_out) {
+            const int64_t o = q * p.k_out + i;
+            if (f[r].pos == kNoPos) {
+                p.out_ids[o] = -1;
+                p.out_dist[o] = (p.metric == KB2_METRIC_L2) ? FLT_MAX : -FLT_MAX;
+                if (p.out_pos) p.out_pos[o] = -1;
+            } else {
+                p.out_ids[o] = f[r].label;
+                p.out_dist[o] = (p.metric == KB2_METRIC_L2) ? f[r].key : -f[r].key;
+                if (p.out_pos) p.out_pos[o] = (int32_t)f[r].pos;
+            }
+        }
+    }
 }
 
 // reduce [nq][n_in] partial entries to the best n_keep per query, in place at the front of each
