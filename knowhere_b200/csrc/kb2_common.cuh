@@ -104,6 +104,12 @@ ldg_stream_u4(const uint4* p) {
                  : "l"(p));
     return r;
 }
+__device__ __forceinline__ uint2
+ldg_stream_u2(const uint2* p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
 __device__ __forceinline__ float4
 ldg_stream_f4(const float4* p) {
     float4 r;

@@ -67,10 +67,14 @@ init_kernel_attributes() {
         set((const void*)ivfpq_scan_generic_kernel<KB2_METRIC_IP>);
         set((const void*)ivfflat_scan_kernel<KB2_METRIC_L2>);
         set((const void*)ivfflat_scan_kernel<KB2_METRIC_IP>);
-        set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_L2, 1, 8>);
-        set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_IP, 1, 8>);
-        set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_L2, 3, 2>);
-        set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_IP, 3, 2>);
+        set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_L2, 1, 8, true>);
+        set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_IP, 1, 8, true>);
+        set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_L2, 3, 2, true>);
+        set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_IP, 3, 2, true>);
+        set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_L2, 1, 8, false>);
+        set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_IP, 1, 8, false>);
+        set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_L2, 3, 2, false>);
+        set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_IP, 3, 2, false>);
         set((const void*)pqtc::bound_kernel<KB2_METRIC_L2, 32>);
         set((const void*)pqtc::bound_kernel<KB2_METRIC_IP, 32>);
         set((const void*)pqtc::bound_kernel<KB2_METRIC_L2, 64>);
@@ -314,19 +318,21 @@ launch_finalize(IndexBase& ix, FinalizeParams fp, int64_t nq) {
     KB2_REQUIRE(fp.n_sort <= kMaxSortEntries, KB2_INTERNAL_ERROR, "finalize: too many partial candidates");
     KB2_REQUIRE(fp.k_sel <= kMaxK && fp.k_out <= fp.k_sel, KB2_INVALID_ARGS, "k too large");
     static const bool warp_path = [] { const char* e = getenv("KB2_FINALIZE"); return !(e && !strcmp(e, "cta")); }();
-    if (warp_path && fp.k_sel <= 128 && fp.d <= 1024 && (fp.n_partial <= 256 || fp.counts)) {
-        // one warp per query (see finalize_warp_kernel); variable-length rows longer than 256 entries fall through to the
+    if (warp_path && fp.k_sel <= 128 && fp.d <= 1024 && (fp.n_partial <= 512 || fp.counts)) {
+        // one warp per query (see finalize_warp_kernel); variable-length rows longer than 512 entries fall through to the
         // CTA kernel below, which then skips the short ones
         const size_t smem_w = (size_t)kFinWarps * ((size_t)((fp.d + 3) & ~3) * 4 + 128 * 24);
         const unsigned g = (unsigned)((nq + kFinWarps - 1) / kFinWarps);
         if (fp.n_partial <= 128)
             finalize_warp_kernel<4><<<g, kFinWarps * 32, smem_w, ix.stream>>>(fp, nq);
-        else
+        else if (fp.n_partial <= 256)
             finalize_warp_kernel<8><<<g, kFinWarps * 32, smem_w, ix.stream>>>(fp, nq);
+        else
+            finalize_warp_kernel<16><<<g, kFinWarps * 32, smem_w, ix.stream>>>(fp, nq);
         ix.last.launches++;
         KB2_CUDA_CHECK(cudaGetLastError());
-        if (fp.n_partial <= 256) return;
-        fp.split_small = 256;
+        if (fp.n_partial <= 512) return;
+        fp.split_small = 512;
     }
     const size_t smem = (size_t)fp.n_sort * 8 + (size_t)fp.k_sel * 16 + (size_t)fp.d * 4 + 16;
     finalize_kernel<<<(unsigned)nq, 256, smem, ix.stream>>>(fp);
@@ -1064,12 +1070,17 @@ struct IvfIndex : IndexBase {
         tp.qflag = s_cand_cnt.p + nq;
         tp.counters = d_counter.p;
         if (timing) KB2_CUDA_CHECK(cudaEventRecord(ev2, st));
-#define KB2_TC_LAUNCH(GG, DD)                                                                                                         \
+#define KB2_TC_LAUNCH(GG, DD, CC)                                                                                                     \
     if (metric == KB2_METRIC_L2)                                                                                                     \
-        pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_L2, GG, DD><<<kNumSMs, pqtc::THREADS, pqtc::TcCfg<GG, DD>::SMEM_BYTES, st>>>(tp);    \
+        pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_L2, GG, DD, CC><<<kNumSMs, pqtc::THREADS, pqtc::TcCfg<GG, DD>::SMEM_BYTES, st>>>(tp); \
     else                                                                                                                             \
-        pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_IP, GG, DD><<<kNumSMs, pqtc::THREADS, pqtc::TcCfg<GG, DD>::SMEM_BYTES, st>>>(tp);
-        if (tc_geom_18()) { KB2_TC_LAUNCH(1, 8) } else { KB2_TC_LAUNCH(3, 2) }
+        pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_IP, GG, DD, CC><<<kNumSMs, pqtc::THREADS, pqtc::TcCfg<GG, DD>::SMEM_BYTES, st>>>(tp);
+        static const bool coop = [] { const char* e = getenv("KB2_TC_COOP"); return !(e && atoi(e) == 0); }();
+        if (coop) {
+            if (tc_geom_18()) { KB2_TC_LAUNCH(1, 8, true) } else { KB2_TC_LAUNCH(3, 2, true) }
+        } else {
+            if (tc_geom_18()) { KB2_TC_LAUNCH(1, 8, false) } else { KB2_TC_LAUNCH(3, 2, false) }
+        }
 #undef KB2_TC_LAUNCH
         if (timing) KB2_CUDA_CHECK(cudaEventRecord(ev3, st));
         KB2_CUDA_CHECK(cudaGetLastError());
