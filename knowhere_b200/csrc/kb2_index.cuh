@@ -67,14 +67,10 @@ init_kernel_attributes() {
         set((const void*)ivfpq_scan_generic_kernel<KB2_METRIC_IP>);
         set((const void*)ivfflat_scan_kernel<KB2_METRIC_L2>);
         set((const void*)ivfflat_scan_kernel<KB2_METRIC_IP>);
-        set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_L2, 1, 8, true>);
-        set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_IP, 1, 8, true>);
-        set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_L2, 3, 2, true>);
-        set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_IP, 3, 2, true>);
-        set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_L2, 1, 8, false>);
-        set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_IP, 1, 8, false>);
-        set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_L2, 3, 2, false>);
-        set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_IP, 3, 2, false>);
+        set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_L2, 1, 8>);
+        set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_IP, 1, 8>);
+        set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_L2, 3, 2>);
+        set((const void*)pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_IP, 3, 2>);
         set((const void*)pqtc::bound_kernel<KB2_METRIC_L2, 32>);
         set((const void*)pqtc::bound_kernel<KB2_METRIC_IP, 32>);
         set((const void*)pqtc::bound_kernel<KB2_METRIC_L2, 64>);
@@ -1070,17 +1066,12 @@ struct IvfIndex : IndexBase {
         tp.qflag = s_cand_cnt.p + nq;
         tp.counters = d_counter.p;
         if (timing) KB2_CUDA_CHECK(cudaEventRecord(ev2, st));
-#define KB2_TC_LAUNCH(GG, DD, CC)                                                                                                     \
+#define KB2_TC_LAUNCH(GG, DD)                                                                                                         \
     if (metric == KB2_METRIC_L2)                                                                                                     \
-        pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_L2, GG, DD, CC><<<kNumSMs, pqtc::THREADS, pqtc::TcCfg<GG, DD>::SMEM_BYTES, st>>>(tp); \
+        pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_L2, GG, DD><<<kNumSMs, pqtc::THREADS, pqtc::TcCfg<GG, DD>::SMEM_BYTES, st>>>(tp);    \
     else                                                                                                                             \
-        pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_IP, GG, DD, CC><<<kNumSMs, pqtc::THREADS, pqtc::TcCfg<GG, DD>::SMEM_BYTES, st>>>(tp);
-        static const bool coop = [] { const char* e = getenv("KB2_TC_COOP"); return !(e && atoi(e) == 0); }();
-        if (coop) {
-            if (tc_geom_18()) { KB2_TC_LAUNCH(1, 8, true) } else { KB2_TC_LAUNCH(3, 2, true) }
-        } else {
-            if (tc_geom_18()) { KB2_TC_LAUNCH(1, 8, false) } else { KB2_TC_LAUNCH(3, 2, false) }
-        }
+        pqtc::ivfpq_tc_filter_kernel<KB2_METRIC_IP, GG, DD><<<kNumSMs, pqtc::THREADS, pqtc::TcCfg<GG, DD>::SMEM_BYTES, st>>>(tp);
+        if (tc_geom_18()) { KB2_TC_LAUNCH(1, 8) } else { KB2_TC_LAUNCH(3, 2) }
 #undef KB2_TC_LAUNCH
         if (timing) KB2_CUDA_CHECK(cudaEventRecord(ev3, st));
         KB2_CUDA_CHECK(cudaGetLastError());
@@ -1403,6 +1394,7 @@ struct IvfIndex : IndexBase {
         fp.k_sel = (int)std::min<int64_t>(std::min(pl.Ksel, nprobe + 16), nlist);
         fp.k_out = nprobe;
         fp.rerank = 1;
+        fp.rerank_all = 1;
         fp.raw = centroids.p;
         fp.raw_by_pos = 1;
         fp.queries = dq + q_lo * dim;

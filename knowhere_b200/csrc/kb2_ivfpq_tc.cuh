@@ -35,7 +35,6 @@
 // Work item = (list, chunk of <= 256 of the queries probing it); items are laid out by a single-CTA plan kernel
 // from the coarse result (count -> scan -> fill).
 #pragma once
-#include <type_traits>
 #include <cuda_bf16.h>
 
 #include <cub/block/block_scan.cuh>
@@ -187,12 +186,7 @@ split3_bf16(float x, uint32_t& hi, uint32_t& mid, uint32_t& lo) {
     lo = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(r2));
 }
 
-// COOP = true: the eight decoder warps fill ONE tile together (thread = row x half of the chunks) and the eight epilogue
-// warps drain ONE accumulator together (warp = lane quarter x every other 32-column chunk).  With a warp group per tile
-// (COOP = false, round-2 first version) the group could not start tile t+2 before the MMA of tile t had released the
-// group's only A buffer / accumulator, so a group's period was decode + MMA (ncu: decoders 44 %, epilogue 46 % of their time
-// in those waits); sharing the tile turns the two buffers into real double buffering: period = max(decode, MMA, epilogue).
-template <int METRIC, int G, int DSUB, bool COOP = true>
+template <int METRIC, int G, int DSUB>
 __global__ void __launch_bounds__(THREADS, 1)
 ivfpq_tc_filter_kernel(Params p) {
     using C = TcCfg<G, DSUB>;
@@ -253,10 +247,10 @@ ivfpq_tc_filter_kernel(Params p) {
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; i++) {
-            tc::mbar_init(bar_a_full(i), COOP ? 2 * GROUP_THREADS : GROUP_THREADS);
+            tc::mbar_init(bar_a_full(i), GROUP_THREADS);
             tc::mbar_init(bar_a_empty(i), 1);
             tc::mbar_init(bar_acc_full(i), 1);
-            tc::mbar_init(bar_acc_empty(i), COOP ? 2 * GROUP_THREADS : GROUP_THREADS);
+            tc::mbar_init(bar_acc_empty(i), GROUP_THREADS);
             tc::mbar_init(bar_meta_full(i), 2 * GROUP_THREADS);
             tc::mbar_init(bar_meta_free(i), 2 * GROUP_THREADS);
         }
@@ -332,132 +326,6 @@ ivfpq_tc_filter_kernel(Params p) {
             const int64_t off = p.list_off[l];
             const int ntiles = (len + TM - 1) / TM;
             const int par = it & 1;
-            // ---- B operand + next item's thresholds (runs after the item's first tile(s) were decoded)
-            auto stage_b_and_meta = [&]() {
-                // ---- B operand: the item's queries (bf16) gathered by index with cp.async, K-major no-swizzle layout,
-                //      plus the threshold chunk [1, 1, 1, h_hi, h_mid, h_lo, 0, 0] of every column
-                asm volatile("bar.sync 2, 256;" ::: "memory");          // meta[par] (thresholds, query indices) written by all decoders
-                mbar_wait_g(bar_b_free, ((uint32_t)it & 1u) ^ 1u);
-                {
-                    const float* m_h = (const float*)(sm + OFF_META + par * META_BYTES);
-                    const int* m_q = (const int*)(m_h + 2 * NQT);
-                    const uint32_t Bs = base + OFF_B;
-                    unsigned char* B = sm + OFF_B;
-                    const int kc = tid >> 3;        // 16-byte chunk along K (0..15)
-                    const int rsub = tid & 7;
-                    for (int blk = dg; blk < nmma / 8 && kc < XCHUNK; blk += 2) {
-                        const int row = blk * 8 + rsub;
-                        const int q = m_q[row];
-                        const uint32_t dst = (uint32_t)(blk * GRP_BYTES + kc * 128 + rsub * 16);
-                        if (q >= 0) {
-                            const void* src = reinterpret_cast<const uint4*>(p.qb16 + (int64_t)q * KD) + kc;
-                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(Bs + dst), "l"(src) : "memory");
-                        } else {
-                            *reinterpret_cast<uint4*>(B + dst) = make_uint4(0, 0, 0, 0);
-                        }
-                    }
-                    if (dt < nmma) {   // one column per decoder thread
-                        uint32_t hh, hm, hl;
-                        split3_bf16(m_h[dt], hh, hm, hl);
-                        unsigned char* Bc = B + (dt >> 3) * GRP_BYTES + (dt & 7) * 16;
-                        *reinterpret_cast<uint4*>(Bc + XCHUNK * 128) = make_uint4(0x3F803F80u, 0x3F80u | (hh << 16), hm | (hl << 16), 0u);
-                        *reinterpret_cast<uint4*>(Bc + (XCHUNK + 1) * 128) = make_uint4(0u, 0u, 0u, 0u);
-                    }
-                    asm volatile("cp.async.wait_all;" ::: "memory");
-                }
-                tc::fence_proxy_async();
-                tc::mbar_arrive(bar_b_full);
-                // thresholds of the NEXT item (other meta buffer)
-                if (item_next < n_items) write_meta(item_next, it + 1);
-            };
-            if constexpr (COOP) {
-            // ================= cooperative tiles: thread (row tid, half dg) =================
-            static_assert(!COOP || DSUB == 8 || DSUB == 2, "cooperative decode: DSUB 8 (m16 x 8) or 2 (m48 x 2)");
-            const uint4* code_src = (DSUB == 8) ? p.codes : p.codes_plain;
-            uint2 w_next[G];
-#pragma unroll
-            for (int g = 0; g < G; g++) w_next[g] = make_uint2(0, 0);
-            float t_next = 0.f;
-            auto load_codes = [&](int t) {
-                const int64_t pn = off + (int64_t)t * TM + tid;
-                if (t < ntiles && pn < p.npad) {
-#pragma unroll
-                    for (int gg = 0; gg < G; gg++)
-                        w_next[gg] = ldg_stream_u2(reinterpret_cast<const uint2*>(code_src + (int64_t)gg * p.npad + pn) + dg);
-                    if (METRIC == KB2_METRIC_L2 && dg == 0) t_next = __ldg(p.t1 + pn);
-                }
-            };
-            // H = this thread's half (compile-time so that every register index below is static)
-            auto decode_half = [&](auto half_tag, unsigned char* A, const uint2 (&w)[G], float tv, int t) {
-                constexpr int H = decltype(half_tag)::value;
-                if constexpr (DSUB == 8) {
-                    // bytes 8H .. 8H+7 of the rotated code word: sub-quantizer (8H + s + tid) & 15 (see the COOP = false path)
-#pragma unroll
-                    for (int gg = 0; gg < G; gg++) {
-                        const uint32_t ww[2] = {w[gg].x, w[gg].y};
-                        uint4 v[8];
-#pragma unroll
-                        for (int s = 0; s < 8; s++) {
-                            const uint32_t byte = (ww[s >> 2] >> (8 * (s & 3))) & 255u;
-                            v[s] = tab[byte * (16 * G) + gg * 16 + ((8 * H + s + tid) & 15)];
-                        }
-#pragma unroll
-                        for (int s = 0; s < 8; s++) *reinterpret_cast<uint4*>(A + (gg * 16 + ((8 * H + s + tid) & 15)) * 128) = v[s];
-                    }
-                } else {
-                    // DSUB == 2: chunk c = sub-quantizers 4c .. 4c+3 = 32-bit word c of the plain code; this half owns words
-                    // 2H, 2H+1 of every 16-byte group
-                    const uint32_t* tab32 = reinterpret_cast<const uint32_t*>(tab);
-                    uint32_t v[G][2][4];
-#pragma unroll
-                    for (int gg = 0; gg < G; gg++) {
-#pragma unroll
-                        for (int cc = 0; cc < 2; cc++) {
-                            const uint32_t word = cc == 0 ? w[gg].x : w[gg].y;
-                            const int c = 4 * gg + 2 * H + cc;
-#pragma unroll
-                            for (int j = 0; j < 4; j++) v[gg][cc][j] = tab32[(c * 4 + j) * 256 + ((word >> (8 * j)) & 255u)];
-                        }
-                    }
-#pragma unroll
-                    for (int gg = 0; gg < G; gg++) {
-#pragma unroll
-                        for (int cc = 0; cc < 2; cc++)
-                            *reinterpret_cast<uint4*>(A + (4 * gg + 2 * H + cc) * 128) =
-                                make_uint4(v[gg][cc][0], v[gg][cc][1], v[gg][cc][2], v[gg][cc][3]);
-                    }
-                }
-                if constexpr (H == 0) {
-                    // test chunk: [-r_hi, -r_mid, -r_lo, 1, 1, 1, 0, 0] (bf16 1.0 = 0x3F80); rows past the end never pass
-                    float r = INFINITY;
-                    if (t * TM + tid < len) r = (METRIC == KB2_METRIC_L2) ? 0.5f * tv : 0.f;
-                    uint32_t rh, rm, rl;
-                    split3_bf16(-r, rh, rm, rl);
-                    *reinterpret_cast<uint4*>(A + XCHUNK * 128) = make_uint4(rh | (rm << 16), rl | (0x3F80u << 16), 0x3F803F80u, 0u);
-                } else {
-                    *reinterpret_cast<uint4*>(A + (XCHUNK + 1) * 128) = make_uint4(0u, 0u, 0u, 0u);
-                }
-            };
-            auto decode_tile = [&](int t) {
-                const uint32_t g = g0 + (uint32_t)t;
-                const int buf = (int)(g & 1u);
-                uint2 w[G];
-#pragma unroll
-                for (int gg = 0; gg < G; gg++) w[gg] = w_next[gg];
-                const float tv = t_next;
-                load_codes(t + 1);
-                mbar_wait_g(bar_a_empty(buf), ((g >> 1) & 1u) ^ 1u);
-                unsigned char* A = sm + OFF_A + buf * A_BYTES + (tid >> 3) * GRP_BYTES + (tid & 7) * 16;
-                if (dg == 0) decode_half(std::integral_constant<int, 0>{}, A, w, tv, t);
-                else decode_half(std::integral_constant<int, 1>{}, A, w, tv, t);
-                tc::fence_proxy_async();
-                tc::mbar_arrive(bar_a_full(buf));
-            };
-            load_codes(0);
-            decode_tile(0);   // needs only a free A buffer: runs while the tensor pipe still works on the previous item
-            stage_b_and_meta();
-            for (int t = 1; t < ntiles; t++) decode_tile(t);
-            } else {
             const int t_first = (int)((dg - (int)(g0 & 1u)) & 1);   // this group's first tile of the item
             uint4 w_next[G];
 #pragma unroll
@@ -545,10 +413,43 @@ ivfpq_tc_filter_kernel(Params p) {
             // the first tile of each group only needs a free A buffer: decode it while the tensor pipe still works on
             // the previous item, then stage the B operand (which must wait for that item's last MMA)
             if (t_first < ntiles) decode_tile(t_first);
-            stage_b_and_meta();
+            // ---- B operand: the item's queries (bf16) gathered by index with cp.async, K-major no-swizzle layout,
+            //      plus the threshold chunk [1, 1, 1, h_hi, h_mid, h_lo, 0, 0] of every column
+            asm volatile("bar.sync 2, 256;" ::: "memory");          // meta[par] (thresholds, query indices) written by all decoders
+            mbar_wait_g(bar_b_free, ((uint32_t)it & 1u) ^ 1u);
+            {
+                const float* m_h = (const float*)(sm + OFF_META + par * META_BYTES);
+                const int* m_q = (const int*)(m_h + 2 * NQT);
+                const uint32_t Bs = base + OFF_B;
+                unsigned char* B = sm + OFF_B;
+                const int kc = tid >> 3;        // 16-byte chunk along K (0..15)
+                const int rsub = tid & 7;
+                for (int blk = dg; blk < nmma / 8 && kc < XCHUNK; blk += 2) {
+                    const int row = blk * 8 + rsub;
+                    const int q = m_q[row];
+                    const uint32_t dst = (uint32_t)(blk * GRP_BYTES + kc * 128 + rsub * 16);
+                    if (q >= 0) {
+                        const void* src = reinterpret_cast<const uint4*>(p.qb16 + (int64_t)q * KD) + kc;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(Bs + dst), "l"(src) : "memory");
+                    } else {
+                        *reinterpret_cast<uint4*>(B + dst) = make_uint4(0, 0, 0, 0);
+                    }
+                }
+                if (dt < nmma) {   // one column per decoder thread
+                    uint32_t hh, hm, hl;
+                    split3_bf16(m_h[dt], hh, hm, hl);
+                    unsigned char* Bc = B + (dt >> 3) * GRP_BYTES + (dt & 7) * 16;
+                    *reinterpret_cast<uint4*>(Bc + XCHUNK * 128) = make_uint4(0x3F803F80u, 0x3F80u | (hh << 16), hm | (hl << 16), 0u);
+                    *reinterpret_cast<uint4*>(Bc + (XCHUNK + 1) * 128) = make_uint4(0u, 0u, 0u, 0u);
+                }
+                asm volatile("cp.async.wait_all;" ::: "memory");
+            }
+            tc::fence_proxy_async();
+            tc::mbar_arrive(bar_b_full);
+            // thresholds of the NEXT item (other meta buffer)
+            if (item_next < n_items) write_meta(item_next, it + 1);
             // ---- this group's remaining tiles
             for (int t = t_first + 2; t < ntiles; t += 2) decode_tile(t);
-            }
             g0 += (uint32_t)ntiles;
             item = item_next;
         }
@@ -624,97 +525,8 @@ ivfpq_tc_filter_kernel(Params p) {
             const float* m_base = (const float*)(sm + OFF_META + par * META_BYTES) + NQT;
             const int* m_q = (const int*)(m_base + NQT);
             if (et == 0) n_codes += (unsigned long long)len * (unsigned long long)nqi;
-            const uint32_t tail_mask = (nmma & 31) ? 0x0000ffffu : 0xffffffffu;   // valid columns of the last chunk
-            if constexpr (COOP) {
-            // ================= cooperative tiles: this warp = lane quarter we, chunks eg, eg + 2, ... =================
-            const int nmine = (nch - eg + 1) >> 1;
-            for (int t = 0; t < ntiles; t++) {
-                const uint32_t g = g0 + (uint32_t)t;
-                const int buf = (int)(g & 1u);
-                mbar_wait_g(bar_acc_full(buf), (g >> 1) & 1u);
-                tc::tc_fence_after();
-                const int rel = t * TM + row;
-                const uint32_t taddr0 = tmem_base + ((uint32_t)(we * 32) << 16) + (uint32_t)(buf * 256 + eg * 32);
-                uint32_t masks[4];
-                uint32_t va[32], vb[32];
-                auto scan_chunk = [&](const uint32_t (&v)[32]) -> uint32_t {
-                    uint32_t gq[8];
-#pragma unroll
-                    for (int i = 0; i < 8; i++) gq[i] = (v[4 * i] & v[4 * i + 1]) & (v[4 * i + 2] & v[4 * i + 3]);
-                    const uint32_t all = ((gq[0] & gq[1]) & (gq[2] & gq[3])) & ((gq[4] & gq[5]) & (gq[6] & gq[7]));
-                    if ((int32_t)all < 0) return 0u;   // all 32 sign bits set: nothing passes
-                    uint32_t m = 0;
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        if ((int32_t)gq[i] >= 0) {
-                            const uint32_t b0 = (~v[4 * i]) >> 31, b1 = (~v[4 * i + 1]) >> 31;
-                            const uint32_t b2 = (~v[4 * i + 2]) >> 31, b3 = (~v[4 * i + 3]) >> 31;
-                            m |= ((b0 | (b1 << 1)) | ((b2 << 2) | (b3 << 3))) << (4 * i);
-                        }
-                    }
-                    return m;
-                };
-                if (nmine > 0) {
-                    KB2_TMEM_LD32(va, taddr0);
-                } else {
-                    tc::tc_fence_before();
-                    tc::mbar_arrive(bar_acc_empty(buf));
-                }
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    masks[k] = 0;
-                    if (k < nmine) {
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        if (k + 1 < nmine) {
-                            if (k & 1) { KB2_TMEM_LD32(va, taddr0 + (uint32_t)((k + 1) * 64)); }
-                            else { KB2_TMEM_LD32(vb, taddr0 + (uint32_t)((k + 1) * 64)); }
-                        } else {
-                            // this warp's part of the tile is in registers: hand the accumulator back before the last test
-                            tc::tc_fence_before();
-                            tc::mbar_arrive(bar_acc_empty(buf));
-                        }
-                        masks[k] = (k & 1) ? scan_chunk(vb) : scan_chunk(va);
-                        if (eg + 2 * k == nch - 1) masks[k] &= tail_mask;
-                    }
-                }
-                uint32_t total = 0;
-#pragma unroll
-                for (int k = 0; k < 4; k++) total += __popc(masks[k]);
-                if (__any_sync(0xffffffffu, total != 0u)) {
-                    uint32_t incl = total;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t tv = __shfl_up_sync(0xffffffffu, incl, o);
-                        if (lane >= o) incl += tv;
-                    }
-                    uint32_t wbase = 0;
-                    if (lane == 31) wbase = atomicAdd(my_cursor, incl);
-                    wbase = __shfl_sync(0xffffffffu, wbase, 31);
-                    uint32_t slot = wbase + incl - total;
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        uint32_t m = masks[k];
-                        while (m) {
-                            const int u = __ffs(m) - 1;
-                            m &= m - 1;
-                            const int col = (eg + 2 * k) * 32 + u;
-                            if (slot < p.log_cap) {
-                                uint4 o;
-                                o.x = (uint32_t)m_q[col];
-                                o.y = (uint32_t)(off + rel);
-                                o.z = __float_as_uint(m_base[col]);
-                                o.w = 0u;
-                                my_log[slot] = o;
-                            } else {
-                                log_over = true;
-                            }
-                            slot++;
-                        }
-                    }
-                }
-            }
-            } else {
             const int t_first = (int)((eg - (int)(g0 & 1u)) & 1);
+            const uint32_t tail_mask = (nmma & 31) ? 0x0000ffffu : 0xffffffffu;   // valid columns of the last chunk
             for (int t = t_first; t < ntiles; t += 2) {
                 const uint32_t g = g0 + (uint32_t)t;   // g & 1 == eg
                 mbar_wait_g(bar_acc_full(eg), (g >> 1) & 1u);
@@ -798,7 +610,6 @@ ivfpq_tc_filter_kernel(Params p) {
                         }
                     }
                 }
-            }
             }
             tc::mbar_arrive(bar_meta_free(par));
             g0 += (uint32_t)ntiles;

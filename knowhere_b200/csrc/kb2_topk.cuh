@@ -239,6 +239,8 @@ struct FinalizeParams {
     const uint32_t* counts;    // optional [nq]: only the first min(counts[q], n_partial) entries of a row are valid ...
     const uint32_t* count_flags;   // ... unless count_flags[q] != 0 (then all n_partial are)
     int split_small;           // > 0: rows with at most this many valid entries were handled by finalize_warp_kernel: skip them
+    int rerank_all;            // 1 (with rerank, n_partial <= 128): exact keys for EVERY candidate instead of the k_sel best by
+                               // approximate key (IVF coarse stage: a superset can only move the result toward the exact top-k)
 };
 
 // dynamic smem: n_sort*8 + k_sel*(4+8+4) + d*4
@@ -450,6 +452,14 @@ __device__ __forceinline__ bool
 fin_less(uint64_t a, uint64_t b) {
     return a < b;
 }
+__device__ __forceinline__ uint32_t
+fin_shfl_xor(uint32_t a, int m) {
+    return __shfl_xor_sync(0xffffffffu, a, m);
+}
+__device__ __forceinline__ bool
+fin_less(uint32_t a, uint32_t b) {
+    return a < b;
+}
 // ascending bitonic sort of 32 * EPL elements held EPL per lane (index = lane * EPL + r)
 template <typename T, int EPL>
 __device__ __forceinline__ void
@@ -487,37 +497,20 @@ warp_bitonic(T (&v)[EPL], int lane) {
 }
 
 constexpr int kFinWarps = 4;
-template <int EPL>   // candidates per lane in step 1: 4 (<= 128 candidates) or 8 (<= 256)
-__global__ void __launch_bounds__(kFinWarps * 32)
-finalize_warp_kernel(FinalizeParams p, int64_t nq) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int dpad = (p.d + 3) & ~3;
-    const size_t per_warp = (size_t)dpad * 4 + 128 * 24;
-    unsigned char* mine = smem_raw + (size_t)warp * per_warp;
-    float* s_q = (float*)mine;
-    int64_t* s_label = (int64_t*)(mine + (size_t)dpad * 4);
-    uint64_t* s_e = (uint64_t*)(s_label + 128);
-    float* s_key = (float*)(s_e + 128);
-    uint32_t* s_pos = (uint32_t*)(s_key + 128);
-    const int64_t q = (int64_t)blockIdx.x * kFinWarps + warp;
-    if (q >= nq) return;
-
-    // ---- 1. approximate order
-    int n = p.n_partial;
-    if (p.counts && !(p.count_flags && p.count_flags[q])) n = (int)min(p.counts[q], (uint32_t)p.n_partial);
-    if (n > 32 * EPL) return;   // (only with p.split_small) left to finalize_kernel
-    const uint64_t* src = p.partial + q * p.partial_stride;
+// step 1 of finalize_warp_kernel for one size class: sort this query's n packed entries (EPL per lane) and leave the best
+// min(k_sel, 128) as (position, key, label) in shared memory
+template <int EPL>
+__device__ __forceinline__ void
+finalize_warp_select(const FinalizeParams& p, const uint64_t* __restrict__ src, int n, int lane, uint32_t* s_pos, float* s_key,
+                     int64_t* s_label, bool sort) {
     uint64_t e[EPL];
 #pragma unroll
     for (int r = 0; r < EPL; r++) {
         const int i = lane * EPL + r;
         e[r] = (i < n) ? src[i] : kEmpty;
     }
-    if (p.rerank)
-        for (int j = lane; j < p.d; j += kWarp) s_q[j] = p.queries[q * p.d + j];
-    warp_bitonic<uint64_t, EPL>(e, lane);
-    const int ksel = p.k_sel;
+    if (sort) warp_bitonic<uint64_t, EPL>(e, lane);
+    const int ksel = sort ? p.k_sel : n;
 #pragma unroll
     for (int r = 0; r < EPL; r++) {
         const int i = lane * EPL + r;
@@ -537,6 +530,36 @@ finalize_warp_kernel(FinalizeParams p, int64_t nq) {
             s_label[i] = label;
         }
     }
+}
+
+template <int EPLMAX>   // largest size class compiled in: 4 (<= 128 candidates), 8 (<= 256) or 16 (<= 512)
+__global__ void __launch_bounds__(kFinWarps * 32)
+finalize_warp_kernel(FinalizeParams p, int64_t nq) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int dpad = (p.d + 3) & ~3;
+    const size_t per_warp = (size_t)dpad * 4 + 128 * 24;
+    unsigned char* mine = smem_raw + (size_t)warp * per_warp;
+    float* s_q = (float*)mine;
+    int64_t* s_label = (int64_t*)(mine + (size_t)dpad * 4);
+    uint64_t* s_e = (uint64_t*)(s_label + 128);
+    float* s_key = (float*)(s_e + 128);
+    uint32_t* s_pos = (uint32_t*)(s_key + 128);
+    const int64_t q = (int64_t)blockIdx.x * kFinWarps + warp;
+    if (q >= nq) return;
+
+    // ---- 1. approximate order (skipped with rerank_all: every candidate gets an exact key)
+    int n = p.n_partial;
+    if (p.counts && !(p.count_flags && p.count_flags[q])) n = (int)min(p.counts[q], (uint32_t)p.n_partial);
+    if (n > 32 * EPLMAX) return;   // (only with p.split_small) left to finalize_kernel
+    const uint64_t* src = p.partial + q * p.partial_stride;
+    if (p.rerank)
+        for (int j = lane; j < p.d; j += kWarp) s_q[j] = p.queries[q * p.d + j];
+    const bool all = p.rerank_all && p.rerank && n <= 128;
+    if (EPLMAX >= 16 && n > 256) finalize_warp_select<(EPLMAX >= 16 ? 16 : 4)>(p, src, n, lane, s_pos, s_key, s_label, true);
+    else if (EPLMAX >= 8 && n > 128) finalize_warp_select<(EPLMAX >= 8 ? 8 : 4)>(p, src, n, lane, s_pos, s_key, s_label, true);
+    else finalize_warp_select<4>(p, src, n, lane, s_pos, s_key, s_label, !all);
+    const int ksel = all ? n : p.k_sel;
     __syncwarp();
 
     // ---- 2. exact keys (same arithmetic and summation order as finalize_kernel)
@@ -615,29 +638,55 @@ finalize_warp_kernel(FinalizeParams p, int64_t nq) {
         __syncwarp();
     }
 
-    // ---- 3. final order by (key, label); empty slots (key inf, label max) go last
-    FinEntry f[4];
+    // ---- 3. final order by (key, label); empty slots (key inf, label max) go last.  Sorted as packed (key, slot) words;
+    //         only when two finite keys are bit-equal (rare) is the sort redone on (key, label) records.
+    uint64_t f[4];
 #pragma unroll
     for (int r = 0; r < 4; r++) {
         const int i = lane * 4 + r;
-        f[r].key = s_key[i];
-        f[r].label = s_label[i];
-        f[r].pos = s_pos[i];
+        f[r] = ((uint64_t)f2ord(s_key[i]) << 32) | (uint32_t)i;
     }
-    warp_bitonic<FinEntry, 4>(f, lane);
+    warp_bitonic<uint64_t, 4>(f, lane);
+    bool tie = false;
+    {
+        const uint32_t kInf = f2ord(INFINITY);
+        const uint32_t nxt = __shfl_down_sync(0xffffffffu, (uint32_t)(f[0] >> 32), 1);
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const uint32_t a = (uint32_t)(f[r] >> 32);
+            const uint32_t b = (r < 3) ? (uint32_t)(f[r < 3 ? r + 1 : 3] >> 32) : nxt;
+            if (a == b && a < kInf && !(r == 3 && lane == 31)) tie = true;
+        }
+    }
+    if (__any_sync(0xffffffffu, tie)) {
+        FinEntry g[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int i = lane * 4 + r;
+            g[r].key = s_key[i];
+            g[r].label = s_label[i];
+            g[r].pos = (uint32_t)i;   // slot
+        }
+        warp_bitonic<FinEntry, 4>(g, lane);
+#pragma unroll
+        for (int r = 0; r < 4; r++) f[r] = ((uint64_t)f2ord(g[r].key) << 32) | g[r].pos;
+    }
 #pragma unroll
     for (int r = 0; r < 4; r++) {
         const int i = lane * 4 + r;
         if (i < p.k_out) {
             const int64_t o = q * p.k_out + i;
-            if (f[r].pos == kNoPos) {
+            const int slot = (int)(uint32_t)f[r];
+            const uint32_t pos = s_pos[slot];
+            if (pos == kNoPos) {
                 p.out_ids[o] = -1;
                 p.out_dist[o] = (p.metric == KB2_METRIC_L2) ? FLT_MAX : -FLT_MAX;
                 if (p.out_pos) p.out_pos[o] = -1;
             } else {
-                p.out_ids[o] = f[r].label;
-                p.out_dist[o] = (p.metric == KB2_METRIC_L2) ? f[r].key : -f[r].key;
-                if (p.out_pos) p.out_pos[o] = (int32_t)f[r].pos;
+                const float key = s_key[slot];
+                p.out_ids[o] = s_label[slot];
+                p.out_dist[o] = (p.metric == KB2_METRIC_L2) ? key : -key;
+                if (p.out_pos) p.out_pos[o] = (int32_t)pos;
             }
         }
     }
