@@ -295,6 +295,7 @@ dense_candidates(IndexBase& ix, const float* Q, int64_t nq, const float* X, cons
         const int per_slice = (int)(((cols + nsplit - 1) / nsplit + 31) / 32 * 32);
         const size_t hist_smem = (size_t)per_slice * 4 + 4160;
         if (pl.Ksel >= 64 && hist_smem <= (size_t)kMaxDynSmem) {
+            select_fast_path_configure();
             select_keys_hist_kernel<<<dim3((unsigned)nq, nsplit), 256, hist_smem, st>>>(
                 ix.s_keys.p, ldk, (int)cols, std::min(k_need, pl.Ksel), pl.Ksel, ix.s_partial.p, pl.S, pl.used, (uint32_t)c0);
         } else {
@@ -314,21 +315,20 @@ launch_finalize(IndexBase& ix, FinalizeParams fp, int64_t nq) {
     KB2_REQUIRE(fp.n_sort <= kMaxSortEntries, KB2_INTERNAL_ERROR, "finalize: too many partial candidates");
     KB2_REQUIRE(fp.k_sel <= kMaxK && fp.k_out <= fp.k_sel, KB2_INVALID_ARGS, "k too large");
     static const bool warp_path = [] { const char* e = getenv("KB2_FINALIZE"); return !(e && !strcmp(e, "cta")); }();
-    if (warp_path && fp.k_sel <= 128 && fp.d <= 1024 && (fp.n_partial <= 512 || fp.counts)) {
-        // one warp per query (see finalize_warp_kernel); variable-length rows longer than 512 entries fall through to the
-        // CTA kernel below, which then skips the short ones
+    if (warp_path && fp.k_sel <= 128 && fp.d <= 1024 && (fp.n_partial <= 256 || fp.counts)) {
+        // one warp per query (see finalize_warp_kernel); variable-length rows longer than 256 entries fall through to the
+        // CTA kernel below, which then skips the short ones (measured at C3: a 512-entry register sort for the tail costs
+        // more than that second launch)
         const size_t smem_w = (size_t)kFinWarps * ((size_t)((fp.d + 3) & ~3) * 4 + 128 * 24);
         const unsigned g = (unsigned)((nq + kFinWarps - 1) / kFinWarps);
         if (fp.n_partial <= 128)
             finalize_warp_kernel<4><<<g, kFinWarps * 32, smem_w, ix.stream>>>(fp, nq);
-        else if (fp.n_partial <= 256)
-            finalize_warp_kernel<8><<<g, kFinWarps * 32, smem_w, ix.stream>>>(fp, nq);
         else
-            finalize_warp_kernel<16><<<g, kFinWarps * 32, smem_w, ix.stream>>>(fp, nq);
+            finalize_warp_kernel<8><<<g, kFinWarps * 32, smem_w, ix.stream>>>(fp, nq);
         ix.last.launches++;
         KB2_CUDA_CHECK(cudaGetLastError());
-        if (fp.n_partial <= 512) return;
-        fp.split_small = 512;
+        if (fp.n_partial <= 256) return;
+        fp.split_small = 256;
     }
     const size_t smem = (size_t)fp.n_sort * 8 + (size_t)fp.k_sel * 16 + (size_t)fp.d * 4 + 16;
     finalize_kernel<<<(unsigned)nq, 256, smem, ix.stream>>>(fp);
@@ -1394,7 +1394,6 @@ struct IvfIndex : IndexBase {
         fp.k_sel = (int)std::min<int64_t>(std::min(pl.Ksel, nprobe + 16), nlist);
         fp.k_out = nprobe;
         fp.rerank = 1;
-        fp.rerank_all = 1;
         fp.raw = centroids.p;
         fp.raw_by_pos = 1;
         fp.queries = dq + q_lo * dim;

@@ -239,8 +239,6 @@ struct FinalizeParams {
     const uint32_t* counts;    // optional [nq]: only the first min(counts[q], n_partial) entries of a row are valid ...
     const uint32_t* count_flags;   // ... unless count_flags[q] != 0 (then all n_partial are)
     int split_small;           // > 0: rows with at most this many valid entries were handled by finalize_warp_kernel: skip them
-    int rerank_all;            // 1 (with rerank, n_partial <= 128): exact keys for EVERY candidate instead of the k_sel best by
-                               // approximate key (IVF coarse stage: a superset can only move the result toward the exact top-k)
 };
 
 // dynamic smem: n_sort*8 + k_sel*(4+8+4) + d*4
@@ -502,15 +500,15 @@ constexpr int kFinWarps = 4;
 template <int EPL>
 __device__ __forceinline__ void
 finalize_warp_select(const FinalizeParams& p, const uint64_t* __restrict__ src, int n, int lane, uint32_t* s_pos, float* s_key,
-                     int64_t* s_label, bool sort) {
+                     int64_t* s_label) {
     uint64_t e[EPL];
 #pragma unroll
     for (int r = 0; r < EPL; r++) {
         const int i = lane * EPL + r;
         e[r] = (i < n) ? src[i] : kEmpty;
     }
-    if (sort) warp_bitonic<uint64_t, EPL>(e, lane);
-    const int ksel = sort ? p.k_sel : n;
+    warp_bitonic<uint64_t, EPL>(e, lane);
+    const int ksel = p.k_sel;
 #pragma unroll
     for (int r = 0; r < EPL; r++) {
         const int i = lane * EPL + r;
@@ -548,18 +546,17 @@ finalize_warp_kernel(FinalizeParams p, int64_t nq) {
     const int64_t q = (int64_t)blockIdx.x * kFinWarps + warp;
     if (q >= nq) return;
 
-    // ---- 1. approximate order (skipped with rerank_all: every candidate gets an exact key)
+    // ---- 1. approximate order
     int n = p.n_partial;
     if (p.counts && !(p.count_flags && p.count_flags[q])) n = (int)min(p.counts[q], (uint32_t)p.n_partial);
     if (n > 32 * EPLMAX) return;   // (only with p.split_small) left to finalize_kernel
     const uint64_t* src = p.partial + q * p.partial_stride;
     if (p.rerank)
         for (int j = lane; j < p.d; j += kWarp) s_q[j] = p.queries[q * p.d + j];
-    const bool all = p.rerank_all && p.rerank && n <= 128;
-    if (EPLMAX >= 16 && n > 256) finalize_warp_select<(EPLMAX >= 16 ? 16 : 4)>(p, src, n, lane, s_pos, s_key, s_label, true);
-    else if (EPLMAX >= 8 && n > 128) finalize_warp_select<(EPLMAX >= 8 ? 8 : 4)>(p, src, n, lane, s_pos, s_key, s_label, true);
-    else finalize_warp_select<4>(p, src, n, lane, s_pos, s_key, s_label, !all);
-    const int ksel = all ? n : p.k_sel;
+    if (EPLMAX >= 16 && n > 256) finalize_warp_select<(EPLMAX >= 16 ? 16 : 4)>(p, src, n, lane, s_pos, s_key, s_label);
+    else if (EPLMAX >= 8 && n > 128) finalize_warp_select<(EPLMAX >= 8 ? 8 : 4)>(p, src, n, lane, s_pos, s_key, s_label);
+    else finalize_warp_select<4>(p, src, n, lane, s_pos, s_key, s_label);
+    const int ksel = p.k_sel;
     __syncwarp();
 
     // ---- 2. exact keys (same arithmetic and summation order as finalize_kernel)
