@@ -48,6 +48,16 @@ METRIC_NAME = "queries/sec at recall@10>=0.95, 10Mx128 f32 IVF_PQ"
 TARGET_RECALL = 0.95
 
 
+def l2_policy(wl, n, d):
+    """what makes the timed region independent of the 126 MB L2 (bench contract: inputs larger than L2, or a flush)"""
+    if wl["index"] == "IVF_PQ":
+        return (f"inputs larger than L2: every step streams the probed lists' codes (the whole {n * wl['build']['m'] / 1e6:.0f} MB "
+                f"code array is touched at this nprobe) and gathers refine rows from a {n * d * 4 / 1e9:.1f} GB store")
+    if wl["index"] == "IVF_FLAT":
+        return f"inputs larger than L2: every step streams the probed lists' fp32 rows (store of {n * d * 4 / 1e6:.0f} MB)"
+    return f"inputs larger than L2: random rows of a {n * d * 4 / 1e9:.2f} GB vector store + {n * 4 * 2 * wl['build'].get('M', 16) / 1e6:.0f} MB of links"
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -435,9 +445,7 @@ def run_ours(args):
                                f", batch={nq}, k={k}",
                    "recall_at_10": recall, "recall_queries": n_gt, "refine_k": cfg.get("refine_k"),
                    "data": "clustered low-rank gaussian mixture, seeds base 42 / query 43 (SURVEY 8d)",
-                   "l2_policy": ("inputs larger than L2: every step streams the probed lists' codes (the whole code array, "
-                                 f"{n * wl['build'].get('m', d * 4) / 1e6:.0f} MB, is touched at this nprobe) and gathers refine rows "
-                                 f"from a {n * d * 4 / 1e9:.1f} GB store; L2 is 126 MB"),
+                   "l2_policy": l2_policy(wl, n, d),
                    "sharding": ("inverted lists packed onto the ranks by size, collectives inside libknowhere_b200.so (kb2_comm_*): probe "
                                 "all-gather, bound all-reduce, one all-gather of per-shard top-k + merge kernel")
                    if world > 1 else "single GPU",

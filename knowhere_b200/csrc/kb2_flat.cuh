@@ -180,19 +180,6 @@ select_keys_kernel(const float* __restrict__ keys, int64_t ldk, int ncols, int K
 // (finalize / reduce sort their input anyway).  It always contains the K_need smallest keys: if the
 // prefix would hold fewer than K_need, the next bin is drained in (key, position) order (rare).
 // grid (nq, nsplit), block 256, dynamic smem: slice*4 + 4160 bytes.
-// KB2_SELECT=hist (host) clears this flag: A/B switch for the minima fast path of select_keys_hist_kernel
-__device__ int g_select_fast = 1;
-__device__ __forceinline__ bool select_fast_path() { return g_select_fast != 0; }
-inline void
-select_fast_path_configure() {
-    static PerDeviceOnce once;
-    once.run([] {
-        const char* e = getenv("KB2_SELECT");
-        const int v = (e && !strcmp(e, "hist")) ? 0 : 1;
-        cudaMemcpyToSymbol(g_select_fast, &v, sizeof(int));
-    });
-}
-
 __global__ void __launch_bounds__(256)
 select_keys_hist_kernel(const float* __restrict__ keys, int64_t ldk, int ncols, int K_need, int K_cap,
                         uint64_t* __restrict__ partial, int slots_per_query, int slot_base, uint32_t pos_base) {
@@ -216,9 +203,8 @@ select_keys_hist_kernel(const float* __restrict__ keys, int64_t ldk, int ncols, 
         if (v < kInfOrd) { lmin = min(lmin, v); lmax = max(lmax, v); }
     }
     for (int i = threadIdx.x; i < 1032; i += blockDim.x) hist[i] = 0;
-    if (threadIdx.x == 0) { ctl[0] = 0xffffffffu; ctl[1] = 0; ctl[2] = 0; ctl[6] = 0; }
+    if (threadIdx.x == 0) { ctl[0] = 0xffffffffu; ctl[1] = 0; ctl[2] = 0; }
     __syncthreads();
-    const uint32_t my_min = lmin;   // this thread's smallest key (thread t holds keys t, t + 256, ...)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
@@ -239,62 +225,6 @@ select_keys_hist_kernel(const float* __restrict__ keys, int64_t ldk, int ncols, 
     const uint32_t range = vmax - vmin;
     const int shift = range < 1024u ? 0 : (32 - __clz(range)) - 10;
     const int nbins = (int)(range >> shift) + 1;   // <= 1024
-    // ---- fast path.  The K_need-th smallest of the per-thread minima is an upper bound of the K_need-th smallest key (those
-    // minima are K_need distinct keys), and with n / 256 keys per thread only ~K_need * (1 + K_need / 512) keys lie below it:
-    // histogram the 256 MINIMA (one shared atomic per thread instead of one per key -- the atomics were this kernel's cost,
-    // ncu r2: 0.18 ms at 10000 x 4096), take the bins up to the one holding the K_need-th minimum, and emit every key in those
-    // bins if at most K_cap qualify.  Otherwise fall through to the histogram of all keys.
-    if (select_fast_path() && K_need <= 192 && n >= 1024 && blockDim.x == 256) {
-        if (my_min < kInfOrd) atomicAdd(&hist[(my_min - vmin) >> shift], 1u);
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            const int lane = threadIdx.x;
-            uint32_t sum = 0;
-            for (int t = 0; t < 32; t++) sum += hist[lane * 32 + t];
-            uint32_t incl = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            const uint32_t excl = incl - sum;
-            const bool crosses = excl < (uint32_t)K_need && incl >= (uint32_t)K_need;
-            if (__ballot_sync(0xffffffffu, crosses) == 0 && lane == 0) ctl[3] = 0;   // fewer than K_need finite minima
-            if (crosses) {
-                uint32_t run = excl;
-                int b = lane * 32;
-                for (int t = 0; t < 32; t++) {
-                    run += hist[lane * 32 + t];
-                    if (run >= (uint32_t)K_need) { b = lane * 32 + t; break; }
-                }
-                ctl[3] = (uint32_t)b + 1;   // bins [0, b] are taken
-            }
-        }
-        __syncthreads();
-        const uint32_t bfast = ctl[3];
-        uint32_t cnt = 0;
-        if (bfast > 0)
-            for (int i = threadIdx.x; i < n; i += blockDim.x) {
-                const uint32_t v = ord[i];
-                cnt += (v < kInfOrd && ((v - vmin) >> shift) < bfast);
-            }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&ctl[6], cnt);
-        for (int i = threadIdx.x; i < 1032; i += blockDim.x) hist[i] = 0;   // clean for the fallback
-        __syncthreads();
-        const uint32_t total = ctl[6];
-        if (bfast > 0 && total <= (uint32_t)K_cap) {   // CTA-uniform; total >= K_need by construction
-            for (int i = threadIdx.x; i < n; i += blockDim.x) {
-                const uint32_t v = ord[i];
-                if (v < kInfOrd && ((v - vmin) >> shift) < bfast)
-                    out[atomicAdd(&ctl[2], 1u)] = ((uint64_t)v << 32) | (pos_base + (uint32_t)(c0 + i));
-            }
-            __syncthreads();
-            for (int i = ctl[2] + threadIdx.x; i < K_cap; i += blockDim.x) out[i] = kEmpty;
-            return;
-        }
-    }
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const uint32_t v = ord[i];
         if (v < kInfOrd) atomicAdd(&hist[(v - vmin) >> shift], 1u);

@@ -295,7 +295,6 @@ dense_candidates(IndexBase& ix, const float* Q, int64_t nq, const float* X, cons
         const int per_slice = (int)(((cols + nsplit - 1) / nsplit + 31) / 32 * 32);
         const size_t hist_smem = (size_t)per_slice * 4 + 4160;
         if (pl.Ksel >= 64 && hist_smem <= (size_t)kMaxDynSmem) {
-            select_fast_path_configure();
             select_keys_hist_kernel<<<dim3((unsigned)nq, nsplit), 256, hist_smem, st>>>(
                 ix.s_keys.p, ldk, (int)cols, std::min(k_need, pl.Ksel), pl.Ksel, ix.s_partial.p, pl.S, pl.used, (uint32_t)c0);
         } else {

@@ -450,14 +450,6 @@ __device__ __forceinline__ bool
 fin_less(uint64_t a, uint64_t b) {
     return a < b;
 }
-__device__ __forceinline__ uint32_t
-fin_shfl_xor(uint32_t a, int m) {
-    return __shfl_xor_sync(0xffffffffu, a, m);
-}
-__device__ __forceinline__ bool
-fin_less(uint32_t a, uint32_t b) {
-    return a < b;
-}
 // ascending bitonic sort of 32 * EPL elements held EPL per lane (index = lane * EPL + r)
 template <typename T, int EPL>
 __device__ __forceinline__ void
