@@ -222,71 +222,79 @@ select_keys_hist_kernel(const float* __restrict__ keys, int64_t ldk, int ncols, 
         for (int i = ctl[2] + threadIdx.x; i < K_cap; i += blockDim.x) out[i] = kEmpty;
         return;
     }
-    const uint32_t range = vmax - vmin;
-    const int shift = range < 1024u ? 0 : (32 - __clz(range)) - 10;
-    const int nbins = (int)(range >> shift) + 1;   // <= 1024
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const uint32_t v = ord[i];
-        if (v < kInfOrd) atomicAdd(&hist[(v - vmin) >> shift], 1u);
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        // warp 0: scan 32 bins per lane, find the largest prefix with cumulative count <= K_cap
-        const int lane = threadIdx.x;
-        uint32_t sum = 0;
-        for (int t = 0; t < 32; t++) sum += hist[lane * 32 + t];
-        uint32_t incl = sum;
+    // Level-wise refinement: histogram the keys of the current value range into <= 1024 bins, emit the largest bin prefix
+    // that still fits, and if that prefix holds fewer than the keys still needed descend into the crossing bin (its range
+    // is 2^shift values: at most 4 levels for 32-bit keys).  Key distributions with outliers (inner products: a few huge
+    // values stretch the range so that most keys share one bin) therefore cost one more pass, not a serial drain.
+    uint32_t base = vmin, span = vmax - vmin;   // current range [base, base + span]
+    uint32_t need = (uint32_t)K_need, cap = (uint32_t)K_cap;
+    for (int level = 0; level < 5; level++) {
+        const int shift = span < 1024u ? 0 : (32 - __clz(span)) - 10;
+        const int nbins = (int)(span >> shift) + 1;   // <= 1024
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint32_t v = ord[i];
+            if (v < kInfOrd && v >= base && v - base <= span) atomicAdd(&hist[(v - base) >> shift], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            // warp 0: scan 32 bins per lane, find the largest prefix with cumulative count <= cap
+            const int lane = threadIdx.x;
+            uint32_t sum = 0;
+            for (int t = 0; t < 32; t++) sum += hist[lane * 32 + t];
+            uint32_t incl = sum;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        const uint32_t excl = incl - sum;
-        // lane owning the crossing: excl <= K_cap < incl ; if total <= K_cap no lane crosses
-        const bool crosses = excl <= (uint32_t)K_cap && incl > (uint32_t)K_cap;
-        const unsigned who = __ballot_sync(0xffffffffu, crosses);
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        if (who == 0 && lane == 0) { ctl[3] = (uint32_t)nbins; ctl[4] = total; }
-        if (crosses) {
-            uint32_t run = excl;
-            int b = lane * 32;
-            for (int t = 0; t < 32; t++) {
-                const uint32_t h = hist[lane * 32 + t];
-                if (run + h > (uint32_t)K_cap) { b = lane * 32 + t; break; }
-                run += h;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
             }
-            ctl[3] = (uint32_t)b;   // bins [0, b) are taken: cum = run <= K_cap
-            ctl[4] = run;
-        }
-    }
-    __syncthreads();
-    const uint32_t btake = ctl[3];
-    const uint32_t taken = ctl[4];
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const uint32_t v = ord[i];
-        if (v < kInfOrd && ((v - vmin) >> shift) < btake)
-            out[atomicAdd(&ctl[2], 1u)] = ((uint64_t)v << 32) | (pos_base + (uint32_t)(c0 + i));
-    }
-    __syncthreads();
-    if (threadIdx.x == 0 && taken < (uint32_t)K_need && btake < (uint32_t)nbins) {
-        // the crossing bin holds more keys than fit: drain it in (key, position) order until K_need is reached
-        uint32_t slot = ctl[2];
-        uint64_t last = 0;
-        bool first = true;
-        for (uint32_t need = (uint32_t)K_need - taken; need > 0; need--) {
-            uint64_t best = kEmpty;
-            for (int i = 0; i < n; i++) {
-                const uint32_t v = ord[i];
-                if (v >= kInfOrd || ((v - vmin) >> shift) != btake) continue;
-                const uint64_t c = ((uint64_t)v << 32) | (pos_base + (uint32_t)(c0 + i));
-                if ((first || c > last) && c < best) best = c;
+            const uint32_t excl = incl - sum;
+            // lane owning the crossing: excl <= cap < incl ; if total <= cap no lane crosses
+            const bool crosses = excl <= cap && incl > cap;
+            const unsigned who = __ballot_sync(0xffffffffu, crosses);
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            if (who == 0 && lane == 0) { ctl[3] = (uint32_t)nbins; ctl[4] = total; ctl[5] = 0; }
+            if (crosses) {
+                uint32_t run = excl, hb = 0;
+                int b = lane * 32;
+                for (int t = 0; t < 32; t++) {
+                    const uint32_t h = hist[lane * 32 + t];
+                    if (run + h > cap) { b = lane * 32 + t; hb = h; break; }
+                    run += h;
+                }
+                ctl[3] = (uint32_t)b;   // bins [0, b) are taken: cum = run <= cap
+                ctl[4] = run;
+                ctl[5] = hb;            // population of the crossing bin
             }
-            if (best == kEmpty) break;
-            out[slot++] = best;
-            last = best;
-            first = false;
         }
-        ctl[2] = slot;
+        __syncthreads();
+        const uint32_t btake = ctl[3];
+        const uint32_t taken = ctl[4];
+        const uint32_t in_cross = ctl[5];
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint32_t v = ord[i];
+            if (v < kInfOrd && v >= base && v - base <= span && ((v - base) >> shift) < btake)
+                out[atomicAdd(&ctl[2], 1u)] = ((uint64_t)v << 32) | (pos_base + (uint32_t)(c0 + i));
+        }
+        for (int i = threadIdx.x; i < 1032; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        if (taken >= need || btake >= (uint32_t)nbins) break;   // enough emitted, or nothing left in this range
+        need -= taken;
+        cap -= taken;
+        if (shift == 0) {
+            // the crossing bin is a single key value held by more entries than fit: any `need` of them complete the
+            // selection (equal keys); take them in position order
+            if (threadIdx.x == 0) {
+                const uint32_t v0 = base + btake;
+                uint32_t slot = ctl[2];
+                for (int i = 0; i < n && need > 0; i++)
+                    if (ord[i] == v0) { out[slot++] = ((uint64_t)v0 << 32) | (pos_base + (uint32_t)(c0 + i)); need--; }
+                ctl[2] = slot;
+            }
+            (void)in_cross;
+            break;
+        }
+        base += btake << shift;
+        span = (1u << shift) - 1u;
     }
     __syncthreads();
     for (int i = ctl[2] + threadIdx.x; i < K_cap; i += blockDim.x) out[i] = kEmpty;

@@ -75,6 +75,8 @@ init_kernel_attributes() {
         set((const void*)pqtc::bound_kernel<KB2_METRIC_IP, 32>);
         set((const void*)pqtc::bound_kernel<KB2_METRIC_L2, 64>);
         set((const void*)pqtc::bound_kernel<KB2_METRIC_IP, 64>);
+        set((const void*)pqtc::bound_kernel<KB2_METRIC_L2, 32, 3, 2>);
+        set((const void*)pqtc::bound_kernel<KB2_METRIC_IP, 32, 3, 2>);
         set((const void*)fltc::ivfflat_tc_kernel<KB2_METRIC_L2, 32>);
         set((const void*)fltc::ivfflat_tc_kernel<KB2_METRIC_IP, 32>);
         set((const void*)fltc::ivfflat_tc_kernel<KB2_METRIC_L2, 128>);
@@ -839,6 +841,7 @@ struct IvfIndex : IndexBase {
     // ---------------------------------------------------------------- list-major tensor-core engine (kb2_ivfpq_tc.cuh)
     static constexpr int kTcCandCap = 2048;     // survivor slots per query (overflow -> LUT kernel redoes the query)
     DevBuf<uint16_t> tc_pqc16, s_qb16;
+    DevBuf<float> tc_pqc_t;   // codebook transposed for the in-kernel tables of bound_kernel<..., 3, 2>
     DevBuf<float> tc_maxn2, s_qnorm, s_pair_base, s_lut, s_bound;
     DevBuf<int32_t> s_lcount, s_lstart, s_items, s_pair_q, s_plan_out, s_flaglist, s_resp;
     DevBuf<uint64_t> s_cand;
@@ -900,6 +903,10 @@ struct IvfIndex : IndexBase {
             tc_maxn2.alloc_exact(M + 4);
             KB2_CUDA_CHECK(cudaMemsetAsync(tc_maxn2.p + M, 0, 16, st));
             pqtc::prepare_tables_kernel<<<M, 256, 0, st>>>(pqc.p, dsub, (__nv_bfloat16*)tc_pqc16.p, tc_maxn2.p);
+            if (tc_geom_32()) {
+                tc_pqc_t.alloc_exact((size_t)M * 256 * dsub);
+                pqtc::transpose_codebook_kernel<<<grid1d((int64_t)M * 256 * dsub, 256), 256, 0, st>>>(pqc.p, M, dsub, tc_pqc_t.p);
+            }
             if (metric == KB2_METRIC_L2 && npad > 0)
                 pqtc::max_abs_kernel<<<kNumSMs * 2, 256, 0, st>>>(t1.p, npad, (uint32_t*)(tc_maxn2.p + M));
             if (dsub < 8) {
@@ -936,8 +943,9 @@ struct IvfIndex : IndexBase {
         const int p0 = std::max(1, std::min((e_p0 ? atoi(e_p0) : 8) * std::max(1, shard_world), nprobe));   // at most this many lists
         const int a_codes = e_ac ? atoi(e_ac) : 3000;                                                        // ... until this many codes
         s_bound.ensure((size_t)nq);
-        if (tc_geom_18()) {
-        s_lut.ensure((size_t)nq * 4096);
+        static const bool generic_a = [] { const char* e = getenv("KB2_TC_PHASE_A"); return e && !strcmp(e, "scan"); }();
+        if (tc_geom_18() || (tc_geom_32() && !generic_a)) {
+        if (tc_geom_18()) s_lut.ensure((size_t)nq * 4096);
         const int32_t* qlist = nullptr;
         const uint32_t* qcount = nullptr;
         unsigned bound_grid = (unsigned)nq;
@@ -961,7 +969,15 @@ struct IvfIndex : IndexBase {
     pqtc::bound_kernel<MM, RW><<<bound_grid, 128, smem, st>>>(s_lut.p, qlist, qcount, nq, sp.probe_ids, sp.probe_dis, nprobe, p0,   \
                                                              a_codes, k_base, list_off.p, list_len.p, (const uint4*)codes.p, t1.p, \
                                                              sp.bitset, rows.p, s_bound.p, d_counter.p + 4);
-            if (metric == KB2_METRIC_L2) {
+            if (tc_geom_32()) {
+                // m48 x dsub2: three groups through one in-kernel table each (no [nq][m][256] table in global memory)
+#define KB2_BOUND_LAUNCH3(MM)                                                                                                       \
+    pqtc::bound_kernel<MM, 32, 3, 2><<<bound_grid, 128, pqtc::bound_smem(32), st>>>(                                                \
+        nullptr, qlist, qcount, nq, sp.probe_ids, sp.probe_dis, nprobe, p0, a_codes, k_base, list_off.p, list_len.p,                \
+        (const uint4*)codes.p, t1.p, sp.bitset, rows.p, s_bound.p, d_counter.p + 4, npad, sp.queries, tc_pqc_t.p);
+                if (metric == KB2_METRIC_L2) { KB2_BOUND_LAUNCH3(KB2_METRIC_L2) } else { KB2_BOUND_LAUNCH3(KB2_METRIC_IP) }
+#undef KB2_BOUND_LAUNCH3
+            } else if (metric == KB2_METRIC_L2) {
                 if (roww == 32) { KB2_BOUND_LAUNCH(KB2_METRIC_L2, 32) } else { KB2_BOUND_LAUNCH(KB2_METRIC_L2, 64) }
             } else {
                 if (roww == 32) { KB2_BOUND_LAUNCH(KB2_METRIC_IP, 32) } else { KB2_BOUND_LAUNCH(KB2_METRIC_IP, 64) }

@@ -983,6 +983,17 @@ compact_flags_kernel(const uint32_t* __restrict__ qflag, int64_t nq, int32_t* __
         asm("ld.shared.f32 %0, [%1+%2];" : "=f"(_v) : "r"(_x >> (ROWW == 32 ? 1 : 0)), "n"(KB2_SMEM_BASE + 4 * (S))); \
         ACC += _v;                                                                            \
     }
+// pqc [M][256][dsub] -> pqc_t [M/16][256][16][dsub] (the 16 sub-quantizers of a group adjacent: coalesced table builds)
+__global__ void
+transpose_codebook_kernel(const float* __restrict__ pqc, int M, int dsub, float* __restrict__ pqc_t) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n = (int64_t)M * 256 * dsub;
+    if (i >= n) return;
+    const int x = (int)(i % dsub);
+    const int j = (int)((i / dsub) % 256);
+    const int m = (int)(i / ((int64_t)dsub * 256));
+    pqc_t[((((int64_t)(m >> 4) * 256 + j) * 16) + (m & 15)) * dsub + x] = pqc[i];
+}
 constexpr int BOUND_KMAX = 6144;    // keys held per query (phase A looks at no more codes than this)
 constexpr int BOUND_BINS = 1024;
 // ROWW = words per code-value row of the skewed table: 32 (32 KB: lanes i and i+16 share a bank, 2 wavefronts per gather,
@@ -990,14 +1001,20 @@ constexpr int BOUND_BINS = 1024;
 constexpr size_t bound_smem(int roww) { return (size_t)roww * 1024 + BOUND_KMAX * 4 + BOUND_BINS * 4 + 64; }
 constexpr size_t BOUND_SMEM = bound_smem(32);
 
-template <int METRIC, int ROWW>
+// G > 1 (m = 16 G sub-quantizers, e.g. m48 x dsub2): the groups are scanned one after the other through the same 32 KB
+// table -- group g's table is built in the kernel from the query and the transposed codebook `pqc_t`
+// ([g][code value][16 sub-quantizers][dsub], see transpose_codebook_kernel), the partial sums of the earlier groups wait in
+// the shared key array.
+template <int METRIC, int ROWW, int G = 1, int DSUB = 8>
 __global__ void __launch_bounds__(128)
 bound_kernel(const float* __restrict__ lut, const int32_t* __restrict__ qlist, const uint32_t* __restrict__ qcount, int64_t nq,
              const int64_t* __restrict__ probe_ids, const float* __restrict__ probe_dis,
              int probe_stride, int p0_max, int min_codes, int k_need, const int64_t* __restrict__ list_off,
              const int32_t* __restrict__ list_len, const uint4* __restrict__ codes, const float* __restrict__ t1,
              const uint8_t* __restrict__ bitset, const int32_t* __restrict__ rows, float* __restrict__ out,
-             unsigned long long* __restrict__ counters) {
+             unsigned long long* __restrict__ counters, int64_t npad = 0, const float* __restrict__ queries = nullptr,
+             const float* __restrict__ pqc_t = nullptr) {
+    static_assert(G == 1 || ROWW == 32, "multi-group phase A uses the 32-word table rows");
     // work list: table i / query qlist[i] for i < *qcount (qlist == NULL: query i, i < nq); CTAs stride the list
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* s_lut = (float*)smem_raw;                              // [256][ROWW]
@@ -1012,8 +1029,28 @@ bound_kernel(const float* __restrict__ lut, const int32_t* __restrict__ qlist, c
     const int64_t n_work = qlist ? (int64_t)*qcount : nq;
     for (int64_t wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
     const int64_t q = qlist ? (int64_t)qlist[wi] : wi;
+    int seen = 0, n_tot = 0;
+    float kmin = INFINITY, kmax = -INFINITY;
+#pragma unroll 1
+    for (int g = 0; g < G; g++) {
     __syncthreads();   // the previous iteration's readers of the shared tables are done
-    {
+    if constexpr (G > 1 || DSUB != 8) {
+        // table of group g from the query: entry (j, mm) = scale * <q_m, c_pq[m][j]>, m = 16 g + mm
+        const float scale = (METRIC == KB2_METRIC_L2) ? -2.f : -1.f;
+        const int mm = threadIdx.x & 15, jsub = threadIdx.x >> 4;   // 16 sub-quantizers x 8 code values per pass
+        float qv[DSUB];
+#pragma unroll
+        for (int x = 0; x < DSUB; x++) qv[x] = queries[q * (int64_t)(16 * G * DSUB) + (g * 16 + mm) * DSUB + x];
+        for (int j = jsub; j < 256; j += 8) {
+            const float* cp = pqc_t + (((size_t)g * 256 + j) * 16 + mm) * DSUB;
+            float a = 0.f;
+#pragma unroll
+            for (int x = 0; x < DSUB; x++) a = fmaf(qv[x], __ldg(cp + x), a);
+            a *= scale;
+            s_lut[j * ROWW + mm] = a;
+            s_lut[j * ROWW + 16 + mm] = a;
+        }
+    } else {
         // lut[q][j*16 + m] -> s_lut[j*32 + m] and s_lut[j*32 + 16 + m]
         const float4* src = reinterpret_cast<const float4*>(lut + wi * 4096);
 #pragma unroll
@@ -1026,13 +1063,16 @@ bound_kernel(const float* __restrict__ lut, const int32_t* __restrict__ qlist, c
             if (ROWW == 64) { dst[8] = v; dst[12] = v; }
         }
     }
-    for (int i = threadIdx.x; i < BOUND_BINS; i += 128) s_hist[i] = 0;
+    if (g == 0)
+        for (int i = threadIdx.x; i < BOUND_BINS; i += 128) s_hist[i] = 0;
     __syncthreads();
     // PRMT builds (byte << 8) | (lane16 << 3) ; >> 1 = byte * 128 + lane16 * 4 (row pitch 128 B)
     // ROWW = 64: (byte << 8) | (lane << 2) is the address itself (row pitch 256 B, word lane + s)
     const uint32_t lane4 = (ROWW == 32) ? ((uint32_t)(lane & 15) << 3) : ((uint32_t)lane << 2);
-    int seen = 0, n_tot = 0;
-    float kmin = INFINITY, kmax = -INFINITY;
+    const uint4* gcodes = codes + (int64_t)g * npad;   // code plane of this group
+    const bool first_g = (g == 0), last_g = (g == G - 1);
+    seen = 0;
+    n_tot = 0;
     const int code_cap = min(BOUND_KMAX, max(min_codes, k_need));   // scan no more than the requested number of codes
     for (int j = 0; j < p0_max && seen < min_codes && n_tot < code_cap; j++) {
         const int64_t l = probe_ids[q * probe_stride + j];
@@ -1050,11 +1090,11 @@ bound_kernel(const float* __restrict__ lut, const int32_t* __restrict__ qlist, c
         float ntA = 0.f, ntB = 0.f;
         auto load_iter = [&](int c0) {
             if (c0 < len) {
-                nA = ldg_stream_u4(codes + off + c0 + lane);        // inside the padded position space even past len
-                if (METRIC == KB2_METRIC_L2) ntA = __ldg(t1 + off + c0 + lane);
+                nA = ldg_stream_u4(gcodes + off + c0 + lane);        // inside the padded position space even past len
+                if (METRIC == KB2_METRIC_L2 && first_g) ntA = __ldg(t1 + off + c0 + lane);
                 if (c0 + 32 < len) {
-                    nB = ldg_stream_u4(codes + off + c0 + 32 + lane);
-                    if (METRIC == KB2_METRIC_L2) ntB = __ldg(t1 + off + c0 + 32 + lane);
+                    nB = ldg_stream_u4(gcodes + off + c0 + 32 + lane);
+                    if (METRIC == KB2_METRIC_L2 && first_g) ntB = __ldg(t1 + off + c0 + 32 + lane);
                 }
             }
         };
@@ -1076,20 +1116,22 @@ bound_kernel(const float* __restrict__ lut, const int32_t* __restrict__ qlist, c
             KB2_BOUND_STEP(wA.z, 2, 10, a0) KB2_BOUND_STEP(wB.z, 2, 10, b0) KB2_BOUND_STEP(wA.z, 3, 11, a1) KB2_BOUND_STEP(wB.z, 3, 11, b1)
             KB2_BOUND_STEP(wA.w, 0, 12, a0) KB2_BOUND_STEP(wB.w, 0, 12, b0) KB2_BOUND_STEP(wA.w, 1, 13, a1) KB2_BOUND_STEP(wB.w, 1, 13, b1)
             KB2_BOUND_STEP(wA.w, 2, 14, a0) KB2_BOUND_STEP(wB.w, 2, 14, b0) KB2_BOUND_STEP(wA.w, 3, 15, a1) KB2_BOUND_STEP(wB.w, 3, 15, b1)
-            float keyA = base + (a0 + a1), keyB = base + (b0 + b1);
+            float keyA = (first_g ? base : s_keys[n_tot + (okA ? relA : 0)]) + (a0 + a1);
+            float keyB = (first_g ? base : s_keys[n_tot + ((hasB && okB) ? relB : 0)]) + (b0 + b1);
             if (okA) {
-                if (bitset && bit_is_set(bitset, rows[posA])) keyA = INFINITY;
+                if (last_g && bitset && bit_is_set(bitset, rows[posA])) keyA = INFINITY;
                 s_keys[n_tot + relA] = keyA;
-                if (keyA < INFINITY) { kmin = fminf(kmin, keyA); kmax = fmaxf(kmax, keyA); }
+                if (last_g && keyA < INFINITY) { kmin = fminf(kmin, keyA); kmax = fmaxf(kmax, keyA); }
             }
             if (hasB && okB) {
-                if (bitset && bit_is_set(bitset, rows[posB])) keyB = INFINITY;
+                if (last_g && bitset && bit_is_set(bitset, rows[posB])) keyB = INFINITY;
                 s_keys[n_tot + relB] = keyB;
-                if (keyB < INFINITY) { kmin = fminf(kmin, keyB); kmax = fmaxf(kmax, keyB); }
+                if (last_g && keyB < INFINITY) { kmin = fminf(kmin, keyB); kmax = fmaxf(kmax, keyB); }
             }
         }
         n_tot += len;
     }
+    }   // groups
     // ---- K-th smallest key, rounded UP to the edge of one of 1024 linear bins over [min, max]: any value >= the
     //      k_need-th best is a valid admission bound, and a bin is far narrower than the filter's error margin
 #pragma unroll
@@ -1134,7 +1176,7 @@ bound_kernel(const float* __restrict__ lut, const int32_t* __restrict__ qlist, c
             if (cum < need) { cum += mine[bb]; b = bb; }
         }
         const float bound = (scale > 0.f) ? lo + ((float)(threadIdx.x * 8 + b) + 1.01f) / scale : hi;
-        out[q] = fmaxf(bound, lo) + 4e-7f * fmaxf(fabsf(lo), fabsf(hi));
+        out[q] = fmaxf(bound, lo) + (G == 1 ? 4e-7f : 2e-6f) * fmaxf(fabsf(lo), fabsf(hi));
     }
     }   // work list
 }
