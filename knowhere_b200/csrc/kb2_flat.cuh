@@ -252,32 +252,31 @@ select_keys_hist_kernel(const float* __restrict__ keys, int64_t ldk, int ncols, 
             const bool crosses = excl <= cap && incl > cap;
             const unsigned who = __ballot_sync(0xffffffffu, crosses);
             const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-            if (who == 0 && lane == 0) { ctl[3] = (uint32_t)nbins; ctl[4] = total; ctl[5] = 0; }
+            if (who == 0 && lane == 0) { ctl[3] = (uint32_t)nbins; ctl[4] = total; }
             if (crosses) {
-                uint32_t run = excl, hb = 0;
+                uint32_t run = excl;
                 int b = lane * 32;
                 for (int t = 0; t < 32; t++) {
                     const uint32_t h = hist[lane * 32 + t];
-                    if (run + h > cap) { b = lane * 32 + t; hb = h; break; }
+                    if (run + h > cap) { b = lane * 32 + t; break; }
                     run += h;
                 }
                 ctl[3] = (uint32_t)b;   // bins [0, b) are taken: cum = run <= cap
                 ctl[4] = run;
-                ctl[5] = hb;            // population of the crossing bin
             }
         }
         __syncthreads();
         const uint32_t btake = ctl[3];
         const uint32_t taken = ctl[4];
-        const uint32_t in_cross = ctl[5];
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
             const uint32_t v = ord[i];
             if (v < kInfOrd && v >= base && v - base <= span && ((v - base) >> shift) < btake)
                 out[atomicAdd(&ctl[2], 1u)] = ((uint64_t)v << 32) | (pos_base + (uint32_t)(c0 + i));
         }
+        __syncthreads();
+        if (taken >= need || btake >= (uint32_t)nbins) break;   // enough emitted, or nothing left in this range (CTA-uniform)
         for (int i = threadIdx.x; i < 1032; i += blockDim.x) hist[i] = 0;
         __syncthreads();
-        if (taken >= need || btake >= (uint32_t)nbins) break;   // enough emitted, or nothing left in this range
         need -= taken;
         cap -= taken;
         if (shift == 0) {
@@ -290,7 +289,6 @@ select_keys_hist_kernel(const float* __restrict__ keys, int64_t ldk, int ncols, 
                     if (ord[i] == v0) { out[slot++] = ((uint64_t)v0 << 32) | (pos_base + (uint32_t)(c0 + i)); need--; }
                 ctl[2] = slot;
             }
-            (void)in_cross;
             break;
         }
         base += btake << shift;
