@@ -890,8 +890,11 @@ struct IvfIndex : IndexBase {
         if (e && !strcmp(e, "lut")) return false;
         if (nprobe < 8 || Ksel > kTcCandCap / 2) return false;
         if (e && !strcmp(e, "tc")) return true;
-        // the decode of a list is amortised over the queries that probe it: needs a few dozen per list
-        return (double)nq * nprobe >= 32.0 * (double)nlist;
+        // the decode of a list is amortised over the queries that probe it.  Measured at C5 (100M x 96, nlist 65536, 19.5
+        // queries per list on average): the query-major LUT engine needs 34.5 ms per 10000-query batch on two GPUs, so the
+        // list-major engine is taken from 8 queries per list on (KB2_TC_MIN_QPL overrides)
+        static const double min_qpl = [] { const char* t = getenv("KB2_TC_MIN_QPL"); return t ? atof(t) : 8.0; }();
+        return (double)nq * nprobe >= min_qpl * (double)nlist;
     }
 
     void
