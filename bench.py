@@ -89,6 +89,16 @@ class ClockSampler:
                                        "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+        # nvidia-smi needs a few hundred ms to start: wait for its first line so that the (tens of ms long) timed region is
+        # sampled from its first step on
+        t0 = time.time()
+        while self.p and time.time() - t0 < 3.0:
+            try:
+                if os.path.getsize(self.f.name) > 0:
+                    break
+            except OSError:
+                pass
+            time.sleep(0.02)
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
@@ -295,11 +305,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks are sampled from the warm-up steps on (same load as the timed steps; the timed region alone lasts ~50 ms)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(args.warmup):
         search_dev(cfg)
     ix.enable_kernel_timing(True)
     kernel_ms, stage_ms, stage_info = [], [], None
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
     if os.environ.get("KB2_PROFILE"):       # ncu --profile-from-start off: capture only the timed steps
         torch.cuda.cudart().cudaProfilerStart()

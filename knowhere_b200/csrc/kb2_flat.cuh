@@ -182,7 +182,8 @@ select_keys_kernel(const float* __restrict__ keys, int64_t ldk, int ncols, int K
 // grid (nq, nsplit), block 256, dynamic smem: slice*4 + 4160 bytes.
 __global__ void __launch_bounds__(256)
 select_keys_hist_kernel(const float* __restrict__ keys, int64_t ldk, int ncols, int K_need, int K_cap,
-                        uint64_t* __restrict__ partial, int slots_per_query, int slot_base, uint32_t pos_base) {
+                        uint64_t* __restrict__ partial, int slots_per_query, int slot_base, uint32_t pos_base,
+                        int allow_fast = 1) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* hist = (uint32_t*)smem_raw;          // 1024 bins (+1)
     uint32_t* ctl = hist + 1032;                   // [0] min [1] max [2] out cursor [3] bstar+1 [4] cum(bstar) [5] shift
@@ -197,20 +198,47 @@ select_keys_hist_kernel(const float* __restrict__ keys, int64_t ldk, int ncols, 
     uint64_t* out = partial + (q * slots_per_query + slot_base + s) * (int64_t)K_cap;
     const uint32_t kInfOrd = f2ord(INFINITY);      // filtered entries: never emitted
     uint32_t lmin = 0xffffffffu, lmax = 0u;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const uint32_t v = f2ord(row[i]);
-        ord[i] = v;
-        if (v < kInfOrd) { lmin = min(lmin, v); lmax = max(lmax, v); }
+    // 128-bit loads when the slice allows it (16 keys per thread at the IVF coarse stage: four LDG.128 in flight instead of
+    // sixteen LDG.32); thread t then owns the keys {4t .. 4t+3} + 1024 j
+    const bool vec = blockDim.x == 256 && (n & 3) == 0 && ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
+    if (vec) {
+        const float4* row4 = reinterpret_cast<const float4*>(row);
+        uint4* ord4 = reinterpret_cast<uint4*>(ord);
+        for (int i = threadIdx.x; i < (n >> 2); i += 256) {
+            const float4 f = __ldg(row4 + i);
+            const uint4 v = make_uint4(f2ord(f.x), f2ord(f.y), f2ord(f.z), f2ord(f.w));
+            ord4[i] = v;
+            if (v.x < kInfOrd) { lmin = min(lmin, v.x); lmax = max(lmax, v.x); }
+            if (v.y < kInfOrd) { lmin = min(lmin, v.y); lmax = max(lmax, v.y); }
+            if (v.z < kInfOrd) { lmin = min(lmin, v.z); lmax = max(lmax, v.z); }
+            if (v.w < kInfOrd) { lmin = min(lmin, v.w); lmax = max(lmax, v.w); }
+        }
+    } else {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint32_t v = f2ord(row[i]);
+            ord[i] = v;
+            if (v < kInfOrd) { lmin = min(lmin, v); lmax = max(lmax, v); }
+        }
     }
+    // Fast path (the IVF coarse stage: best 80 of 4096 keys for each of 10^4 queries).  The keys a thread has just seen form
+    // one of 256 disjoint "chunks" of the slice and `lmin` is that chunk's minimum; a value T with at least K_need chunk minima
+    // <= T is an upper bound of the K_need-th smallest key (K_need distinct keys are <= T).  T is read off a 256-bin
+    // histogram of the chunk minima (256 shared-memory atomics instead of one per key, 8 bins per lane to scan), then every
+    // thread emits its keys <= T: about K_need * (1 + K_need / 256) entries.  If more than K_cap qualify (rare: K_cap is the
+    // next power of two) the level-wise histogram below redoes the row, so the result is always a superset of the K_need best.
+    const bool fast = allow_fast && blockDim.x == 256 && n >= 512 && 2 * K_need <= 256 && K_need <= K_cap;
+    const uint32_t cmin = lmin;   // this thread's chunk minimum (0xffffffff: no finite key)
+    uint32_t cmax = (cmin != 0xffffffffu) ? cmin : 0u;
     for (int i = threadIdx.x; i < 1032; i += blockDim.x) hist[i] = 0;
-    if (threadIdx.x == 0) { ctl[0] = 0xffffffffu; ctl[1] = 0; ctl[2] = 0; }
+    if (threadIdx.x == 0) { ctl[0] = 0xffffffffu; ctl[1] = 0; ctl[2] = 0; ctl[7] = 0; }
     __syncthreads();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
         lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+        cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
     }
-    if ((threadIdx.x & 31) == 0) { atomicMin(&ctl[0], lmin); atomicMax(&ctl[1], lmax); }
+    if ((threadIdx.x & 31) == 0) { atomicMin(&ctl[0], lmin); atomicMax(&ctl[1], lmax); atomicMax(&ctl[7], cmax); }
     __syncthreads();
     const uint32_t vmin = ctl[0], vmax = ctl[1];
     if (vmin > vmax || n <= K_cap) {
@@ -221,6 +249,63 @@ select_keys_hist_kernel(const float* __restrict__ keys, int64_t ldk, int ncols, 
         __syncthreads();
         for (int i = ctl[2] + threadIdx.x; i < K_cap; i += blockDim.x) out[i] = kEmpty;
         return;
+    }
+    if (fast) {
+        // vmin is the smallest chunk minimum, ctl[7] the largest finite one
+        const uint32_t ctop = ctl[7];
+        const uint32_t cspan = ctop - vmin;
+        const int cshift = cspan < 256u ? 0 : (32 - __clz(cspan)) - 8;   // (cspan >> cshift) <= 255
+        if (cmin != 0xffffffffu) atomicAdd(&hist[(cmin - vmin) >> cshift], 1u);
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            uint32_t h[8], sum = 0;
+#pragma unroll
+            for (int t = 0; t < 8; t++) { h[t] = hist[lane * 8 + t]; sum += h[t]; }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const uint32_t excl = incl - sum;
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            if (lane == 0 && total < (uint32_t)K_need) ctl[6] = 0xffffffffu;   // not enough finite chunks: histogram path
+            if (excl < (uint32_t)K_need && incl >= (uint32_t)K_need) {      // exactly one lane when total >= K_need
+                uint32_t run = excl;
+                int b = lane * 8 + 7;
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    run += h[t];
+                    if (run >= (uint32_t)K_need) { b = lane * 8 + t; break; }
+                }
+                // upper edge of bin b, never above the largest chunk minimum
+                const unsigned long long edge = (unsigned long long)vmin + (((unsigned long long)(b + 1)) << cshift) - 1ull;
+                ctl[6] = (uint32_t)min(edge, (unsigned long long)ctop);
+            }
+        }
+        __syncthreads();
+        const uint32_t T = ctl[6];
+        bool done = false;
+        if (T < kInfOrd) {   // CTA-uniform
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const uint32_t v = ord[i];
+                if (v <= T) {
+                    const uint32_t slot = atomicAdd(&ctl[2], 1u);
+                    if (slot < (uint32_t)K_cap) out[slot] = ((uint64_t)v << 32) | (pos_base + (uint32_t)(c0 + i));
+                }
+            }
+            __syncthreads();
+            done = ctl[2] <= (uint32_t)K_cap;
+        }
+        if (done) {
+            for (int i = ctl[2] + threadIdx.x; i < K_cap; i += blockDim.x) out[i] = kEmpty;
+            return;
+        }
+        __syncthreads();   // everybody has read the counter
+        if (threadIdx.x == 0) ctl[2] = 0;
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
     }
     // Level-wise refinement: histogram the keys of the current value range into <= 1024 bins, emit the largest bin prefix
     // that still fits, and if that prefix holds fewer than the keys still needed descend into the crossing bin (its range

@@ -267,7 +267,6 @@ dense_candidates(IndexBase& ix, const float* Q, int64_t nq, const float* X, cons
     KB2_REQUIRE(pl.Ksel <= kMaxK, KB2_INVALID_ARGS, "k too large for the GPU selection kernels (max 1008)");
     pl.S = std::max(2, kMaxSortEntries / pl.Ksel);
     ix.s_partial.ensure((size_t)nq * pl.stride());
-    KB2_CUDA_CHECK(cudaMemsetAsync(ix.s_partial.p, 0xFF, (size_t)nq * pl.stride() * 8, st));
     ix.s_qn.ensure(nq);
     if (metric == KB2_METRIC_L2) {
         row_norms_kernel<<<grid1d(nq * 32, 256), 256, 0, st>>>(Q, nq, d, ix.s_qn.p);
@@ -281,7 +280,16 @@ dense_candidates(IndexBase& ix, const float* Q, int64_t nq, const float* X, cons
     int nsplit = (int)std::min<int64_t>(std::max<int64_t>(1, (2 * kNumSMs + nq - 1) / nq),
                                         std::max<int64_t>(1, chunk / 512));
     nsplit = std::min(nsplit, pl.S - 1);
+    {
+        // empty-entry fill of the slots this call can touch only.  (The whole [nq][S][Ksel] scratch used to be filled: 655 MB
+        // per search at C3's coarse stage, where ONE 1 KB slot per query is used -- ~0.1 ms of a 2.4 ms step.)
+        const int64_t n_chunks = (n + chunk - 1) / chunk;
+        const int64_t slots = std::min<int64_t>(pl.S, n_chunks * nsplit);
+        KB2_CUDA_CHECK(cudaMemset2DAsync(ix.s_partial.p, (size_t)pl.stride() * 8, 0xFF, (size_t)slots * pl.Ksel * 8, (size_t)nq, st));
+    }
     const size_t sel_smem = (size_t)kScanWarps * 2 * pl.Ksel * 8;
+    // chunk-minimum fast path of the wide select: opt-in until measured faster on the GPU (KB2_SELECT_FAST=1)
+    static const bool select_fast = [] { const char* e = getenv("KB2_SELECT_FAST"); return e && atoi(e) != 0; }();
     for (int64_t c0 = 0; c0 < n; c0 += chunk) {
         const int64_t cols = std::min(chunk, n - c0);
         if (pl.used + nsplit > pl.S) {
@@ -298,7 +306,8 @@ dense_candidates(IndexBase& ix, const float* Q, int64_t nq, const float* X, cons
         const size_t hist_smem = (size_t)per_slice * 4 + 4160;
         if (pl.Ksel >= 64 && hist_smem <= (size_t)kMaxDynSmem) {
             select_keys_hist_kernel<<<dim3((unsigned)nq, nsplit), 256, hist_smem, st>>>(
-                ix.s_keys.p, ldk, (int)cols, std::min(k_need, pl.Ksel), pl.Ksel, ix.s_partial.p, pl.S, pl.used, (uint32_t)c0);
+                ix.s_keys.p, ldk, (int)cols, std::min(k_need, pl.Ksel), pl.Ksel, ix.s_partial.p, pl.S, pl.used, (uint32_t)c0,
+                select_fast ? 1 : 0);
         } else {
             select_keys_kernel<<<dim3((unsigned)nq, nsplit), kScanThreads, sel_smem, st>>>(
                 ix.s_keys.p, ldk, (int)cols, pl.Ksel, pl.Ksel, ix.s_partial.p, pl.S, pl.used, (uint32_t)c0);
@@ -856,10 +865,31 @@ struct IvfIndex : IndexBase {
     bool tc_geom_32() const { return G == 3 && M == 48 && dsub == 2; }
     DevBuf<int32_t> s_items2, s_bal_idx, s_bal_idx2;
     DevBuf<uint32_t> s_bal_key, s_bal_key2;
+    // Side stream of the list-major engine: the plan (pairs grouped by list, item table, cost sort: seven small, latency-bound
+    // launches that depend on the coarse result only) runs beside phase A (which fills the SMs with 3 x 128 threads each) and
+    // joins before the filter kernel.  KB2_TC_OVERLAP=0 keeps everything on the handle's stream.
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool
+    plan_overlap() {
+        static const bool on = [] { const char* e = getenv("KB2_TC_OVERLAP"); return !(e && atoi(e) == 0); }();
+        if (!on || getenv("KB2_TC_VERBOSE")) return false;
+        if (!side_stream) {
+            KB2_CUDA_CHECK(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
+            KB2_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+            KB2_CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+        }
+        return true;
+    }
+    ~IvfIndex() override {
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
+        if (side_stream) cudaStreamDestroy(side_stream);
+    }
     // sort the items by descending cost and deal them to the G persistent CTAs in snake order; returns the new item arrays
     int32_t*
-    balance_items(int32_t* items, int64_t max_items, int G_ctas, int tile_cost, int col_cost) {
-        cudaStream_t st = stream;
+    balance_items(int32_t* items, int64_t max_items, int G_ctas, int tile_cost, int col_cost, cudaStream_t st = nullptr) {
+        if (!st) st = stream;
         const char* e = getenv("KB2_TC_BALANCE");
         if (e && atoi(e) == 0) return items;
         s_items2.ensure((size_t)3 * max_items);
@@ -938,6 +968,13 @@ struct IvfIndex : IndexBase {
             marks.emplace_back(name, e);
         };
         mark("start");
+        // the plan below depends on the coarse result only: with the side stream it runs beside phase A
+        const bool ov = plan_overlap();
+        cudaStream_t ps = ov ? side_stream : st;
+        if (ov) {
+            KB2_CUDA_CHECK(cudaEventRecord(ev_fork, st));
+            KB2_CUDA_CHECK(cudaStreamWaitEvent(side_stream, ev_fork, 0));
+        }
         // ---- phase A: exact scan of each query's nearest lists -> upper bound of its k_base-th best key.  A bound taken from ANY
         //      subset of the codes is valid on every rank, so with a communicator the query is handled by the rank that owns
         //      its nearest list (1/world of the batch each; tables only for those) and the bounds are min-reduced.
@@ -1020,25 +1057,30 @@ struct IvfIndex : IndexBase {
         s_qnorm.ensure((size_t)nq);
         s_cand.ensure((size_t)nq * kTcCandCap);
         s_cand_cnt.ensure((size_t)2 * nq);
-        KB2_CUDA_CHECK(cudaMemsetAsync(s_lcount.p, 0, (size_t)2 * nlist * 4, st));
-        KB2_CUDA_CHECK(cudaMemsetAsync(s_cand_cnt.p, 0, (size_t)2 * nq * 4, st));
-        pqtc::count_pairs_kernel<<<grid1d(npairs, 256), 256, 0, st>>>(sp.probe_ids, npairs, list_len.p, s_lcount.p);
+        KB2_CUDA_CHECK(cudaMemsetAsync(s_lcount.p, 0, (size_t)2 * nlist * 4, ps));
+        KB2_CUDA_CHECK(cudaMemsetAsync(s_cand_cnt.p, 0, (size_t)2 * nq * 4, ps));
+        pqtc::count_pairs_kernel<<<grid1d(npairs, 256), 256, 0, ps>>>(sp.probe_ids, npairs, list_len.p, s_lcount.p);
         int32_t* item_list = s_items.p;
         int32_t* item_q0 = s_items.p + max_items;
         int32_t* item_nq = s_items.p + 2 * max_items;
-        pqtc::plan_kernel<<<1, 1024, 0, st>>>(s_lcount.p, (int)nlist, s_lstart.p, item_list, item_q0, item_nq, s_plan_out.p);
+        pqtc::plan_kernel<<<1, 1024, 0, ps>>>(s_lcount.p, (int)nlist, s_lstart.p, item_list, item_q0, item_nq, s_plan_out.p);
         {
             // per tile: decode ~ constant, contraction ~ columns (+ the test K-step)
             // dynamic draw (default): items in descending cost order, CTAs take the next one when free; KB2_TC_SCHED=static
             // keeps the fixed round-robin assignment with the snake deal
-            int32_t* bal = balance_items(s_items.p, max_items, tc_dynamic_sched() ? 0 : kNumSMs, 600, 5);
+            int32_t* bal = balance_items(s_items.p, max_items, tc_dynamic_sched() ? 0 : kNumSMs, 600, 5, ps);
             item_list = bal;
             item_q0 = bal + max_items;
             item_nq = bal + 2 * max_items;
         }
-        pqtc::fill_pairs_kernel<<<grid1d(npairs, 256), 256, 0, st>>>(sp.probe_ids, sp.probe_dis, npairs, nprobe, metric, list_len.p,
+        pqtc::fill_pairs_kernel<<<grid1d(npairs, 256), 256, 0, ps>>>(sp.probe_ids, sp.probe_dis, npairs, nprobe, metric, list_len.p,
                                                                      s_lstart.p, s_lcount.p + nlist, s_pair_q.p, s_pair_base.p);
-        pqtc::prepare_queries_kernel<<<grid1d(nq * 32, 256), 256, 0, st>>>(sp.queries, nq, dim, (__nv_bfloat16*)s_qb16.p, s_qnorm.p);
+        pqtc::prepare_queries_kernel<<<grid1d(nq * 32, 256), 256, 0, ps>>>(sp.queries, nq, dim, (__nv_bfloat16*)s_qb16.p, s_qnorm.p);
+        if (ov) {
+            KB2_CUDA_CHECK(cudaGetLastError());
+            KB2_CUDA_CHECK(cudaEventRecord(ev_join, side_stream));
+            KB2_CUDA_CHECK(cudaStreamWaitEvent(st, ev_join, 0));
+        }
         mark("plan");
         // ---- tensor-core filter + exact re-evaluation of the survivors
         pqtc::Params tp{};
