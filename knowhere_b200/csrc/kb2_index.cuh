@@ -75,6 +75,8 @@ init_kernel_attributes() {
         set((const void*)pqtc::bound_kernel<KB2_METRIC_IP, 32>);
         set((const void*)pqtc::bound_kernel<KB2_METRIC_L2, 64>);
         set((const void*)pqtc::bound_kernel<KB2_METRIC_IP, 64>);
+        set((const void*)pqtc::bound_kernel<KB2_METRIC_L2, 32, 1, 8, 256>);
+        set((const void*)pqtc::bound_kernel<KB2_METRIC_IP, 32, 1, 8, 256>);
         set((const void*)pqtc::bound_kernel<KB2_METRIC_L2, 32, 3, 2>);
         set((const void*)pqtc::bound_kernel<KB2_METRIC_IP, 32, 3, 2>);
         set((const void*)fltc::ivfflat_tc_kernel<KB2_METRIC_L2, 32>);
@@ -288,8 +290,9 @@ dense_candidates(IndexBase& ix, const float* Q, int64_t nq, const float* X, cons
         KB2_CUDA_CHECK(cudaMemset2DAsync(ix.s_partial.p, (size_t)pl.stride() * 8, 0xFF, (size_t)slots * pl.Ksel * 8, (size_t)nq, st));
     }
     const size_t sel_smem = (size_t)kScanWarps * 2 * pl.Ksel * 8;
-    // chunk-minimum fast path of the wide select: opt-in until measured faster on the GPU (KB2_SELECT_FAST=1)
-    static const bool select_fast = [] { const char* e = getenv("KB2_SELECT_FAST"); return e && atoi(e) != 0; }();
+    // chunk-minimum fast path of the wide select (KB2_SELECT_FAST=0: level-wise histogram only).  Measured at C3's coarse stage
+    // (ncu, profiles/r2_summary.md): 0.218 ms -> 0.123 (128-bit loads) -> 0.087 (fast path)
+    static const bool select_fast = [] { const char* e = getenv("KB2_SELECT_FAST"); return !(e && atoi(e) == 0); }();
     for (int64_t c0 = 0; c0 < n; c0 += chunk) {
         const int64_t cols = std::min(chunk, n - c0);
         if (pl.used + nsplit > pl.S) {
@@ -341,7 +344,12 @@ launch_finalize(IndexBase& ix, FinalizeParams fp, int64_t nq) {
         fp.split_small = 256;
     }
     const size_t smem = (size_t)fp.n_sort * 8 + (size_t)fp.k_sel * 16 + (size_t)fp.d * 4 + 16;
-    finalize_kernel<<<(unsigned)nq, 256, smem, ix.stream>>>(fp);
+    unsigned grid = (unsigned)nq;
+    if (fp.split_small > 0 && nq > 8 * kNumSMs) {   // tail pass: a few CTAs per SM walk the rows, most of which they skip
+        grid = 8u * kNumSMs;
+        fp.row_loop_nq = nq;
+    }
+    finalize_kernel<<<grid, 256, smem, ix.stream>>>(fp);
     ix.last.launches++;
     KB2_CUDA_CHECK(cudaGetLastError());
 }
@@ -1002,7 +1010,9 @@ struct IvfIndex : IndexBase {
         {
             const char* e_rw = getenv("KB2_BOUND_ROWW");
             const int roww = (e_rw && atoi(e_rw) == 64) ? 64 : 32;   // measured at C3: 0.37 ms (32, 3 CTAs/SM) vs 0.52 ms (64, 2 CTAs/SM)
-            const size_t smem = pqtc::bound_smem(roww);
+            const size_t smem = pqtc::bound_smem(roww, pqtc::bound_kmax(a_codes, k_base));
+            // measured at C3 (profiles/r2_summary.md): 0.274 ms with 128 threads, 0.234 ms with 256
+            static const int bound_nt = [] { const char* e = getenv("KB2_BOUND_NT"); return e ? atoi(e) : 256; }();
 #define KB2_BOUND_LAUNCH(MM, RW)                                                                                                    \
     pqtc::lut_build_kernel<MM><<<kNumSMs, 256, 0, st>>>(sp.queries, nq, qlist, qcount, pqc.p, s_lut.p);                             \
     mark("lut");                                                                                                                    \
@@ -1012,11 +1022,22 @@ struct IvfIndex : IndexBase {
             if (tc_geom_32()) {
                 // m48 x dsub2: three groups through one in-kernel table each (no [nq][m][256] table in global memory)
 #define KB2_BOUND_LAUNCH3(MM)                                                                                                       \
-    pqtc::bound_kernel<MM, 32, 3, 2><<<bound_grid, 128, pqtc::bound_smem(32), st>>>(                                                \
+    pqtc::bound_kernel<MM, 32, 3, 2><<<bound_grid, 128, pqtc::bound_smem(32, pqtc::bound_kmax(a_codes, k_base)), st>>>(             \
         nullptr, qlist, qcount, nq, sp.probe_ids, sp.probe_dis, nprobe, p0, a_codes, k_base, list_off.p, list_len.p,                \
         (const uint4*)codes.p, t1.p, sp.bitset, rows.p, s_bound.p, d_counter.p + 4, npad, sp.queries, tc_pqc_t.p);
                 if (metric == KB2_METRIC_L2) { KB2_BOUND_LAUNCH3(KB2_METRIC_L2) } else { KB2_BOUND_LAUNCH3(KB2_METRIC_IP) }
 #undef KB2_BOUND_LAUNCH3
+            } else if (bound_nt == 256 && roww == 32) {
+                // 8 warps per CTA over the same tables (default; KB2_BOUND_NT=128 for the 4-warp instance)
+#define KB2_BOUND_LAUNCH256(MM)                                                                                                     \
+    pqtc::lut_build_kernel<MM><<<kNumSMs, 256, 0, st>>>(sp.queries, nq, qlist, qcount, pqc.p, s_lut.p);                             \
+    mark("lut");                                                                                                                    \
+    pqtc::bound_kernel<MM, 32, 1, 8, 256><<<bound_grid, 256, smem, st>>>(s_lut.p, qlist, qcount, nq, sp.probe_ids, sp.probe_dis,     \
+                                                                         nprobe, p0, a_codes, k_base, list_off.p, list_len.p,       \
+                                                                         (const uint4*)codes.p, t1.p, sp.bitset, rows.p, s_bound.p, \
+                                                                         d_counter.p + 4);
+                if (metric == KB2_METRIC_L2) { KB2_BOUND_LAUNCH256(KB2_METRIC_L2) } else { KB2_BOUND_LAUNCH256(KB2_METRIC_IP) }
+#undef KB2_BOUND_LAUNCH256
             } else if (metric == KB2_METRIC_L2) {
                 if (roww == 32) { KB2_BOUND_LAUNCH(KB2_METRIC_L2, 32) } else { KB2_BOUND_LAUNCH(KB2_METRIC_L2, 64) }
             } else {
@@ -1142,7 +1163,9 @@ struct IvfIndex : IndexBase {
 #define KB2_TC_EVAL(MM, GG, DD)                                                                                                      \
     pqtc::exact_eval_kernel<MM, GG, DD><<<(unsigned)nq, 128, 0, st>>>(sp.queries, pqc.p, eval_lut, s_bound.p, (const uint4*)codes.p, npad, t1.p,  \
                                                                       sp.bitset, rows.p, s_cand.p, s_cand_cnt.p, kTcCandCap, tp.qflag,  \
-                                                                      s_logcnt.p + n_logs + 1);
+                                                                      s_logcnt.p + n_logs + 1, eval_trim ? k_base : 0);
+        // trim every survivor row to its k' best inside exact_eval (KB2_EVAL_TRIM=0: off).  Measured at C3: step 1.977 -> 1.957 ms
+        static const bool eval_trim = [] { const char* e = getenv("KB2_EVAL_TRIM"); return !(e && atoi(e) == 0); }();
         const float* eval_lut = (tc_geom_18() && !dist) ? s_lut.p : nullptr;   // tables of the whole batch exist only without a communicator
         if (tc_geom_18()) {
             if (metric == KB2_METRIC_L2) { KB2_TC_EVAL(KB2_METRIC_L2, 1, 8) } else { KB2_TC_EVAL(KB2_METRIC_IP, 1, 8) }

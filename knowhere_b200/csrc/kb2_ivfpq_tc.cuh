@@ -867,10 +867,13 @@ __global__ void __launch_bounds__(128)
 exact_eval_kernel(const float* __restrict__ queries, const float* __restrict__ pqc, const float* __restrict__ lut,
                   const float* __restrict__ bound_of,
                   const uint4* __restrict__ codes, int64_t npad, const float* __restrict__ t1, const uint8_t* __restrict__ bitset,
-                  const int32_t* __restrict__ rows, uint64_t* __restrict__ cand, const uint32_t* __restrict__ cand_cnt, int cap,
-                  uint32_t* __restrict__ qflag, const uint32_t* __restrict__ log_over) {
+                  const int32_t* __restrict__ rows, uint64_t* __restrict__ cand, uint32_t* __restrict__ cand_cnt, int cap,
+                  uint32_t* __restrict__ qflag, const uint32_t* __restrict__ log_over, int k_trim = 0) {
     constexpr int KDIM = 16 * G * DSUB;
     __shared__ __align__(16) float s_q[KDIM];
+    __shared__ uint32_t s_h[256];
+    __shared__ float s_red[8];
+    __shared__ uint32_t s_ctl[2];   // [0] crossing bin, [1] entries kept
     const int64_t q = blockIdx.x;
     if (*log_over) {
         if (threadIdx.x == 0) qflag[q] = 1u;
@@ -890,8 +893,8 @@ exact_eval_kernel(const float* __restrict__ queries, const float* __restrict__ p
     const float bound = bound_of[q];
     const float scale = (METRIC == KB2_METRIC_L2) ? -2.f : -1.f;
     uint64_t* row = cand + q * cap;
-    for (uint32_t i = threadIdx.x; i < n; i += 128) {
-        const uint64_t ent = row[i];
+    // exact key of one logged survivor; returns the packed (key, position) entry, or kEmpty when it is above the bound / filtered
+    auto eval = [&](uint64_t ent, float& key_out) -> uint64_t {
         const uint32_t pos = (uint32_t)ent;
         const float base = __uint_as_float((uint32_t)(ent >> 32));
         float acc0 = (METRIC == KB2_METRIC_L2) ? __ldg(t1 + pos) : 0.f, acc1 = 0.f;
@@ -920,9 +923,148 @@ exact_eval_kernel(const float* __restrict__ queries, const float* __restrict__ p
         const float key = __fadd_rn(base, __fadd_rn(acc0, acc1));
         bool keep = key <= bound;
         if (keep && bitset) keep = !bit_is_set(bitset, rows[pos]);
-        // (Compacting the kept entries to the front of the row was tried: nearly every logged survivor passes the exact test
-        //  -- the filter's margin is small -- so finalize had nothing less to sort, and the staging made this kernel 4x slower.)
-        row[i] = keep ? pack_kp(key, pos) : kEmpty;
+        key_out = keep ? key : INFINITY;
+        return keep ? pack_kp(key, pos) : kEmpty;
+    };
+    if (k_trim > 0 && n <= 512u && n > (uint32_t)k_trim) {   // CTA-uniform
+        // Trim to the k_trim best.  Nearly every logged survivor passes `key <= bound` (the filter's margin is small), and the
+        // bound itself comes from a sample of the codes, so a row holds ~4x the k' entries finalize needs (C3: 146 on average,
+        // rows above 256 went to the CTA-wide finalize).  All exact keys of the row are here: a 256-bin histogram over their
+        // range gives a cut that keeps the k_trim smallest (+ the rest of the crossing bin); the kept entries are compacted
+        // to the front of the row (every thread holds its entries in registers before the first write) and the row's count is
+        // rewritten.  Shared memory stays at ~1.5 KB so that the L1 keeps serving the table gathers.
+        uint64_t pk[4];
+        float kf[4];
+        float lo = INFINITY, hi = -INFINITY;
+        s_h[threadIdx.x] = 0;
+        s_h[threadIdx.x + 128] = 0;
+        if (threadIdx.x == 0) s_ctl[1] = 0;
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+            const uint32_t i = threadIdx.x + it * 128;
+            pk[it] = kEmpty;
+            kf[it] = INFINITY;
+            if (i < n) pk[it] = eval(row[i], kf[it]);
+            if (kf[it] < INFINITY) { lo = fminf(lo, kf[it]); hi = fmaxf(hi, kf[it]); }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if ((threadIdx.x & 31) == 0) { s_red[threadIdx.x >> 5] = lo; s_red[4 + (threadIdx.x >> 5)] = hi; }
+        __syncthreads();   // all entries of the row are in registers from here on
+        lo = fminf(fminf(s_red[0], s_red[1]), fminf(s_red[2], s_red[3]));
+        hi = fmaxf(fmaxf(s_red[4], s_red[5]), fmaxf(s_red[6], s_red[7]));
+        const float sc = (hi > lo) ? 256.f / (hi - lo) : 0.f;
+        int bin[4];
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+            bin[it] = 256;
+            if (kf[it] < INFINITY) {
+                bin[it] = min(255, (int)((kf[it] - lo) * sc));
+                atomicAdd(&s_h[bin[it]], 1u);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            uint32_t h[8], sum = 0;
+#pragma unroll
+            for (int t = 0; t < 8; t++) { h[t] = s_h[lane * 8 + t]; sum += h[t]; }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const uint32_t excl = incl - sum;
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            if (lane == 0 && total < (uint32_t)k_trim) s_ctl[0] = 255u;   // fewer than k_trim valid entries: keep them all
+            if (excl < (uint32_t)k_trim && incl >= (uint32_t)k_trim) {
+                uint32_t run = excl;
+                int b = lane * 8 + 7;
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    run += h[t];
+                    if (run >= (uint32_t)k_trim) { b = lane * 8 + t; break; }
+                }
+                s_ctl[0] = (uint32_t)b;
+            }
+        }
+        __syncthreads();
+        const int bstar = (int)s_ctl[0];
+#pragma unroll
+        for (int it = 0; it < 4; it++)
+            if (bin[it] <= bstar) row[atomicAdd(&s_ctl[1], 1u)] = pk[it];
+        __syncthreads();
+        if (threadIdx.x == 0) cand_cnt[q] = s_ctl[1];
+        return;
+    }
+    float lo = INFINITY, hi = -INFINITY;
+    for (uint32_t i = threadIdx.x; i < n; i += 128) {
+        float kf;
+        row[i] = eval(row[i], kf);
+        if (kf < INFINITY) { lo = fminf(lo, kf); hi = fmaxf(hi, kf); }
+    }
+    if (k_trim > 0 && k_trim <= 96 && n > 512u) {   // CTA-uniform
+        // Long rows (queries in dense regions: up to `cap` logged survivors) are what the CTA-wide finalize spent its time on
+        // (a 2048-entry bitonic sort for the 40 best).  Same cut as above, but the entries stay in global memory: every thread
+        // re-reads the packed exact keys it has just written (its own stores), the kept ones are staged in shared memory
+        // (at most 128, otherwise the row is left as it is) and written to the front of the row after a barrier.
+        __shared__ uint64_t s_stage[128];
+        s_h[threadIdx.x] = 0;
+        s_h[threadIdx.x + 128] = 0;
+        if (threadIdx.x == 0) { s_ctl[0] = 0xffffffffu; s_ctl[1] = 0; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if ((threadIdx.x & 31) == 0) { s_red[threadIdx.x >> 5] = lo; s_red[4 + (threadIdx.x >> 5)] = hi; }
+        __syncthreads();
+        lo = fminf(fminf(s_red[0], s_red[1]), fminf(s_red[2], s_red[3]));
+        hi = fmaxf(fmaxf(s_red[4], s_red[5]), fmaxf(s_red[6], s_red[7]));
+        const float sc = (hi > lo) ? 256.f / (hi - lo) : 0.f;
+        for (uint32_t i = threadIdx.x; i < n; i += 128) {
+            const uint64_t e = row[i];
+            if (e != kEmpty) atomicAdd(&s_h[min(255, (int)((unpack_key(e) - lo) * sc))], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            uint32_t h[8], sum = 0;
+#pragma unroll
+            for (int t = 0; t < 8; t++) { h[t] = s_h[lane * 8 + t]; sum += h[t]; }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const uint32_t excl = incl - sum;
+            if (excl < (uint32_t)k_trim && incl >= (uint32_t)k_trim) {
+                uint32_t run = excl;
+                int b = lane * 8 + 7;
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    run += h[t];
+                    if (run >= (uint32_t)k_trim) { b = lane * 8 + t; break; }
+                }
+                if (run <= 128u) s_ctl[0] = (uint32_t)b;   // entries in bins [0, b]: they fit the staging buffer
+            }
+        }
+        __syncthreads();
+        const uint32_t bstar = s_ctl[0];
+        if (bstar == 0xffffffffu) return;   // fewer than k_trim valid entries, or a crowded crossing bin: leave the row alone
+        for (uint32_t i = threadIdx.x; i < n; i += 128) {
+            const uint64_t e = row[i];
+            if (e != kEmpty && (uint32_t)min(255, (int)((unpack_key(e) - lo) * sc)) <= bstar) s_stage[atomicAdd(&s_ctl[1], 1u)] = e;
+        }
+        __syncthreads();   // every read of the row is done
+        const uint32_t nk = s_ctl[1];
+        for (uint32_t i = threadIdx.x; i < nk; i += 128) row[i] = s_stage[i];
+        if (threadIdx.x == 0) cand_cnt[q] = nk;
     }
 }
 
@@ -1000,15 +1142,22 @@ constexpr int BOUND_KMAX = 6144;    // keys held per query (phase A looks at no 
 constexpr int BOUND_BINS = 1024;
 // ROWW = words per code-value row of the skewed table: 32 (32 KB: lanes i and i+16 share a bank, 2 wavefronts per gather,
 // 3 CTAs/SM) or 64 (64 KB: conflict-free like the LUT kernel, 2 CTAs/SM)
-constexpr size_t bound_smem(int roww) { return (size_t)roww * 1024 + BOUND_KMAX * 4 + BOUND_BINS * 4 + 64; }
+// keys actually held for a launch: the requested number of codes rounded up (C3: 3000 -> 3008 keys = 12 KB instead of 24 KB, i.e.
+// 48 KB per CTA and four CTAs per SM instead of three)
+__host__ __device__ constexpr int bound_kmax(int min_codes, int k_need) {
+    const int want = ((min_codes > k_need ? min_codes : k_need) + 63) & ~63;
+    return want < BOUND_KMAX ? want : BOUND_KMAX;
+}
+constexpr size_t bound_smem(int roww, int kmax = BOUND_KMAX) { return (size_t)roww * 1024 + (size_t)kmax * 4 + BOUND_BINS * 4 + 128; }
 constexpr size_t BOUND_SMEM = bound_smem(32);
 
 // G > 1 (m = 16 G sub-quantizers, e.g. m48 x dsub2): the groups are scanned one after the other through the same 32 KB
 // table -- group g's table is built in the kernel from the query and the transposed codebook `pqc_t`
 // ([g][code value][16 sub-quantizers][dsub], see transpose_codebook_kernel), the partial sums of the earlier groups wait in
 // the shared key array.
-template <int METRIC, int ROWW, int G = 1, int DSUB = 8>
-__global__ void __launch_bounds__(128)
+// NT = threads per CTA: 128 (4 warps) or 256 (8 warps over the same tables: twice the gathers in flight per shared-memory byte)
+template <int METRIC, int ROWW, int G = 1, int DSUB = 8, int NT = 128>
+__global__ void __launch_bounds__(NT)
 bound_kernel(const float* __restrict__ lut, const int32_t* __restrict__ qlist, const uint32_t* __restrict__ qcount, int64_t nq,
              const int64_t* __restrict__ probe_ids, const float* __restrict__ probe_dis,
              int probe_stride, int p0_max, int min_codes, int k_need, const int64_t* __restrict__ list_off,
@@ -1017,12 +1166,16 @@ bound_kernel(const float* __restrict__ lut, const int32_t* __restrict__ qlist, c
              unsigned long long* __restrict__ counters, int64_t npad = 0, const float* __restrict__ queries = nullptr,
              const float* __restrict__ pqc_t = nullptr) {
     static_assert(G == 1 || ROWW == 32, "multi-group phase A uses the 32-word table rows");
+    static_assert(NT == 128 || NT == 256, "bound_kernel block size");
+    constexpr int NW = NT / 32;               // warps
+    constexpr int BPT = BOUND_BINS / NT;      // histogram bins owned by a thread
     // work list: table i / query qlist[i] for i < *qcount (qlist == NULL: query i, i < nq); CTAs stride the list
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* s_lut = (float*)smem_raw;                              // [256][ROWW]
-    float* s_keys = (float*)(smem_raw + ROWW * 1024);             // [BOUND_KMAX]
-    uint32_t* s_hist = (uint32_t*)(s_keys + BOUND_KMAX);          // [BOUND_BINS]
-    float* s_red = (float*)(s_hist + BOUND_BINS);                 // [16]
+    const int key_cap = bound_kmax(min_codes, k_need);            // (the host sizes the shared memory with the same function)
+    float* s_keys = (float*)(smem_raw + ROWW * 1024);             // [key_cap]
+    uint32_t* s_hist = (uint32_t*)(s_keys + key_cap);             // [BOUND_BINS]
+    float* s_red = (float*)(s_hist + BOUND_BINS);                 // [32]: min [0,8) max [8,16) warp sums [16,24)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if ((uint32_t)__cvta_generic_to_shared(smem_raw) != (uint32_t)KB2_SMEM_BASE) {
         if (threadIdx.x == 0 && counters) atomicExch(counters + 1, 0xBAD5ull);   // layout assumption violated: host raises an error
@@ -1043,7 +1196,7 @@ bound_kernel(const float* __restrict__ lut, const int32_t* __restrict__ qlist, c
         float qv[DSUB];
 #pragma unroll
         for (int x = 0; x < DSUB; x++) qv[x] = queries[q * (int64_t)(16 * G * DSUB) + (g * 16 + mm) * DSUB + x];
-        for (int j = jsub; j < 256; j += 8) {
+        for (int j = jsub; j < 256; j += NT / 16) {
             const float* cp = pqc_t + (((size_t)g * 256 + j) * 16 + mm) * DSUB;
             float a = 0.f;
 #pragma unroll
@@ -1056,8 +1209,8 @@ bound_kernel(const float* __restrict__ lut, const int32_t* __restrict__ qlist, c
         // lut[q][j*16 + m] -> s_lut[j*32 + m] and s_lut[j*32 + 16 + m]
         const float4* src = reinterpret_cast<const float4*>(lut + wi * 4096);
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int idx = threadIdx.x + i * 128;       // float4 index: j = idx / 4, m4 = (idx % 4) * 4
+        for (int i = 0; i < 1024 / NT; i++) {
+            const int idx = threadIdx.x + i * NT;        // float4 index: j = idx / 4, m4 = (idx % 4) * 4
             const float4 v = __ldg(src + idx);
             float4* dst = reinterpret_cast<float4*>(s_lut + (idx >> 2) * ROWW + (idx & 3) * 4);
             dst[0] = v;
@@ -1066,7 +1219,7 @@ bound_kernel(const float* __restrict__ lut, const int32_t* __restrict__ qlist, c
         }
     }
     if (g == 0)
-        for (int i = threadIdx.x; i < BOUND_BINS; i += 128) s_hist[i] = 0;
+        for (int i = threadIdx.x; i < BOUND_BINS; i += NT) s_hist[i] = 0;
     __syncthreads();
     // PRMT builds (byte << 8) | (lane16 << 3) ; >> 1 = byte * 128 + lane16 * 4 (row pitch 128 B)
     // ROWW = 64: (byte << 8) | (lane << 2) is the address itself (row pitch 256 B, word lane + s)
@@ -1075,7 +1228,7 @@ bound_kernel(const float* __restrict__ lut, const int32_t* __restrict__ qlist, c
     const bool first_g = (g == 0), last_g = (g == G - 1);
     seen = 0;
     n_tot = 0;
-    const int code_cap = min(BOUND_KMAX, max(min_codes, k_need));   // scan no more than the requested number of codes
+    const int code_cap = min(key_cap, max(min_codes, k_need));   // scan no more than the requested number of codes
     for (int j = 0; j < p0_max && seen < min_codes && n_tot < code_cap; j++) {
         const int64_t l = probe_ids[q * probe_stride + j];
         if (l < 0) continue;
@@ -1101,7 +1254,7 @@ bound_kernel(const float* __restrict__ lut, const int32_t* __restrict__ qlist, c
             }
         };
         load_iter(warp * 64);
-        for (int c0 = warp * 64; c0 < len; c0 += 256) {
+        for (int c0 = warp * 64; c0 < len; c0 += NW * 64) {
             const int relA = c0 + lane, relB = c0 + 32 + lane;
             const bool okA = relA < len, okB = relB < len;
             const uint32_t posA = (uint32_t)(off + relA), posB = (uint32_t)(off + relB);
@@ -1109,7 +1262,7 @@ bound_kernel(const float* __restrict__ lut, const int32_t* __restrict__ qlist, c
             const uint4 wA = nA;
             const uint4 wB = hasB ? nB : nA;
             float a0 = ntA, a1 = 0.f, b0 = hasB ? ntB : 0.f, b1 = 0.f;
-            load_iter(c0 + 256);
+            load_iter(c0 + NW * 64);
             KB2_BOUND_STEP(wA.x, 0, 0, a0)  KB2_BOUND_STEP(wB.x, 0, 0, b0)  KB2_BOUND_STEP(wA.x, 1, 1, a1)  KB2_BOUND_STEP(wB.x, 1, 1, b1)
             KB2_BOUND_STEP(wA.x, 2, 2, a0)  KB2_BOUND_STEP(wB.x, 2, 2, b0)  KB2_BOUND_STEP(wA.x, 3, 3, a1)  KB2_BOUND_STEP(wB.x, 3, 3, b1)
             KB2_BOUND_STEP(wA.y, 0, 4, a0)  KB2_BOUND_STEP(wB.y, 0, 4, b0)  KB2_BOUND_STEP(wA.y, 1, 5, a1)  KB2_BOUND_STEP(wB.y, 1, 5, b1)
@@ -1141,32 +1294,35 @@ bound_kernel(const float* __restrict__ lut, const int32_t* __restrict__ qlist, c
         kmin = fminf(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
         kmax = fmaxf(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
     }
-    if (lane == 0) { s_red[warp] = kmin; s_red[4 + warp] = kmax; }
+    if (lane == 0) { s_red[warp] = kmin; s_red[8 + warp] = kmax; }
     __syncthreads();
-    const float lo = fminf(fminf(s_red[0], s_red[1]), fminf(s_red[2], s_red[3]));
-    const float hi = fmaxf(fmaxf(s_red[4], s_red[5]), fmaxf(s_red[6], s_red[7]));
+    float lo = s_red[0], hi = s_red[8];
+#pragma unroll
+    for (int w = 1; w < NW; w++) { lo = fminf(lo, s_red[w]); hi = fmaxf(hi, s_red[8 + w]); }
     const float scale = (hi > lo) ? (float)BOUND_BINS / (hi - lo) : 0.f;
-    for (int i = threadIdx.x; i < n_tot; i += 128) {
+    for (int i = threadIdx.x; i < n_tot; i += NT) {
         const float kv = s_keys[i];
         if (kv < INFINITY) atomicAdd(&s_hist[min(BOUND_BINS - 1, (int)((kv - lo) * scale))], 1u);
     }
     __syncthreads();
-    // thread t owns bins [8t, 8t+8): exclusive prefix over threads, then the owner of the crossing writes the bound
-    uint32_t mine[8], tsum = 0;
+    // thread t owns bins [BPT t, BPT (t+1)): exclusive prefix over threads, then the owner of the crossing writes the bound
+    uint32_t mine[BPT], tsum = 0;
 #pragma unroll
-    for (int b = 0; b < 8; b++) { mine[b] = s_hist[threadIdx.x * 8 + b]; tsum += mine[b]; }
+    for (int b = 0; b < BPT; b++) { mine[b] = s_hist[threadIdx.x * BPT + b]; tsum += mine[b]; }
     uint32_t incl = tsum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += v;
     }
-    uint32_t* s_wsum = (uint32_t*)(s_red + 8);
+    uint32_t* s_wsum = (uint32_t*)(s_red + 16);
     if (lane == 31) s_wsum[warp] = incl;
     __syncthreads();
     uint32_t before = incl - tsum;
     for (int w = 0; w < warp; w++) before += s_wsum[w];
-    const uint32_t total = s_wsum[0] + s_wsum[1] + s_wsum[2] + s_wsum[3];
+    uint32_t total = 0;
+#pragma unroll
+    for (int w = 0; w < NW; w++) total += s_wsum[w];
     const uint32_t need = (uint32_t)k_need;
     if (total < need || seen < 4 * k_need) {
         if (threadIdx.x == 0) out[q] = INFINITY;   // no (or only a loose) bound: the LUT kernel redoes the query
@@ -1174,10 +1330,10 @@ bound_kernel(const float* __restrict__ lut, const int32_t* __restrict__ qlist, c
         uint32_t cum = before;
         int b = 0;
 #pragma unroll
-        for (int bb = 0; bb < 8; bb++) {
+        for (int bb = 0; bb < BPT; bb++) {
             if (cum < need) { cum += mine[bb]; b = bb; }
         }
-        const float bound = (scale > 0.f) ? lo + ((float)(threadIdx.x * 8 + b) + 1.01f) / scale : hi;
+        const float bound = (scale > 0.f) ? lo + ((float)(threadIdx.x * BPT + b) + 1.01f) / scale : hi;
         out[q] = fmaxf(bound, lo) + (G == 1 ? 4e-7f : 2e-6f) * fmaxf(fabsf(lo), fabsf(hi));
     }
     }   // work list

@@ -239,11 +239,12 @@ struct FinalizeParams {
     const uint32_t* counts;    // optional [nq]: only the first min(counts[q], n_partial) entries of a row are valid ...
     const uint32_t* count_flags;   // ... unless count_flags[q] != 0 (then all n_partial are)
     int split_small;           // > 0: rows with at most this many valid entries were handled by finalize_warp_kernel: skip them
+    int64_t row_loop_nq;       // > 0: finalize_kernel strides the rows [0, row_loop_nq) with its grid (0: row = blockIdx.x)
 };
 
 // dynamic smem: n_sort*8 + k_sel*(4+8+4) + d*4
-__global__ void __launch_bounds__(256)
-finalize_kernel(FinalizeParams p) {
+__device__ __forceinline__ void
+finalize_row(FinalizeParams p, const int64_t q) {   // p by value: the variable-length branch edits its copy
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* s_sort = (uint64_t*)smem_raw;
     int64_t* s_label = (int64_t*)(s_sort + p.n_sort);
@@ -251,7 +252,6 @@ finalize_kernel(FinalizeParams p) {
     uint32_t* s_pos = (uint32_t*)(s_key + p.k_sel);
     float* s_q = (float*)(s_pos + p.k_sel);
 
-    const int64_t q = blockIdx.x;
     const uint64_t* src = p.partial + q * p.partial_stride;
     if (p.counts && !(p.count_flags && p.count_flags[q])) {
         // variable-length row (tensor-core PQ engine): sort only what is there
@@ -416,6 +416,21 @@ finalize_kernel(FinalizeParams p) {
     // k_out > k_sel cannot happen (host guarantees k_sel >= k_out)
 }
 
+// grid = nq (one CTA per query), or -- p.row_loop_nq > 0 -- any grid striding the rows: as the tail pass after
+// finalize_warp_kernel nearly every row is skipped, and launching one 256-thread CTA with ~17 KB of shared memory per query only
+// to exit costs ~1.2 us per CTA and SM (measured at C3: 80 us for 10 000 empty CTAs)
+__global__ void __launch_bounds__(256)
+finalize_kernel(FinalizeParams p) {
+    if (p.row_loop_nq > 0) {
+        for (int64_t q = blockIdx.x; q < p.row_loop_nq; q += gridDim.x) {
+            finalize_row(p, q);
+            __syncthreads();
+        }
+    } else {
+        finalize_row(p, (int64_t)blockIdx.x);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Finalize, small case (n_partial <= 128 candidates): ONE WARP per query, four queries per CTA.  Same contract and the same
 // results as finalize_kernel; the CTA version spends its time in barriers and O(n^2) ranking loops (ncu r2: 12 k warp
@@ -556,48 +571,63 @@ finalize_warp_kernel(FinalizeParams p, int64_t nq) {
         const bool vec4 = (p.d & 3) == 0 && (p.raw16 ? (reinterpret_cast<uintptr_t>(p.raw16) & 7) == 0
                                                       : (reinterpret_cast<uintptr_t>(p.raw) & 15) == 0);
         if (vec4) {
+            // eight candidates per step (two groups of four, 8 lanes per row, 128 B per row and load): the re-rank is a chain of
+            // dependent random-row round trips (L2 for the centroid table, HBM for the refine store), so what sets its duration
+            // is the number of rows in flight per warp.  Per candidate the arithmetic and its order are unchanged.
             const int sub = lane & 7, grp = lane >> 3;
             const float4* q4 = reinterpret_cast<const float4*>(s_q);
-            for (int i0 = 0; i0 < ksel; i0 += 4) {
-                const int i = i0 + grp;
-                const uint32_t pos = (i < ksel) ? s_pos[i] : kNoPos;
-                float acc = 0.f;
-                if (pos != kNoPos) {
-                    const int64_t r = p.raw_by_pos ? (int64_t)pos : (p.rows ? (int64_t)p.rows[pos] : (int64_t)pos);
-                    const float4* x4 = p.raw16 ? nullptr : reinterpret_cast<const float4*>(p.raw + r * (int64_t)p.d);
-                    const uint2* h4 = p.raw16 ? reinterpret_cast<const uint2*>(p.raw16 + r * (int64_t)p.d) : nullptr;
-                    for (int j = sub; j < (p.d >> 2); j += 8) {
-                        float4 xv;
-                        if (x4) {
-                            xv = __ldg(x4 + j);
-                        } else {
-                            const uint2 h = __ldg(h4 + j);
-                            if (p.raw16_kind == 1) {
-                                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h.x));
-                                const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
-                                xv = make_float4(a.x, a.y, b.x, b.y);
-                            } else {
-                                xv = make_float4(__uint_as_float(h.x << 16), __uint_as_float(h.x & 0xffff0000u),
-                                                 __uint_as_float(h.y << 16), __uint_as_float(h.y & 0xffff0000u));
-                            }
-                        }
-                        const float4 qv = q4[j];
-                        if (p.metric == KB2_METRIC_L2) {
-                            float t;
-                            t = qv.x - xv.x; acc = fmaf(t, t, acc);
-                            t = qv.y - xv.y; acc = fmaf(t, t, acc);
-                            t = qv.z - xv.z; acc = fmaf(t, t, acc);
-                            t = qv.w - xv.w; acc = fmaf(t, t, acc);
-                        } else {
-                            acc = fmaf(qv.x, xv.x, acc); acc = fmaf(qv.y, xv.y, acc);
-                            acc = fmaf(qv.z, xv.z, acc); acc = fmaf(qv.w, xv.w, acc);
-                        }
-                    }
+            const int nj = p.d >> 2;
+            auto load4 = [&](const float4* x4, const uint2* h4, int j) -> float4 {
+                if (x4) return __ldg(x4 + j);
+                const uint2 h = __ldg(h4 + j);
+                if (p.raw16_kind == 1) {
+                    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h.x));
+                    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+                    return make_float4(a.x, a.y, b.x, b.y);
                 }
-                acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-                if (sub == 0 && pos != kNoPos) s_key[i] = (p.metric == KB2_METRIC_L2) ? acc : -acc;
+                return make_float4(__uint_as_float(h.x << 16), __uint_as_float(h.x & 0xffff0000u), __uint_as_float(h.y << 16),
+                                   __uint_as_float(h.y & 0xffff0000u));
+            };
+            auto accum = [&](float acc, const float4& qv, const float4& xv) -> float {
+                if (p.metric == KB2_METRIC_L2) {
+                    float t;
+                    t = qv.x - xv.x; acc = fmaf(t, t, acc);
+                    t = qv.y - xv.y; acc = fmaf(t, t, acc);
+                    t = qv.z - xv.z; acc = fmaf(t, t, acc);
+                    t = qv.w - xv.w; acc = fmaf(t, t, acc);
+                } else {
+                    acc = fmaf(qv.x, xv.x, acc); acc = fmaf(qv.y, xv.y, acc);
+                    acc = fmaf(qv.z, xv.z, acc); acc = fmaf(qv.w, xv.w, acc);
+                }
+                return acc;
+            };
+            for (int i0 = 0; i0 < ksel; i0 += 8) {
+                const int ia = i0 + grp, ib = i0 + 4 + grp;
+                const uint32_t pa = (ia < ksel) ? s_pos[ia] : kNoPos;
+                const uint32_t pb = (ib < ksel) ? s_pos[ib] : kNoPos;
+                const int64_t ra = p.raw_by_pos ? (int64_t)pa : (p.rows && pa != kNoPos ? (int64_t)p.rows[pa] : (int64_t)pa);
+                const int64_t rb = p.raw_by_pos ? (int64_t)pb : (p.rows && pb != kNoPos ? (int64_t)p.rows[pb] : (int64_t)pb);
+                const float4* xa = (p.raw16 || pa == kNoPos) ? nullptr : reinterpret_cast<const float4*>(p.raw + ra * (int64_t)p.d);
+                const float4* xb = (p.raw16 || pb == kNoPos) ? nullptr : reinterpret_cast<const float4*>(p.raw + rb * (int64_t)p.d);
+                const uint2* ha = (p.raw16 && pa != kNoPos) ? reinterpret_cast<const uint2*>(p.raw16 + ra * (int64_t)p.d) : nullptr;
+                const uint2* hb = (p.raw16 && pb != kNoPos) ? reinterpret_cast<const uint2*>(p.raw16 + rb * (int64_t)p.d) : nullptr;
+                float acca = 0.f, accb = 0.f;
+                for (int j = sub; j < nj; j += 8) {
+                    float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+                    if (pa != kNoPos) va = load4(xa, ha, j);
+                    if (pb != kNoPos) vb = load4(xb, hb, j);
+                    const float4 qv = q4[j];
+                    if (pa != kNoPos) acca = accum(acca, qv, va);
+                    if (pb != kNoPos) accb = accum(accb, qv, vb);
+                }
+                acca += __shfl_xor_sync(0xffffffffu, acca, 4);
+                accb += __shfl_xor_sync(0xffffffffu, accb, 4);
+                acca += __shfl_xor_sync(0xffffffffu, acca, 2);
+                accb += __shfl_xor_sync(0xffffffffu, accb, 2);
+                acca += __shfl_xor_sync(0xffffffffu, acca, 1);
+                accb += __shfl_xor_sync(0xffffffffu, accb, 1);
+                if (sub == 0 && pa != kNoPos) s_key[ia] = (p.metric == KB2_METRIC_L2) ? acca : -acca;
+                if (sub == 0 && pb != kNoPos) s_key[ib] = (p.metric == KB2_METRIC_L2) ? accb : -accb;
             }
         } else {
             for (int i = 0; i < ksel; i++) {
