@@ -64,6 +64,7 @@ struct HnswSearchParams {
     const int32_t* q_nodes;     // optional: query i is the stored vector of node q_nodes[i]
     const int32_t* node_rank;   // optional: insertion rank of every node; the descent only moves to nodes of rank < rank_limit
     int rank_limit;             //           (= nodes already linked on the beam level)
+    int key8;                   // 1: level-0 expansion evaluates eight fresh neighbours per batch (KB2_HNSW_KEY8, opt-in)
 };
 
 constexpr int kHnswWarps = 4;  // warps (queries in flight) per CTA
@@ -179,6 +180,59 @@ hnsw_key4(const float* __restrict__ vecs, int d, const float* s_q, int32_t v0, i
     k1 = (METRIC == KB2_METRIC_L2) ? a1 : -a1;
     k2 = (METRIC == KB2_METRIC_L2) ? a2 : -a2;
     k3 = (METRIC == KB2_METRIC_L2) ? a3 : -a3;
+}
+
+// eight rows at once, three dimension chunks unrolled: 24 independent 128-bit loads in flight per lane (a 768-d row is six
+// chunks per lane: two round trips per eight rows instead of four with two hnsw_key4 calls).  Per row the arithmetic and
+// its order are those of hnsw_key4, so the keys are bit-identical.
+template <int METRIC>
+__device__ __forceinline__ void
+hnsw_key8(const float* __restrict__ vecs, int d, const float* s_q, const int32_t (&v)[8], int lane, float (&k)[8]) {
+    const float4* x[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) x[r] = reinterpret_cast<const float4*>(vecs + (int64_t)v[r] * d);
+    const float4* q4 = reinterpret_cast<const float4*>(s_q);
+    float acc[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) acc[r] = 0.f;
+    const int nj = d >> 2;
+    auto fold = [&](float& ac, const float4& q, const float4& a) {
+        if (METRIC == KB2_METRIC_L2) {
+            float t;
+            t = q.x - a.x; ac = fmaf(t, t, ac); t = q.y - a.y; ac = fmaf(t, t, ac);
+            t = q.z - a.z; ac = fmaf(t, t, ac); t = q.w - a.w; ac = fmaf(t, t, ac);
+        } else {
+            ac = fmaf(a.x, q.x, ac); ac = fmaf(a.y, q.y, ac);
+            ac = fmaf(a.z, q.z, ac); ac = fmaf(a.w, q.w, ac);
+        }
+    };
+    int j = lane;
+    for (; j + 2 * kWarp < nj; j += 3 * kWarp) {   // three chunks of every row: all 24 loads first
+        float4 a[3][8];
+#pragma unroll
+        for (int u = 0; u < 3; u++)
+#pragma unroll
+            for (int r = 0; r < 8; r++) a[u][r] = ldg_stream_f4(x[r] + j + u * kWarp);
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+            const float4 q = q4[j + u * kWarp];
+#pragma unroll
+            for (int r = 0; r < 8; r++) fold(acc[r], q, a[u][r]);
+        }
+    }
+    for (; j < nj; j += kWarp) {
+        float4 a[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) a[r] = ldg_stream_f4(x[r] + j);
+        const float4 q = q4[j];
+#pragma unroll
+        for (int r = 0; r < 8; r++) fold(acc[r], q, a[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const float t = warp_sum(acc[r]);
+        k[r] = (METRIC == KB2_METRIC_L2) ? t : -t;
+    }
 }
 
 // greedy descent from max_level to level 1 (HnswSearcher.h:116-170,334-356): first strict minimum over the link slots
@@ -318,6 +372,21 @@ hnsw_search_kernel(HnswSearchParams p) {
                 // distances of the fresh neighbours, four (then two) at a time, in slot order
                 float myk = INFINITY;
                 unsigned rem = fm;
+                while (p.key8 && (p.d & 3) == 0 && __popc(rem) >= 8) {
+                    int js[8];
+                    int32_t vs[8];
+                    float ks[8];
+#pragma unroll
+                    for (int r = 0; r < 8; r++) {
+                        js[r] = __ffs(rem) - 1;
+                        rem &= rem - 1;
+                        vs[r] = __shfl_sync(0xffffffffu, v, js[r]);
+                    }
+                    hnsw_key8<METRIC>(p.vecs, p.d, s_q, vs, lane, ks);
+#pragma unroll
+                    for (int r = 0; r < 8; r++)
+                        if (lane == js[r]) myk = ks[r];
+                }
                 while ((p.d & 3) == 0 && __popc(rem) >= 4) {
                     const int j0 = __ffs(rem) - 1; rem &= rem - 1;
                     const int j1 = __ffs(rem) - 1; rem &= rem - 1;
@@ -1493,6 +1562,8 @@ struct HnswIndex : IndexBase {
         p.next_query = d_next.p;
         p.labels = custom_labels ? d_labels.p : nullptr;
         p.stats = d_counter.p;
+        static const int key8 = [] { const char* e = getenv("KB2_HNSW_KEY8"); return (e && atoi(e) != 0) ? 1 : 0; }();
+        p.key8 = key8;
         return p;
     }
 
