@@ -470,6 +470,9 @@ def run_ours(args):
         "roofline": roofline,
     }
 
+    if isinstance(roofline.get("hbm_algorithmic"), dict):
+        # SURVEY 8(d)'s HBM view of the same launch at top level too (per kernel and over the whole step)
+        out["roofline_hbm_algorithmic"] = roofline["hbm_algorithmic"]
     # ---- CPU baseline beside it (rank 0, N=1 only): the reference's own CPU code on the host cores
     if world == 1 and not args.no_cpu_baseline and wl["index"] in ("IVF_PQ", "IVF_FLAT"):
         try:

@@ -19,18 +19,21 @@
 // (tests/test_ivf_gpu.py::test_ivfpq_tc_engine_matches_lut_engine).  Queries whose bound is missing (fewer
 // than K codes in their nearest lists) or whose survivor buffer overflows are flagged and redone by the LUT kernel.
 //
-// sm_100a mapping (one persistent CTA per SM, 288 threads):
+// sm_100a mapping (one persistent CTA per SM, 544 threads, all 512 TMEM columns, <= 219.5 KB of shared memory):
 //   warps 0-7  decoders : (two groups of 4 warps, one per A buffer, so two tiles are decoded concurrently)
-//                         code tile -> A operand [128 codes x 128 dims] bf16 in the no-swizzle K-major UMMA
-//                         layout (16-byte sub-vector of sub-quantizer m = one core-matrix row), via a 64 KB bf16
-//                         copy of the PQ codebooks in shared memory; also stage the B operand (bf16 queries of the
-//                         item, gathered by index) and the per-column thresholds.
-//   warp  16   MMA      : 8 x tcgen05.mma.kind::f16 (M=128, N=16..256, K=16) per tile into one of two 256-column
+//                         code tile -> A operand [128 codes x K] bf16 in the no-swizzle K-major UMMA layout (16-byte
+//                         sub-vector of sub-quantizer m = one core-matrix row), via a bf16 copy of the PQ codebooks in
+//                         shared memory, + the admission-test K-step [-r_hi, -r_mid, -r_lo, 1, 1, 1, 0, 0]; they also stage
+//                         the B operand (bf16 queries of the item, gathered by index, + [1, 1, 1, h_hi, h_mid, h_lo, 0, 0])
+//                         and the per-column meta data, one item ahead.
+//   warp  16   MMA      : K/16 + 1 x tcgen05.mma.kind::f16 (M=128, N=16..256, K=16) per tile into one of two 256-column
 //                         TMEM accumulators; tcgen05.commit releases the A buffer and publishes the accumulator.
-//   warps 8-15 epilogue : (two groups of 4 warps, one per accumulator) tcgen05.ld (32 lanes x 32 columns, double-buffered in registers), 2 instructions per
-//                         (code, query) pair (FADD threshold + FSETP), survivors -> one shared-memory slot
-//                         reservation per thread and tile -> CTA-private survivor log in global memory (plain
-//                         coalesced stores, nothing on the critical path waits for a global round trip).
+//   warps 8-15 epilogue : (two groups of 4 warps, one per accumulator) tcgen05.ld (32 lanes x 32 columns, double-buffered in
+//                         registers); the accumulator holds D = S' + h - r, so "survives" is a clear sign bit: an AND tree
+//                         over the 32 words decides "nothing passes" and only hits are expanded -> one shared-memory slot
+//                         reservation per warp and tile -> the group's private survivor log in global memory (plain
+//                         stores, nothing on the critical path waits for a global round trip).
+//   Items are drawn from a global ticket counter in descending-cost order.
 // Then: scatter_survivors_kernel groups the log by query, exact_eval_kernel recomputes the survivors' keys in fp32.
 // Work item = (list, chunk of <= 256 of the queries probing it); items are laid out by a single-CTA plan kernel
 // from the coarse result (count -> scan -> fill).
@@ -861,7 +864,7 @@ lut_build_kernel(const float* __restrict__ queries, int64_t nq, const int32_t* _
 // added into two interleaved accumulators over the stored byte order, key = base + (acc0 + acc1) — so both engines
 // produce bit-identical keys.  The entries are recomputed from the fp32 codebook (L1/L2 resident) instead of read from
 // a per-query table: no [nq][4096] table has to exist for the queries whose phase A ran on another rank.
-// grid = nq, block = 128.  Survivors above the bound become kEmpty.
+// grid = nq, block = 128.  Survivors above the bound are dropped; with k_trim > 0 the row is cut to its k_trim best and compacted.
 template <int METRIC, int G, int DSUB>
 __global__ void __launch_bounds__(128)
 exact_eval_kernel(const float* __restrict__ queries, const float* __restrict__ pqc, const float* __restrict__ lut,
@@ -1119,7 +1122,7 @@ compact_flags_kernel(const uint32_t* __restrict__ qflag, int64_t nq, int32_t* __
 // row[w] = LUT[w % 16][j]; lane i reads word (i % 16) + s at step s, i.e. sub-quantizer (pos + s) % 16 — the address
 // is one byte-permute plus an immediate (PRMT + LDS + FADD per look-up, like the LUT kernel), lanes i and i+16 share
 // a bank (2 wavefronts per gather).  The keys go to shared memory and the bound is read off a 1024-bin histogram
-// (no top-k structure at all).  grid = nq, block = 128 (4 warps); dynamic smem = BOUND_SMEM (61 KB).
+// (no top-k structure at all).  grid = nq, block = NT (128 or 256); dynamic smem = bound_smem(ROWW, bound_kmax(...)) (48 KB at C3).
 #define KB2_BOUND_STEP(WORD, KB, S, ACC)                                                      \
     {                                                                                         \
         const uint32_t _x = __byte_perm((WORD), lane4, 0x6504u | ((KB) << 4));                \
