@@ -415,7 +415,9 @@ def run_ours(args):
         tpeak, tsrc = peaks_tensor()
         flops = ctr["codes"] * 2.0 * d * 3.0       # 3 x TF32 MMAs per product
         roofline = {"bound": "hbm", "kernel": "ivfflat_tc_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "peak_source": peak_src, "traffic": None, "kernel_ms": k_ms,
+                    "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic, "kernel_ms": k_ms,
+                    "traffic_source": "constant from profiles/scan_kernel_traffic.json (ncu --set full of this kernel at this "
+                                      "workload), not measured in this run",
                     "algorithmic_bytes_per_launch": alg_bytes, "rows_scanned_per_launch": ctr["codes"],
                     "physical_index_bytes": n * d * 4, "physical_frac_of_hbm_peak": n * d * 4 / (k_ms / 1e3) / 1e9 / peak,
                     "tf32_tflops_issued": flops / (k_ms / 1e3) / 1e12,
