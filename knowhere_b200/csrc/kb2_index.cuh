@@ -878,6 +878,7 @@ struct IvfIndex : IndexBase {
     // joins before the filter kernel.  KB2_TC_OVERLAP=0 keeps everything on the handle's stream.
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool side_pending = false;   // forked, not yet joined (only ever observed true after an exception)
     bool
     plan_overlap() {
         static const bool on = [] { const char* e = getenv("KB2_TC_OVERLAP"); return !(e && atoi(e) == 0); }();
@@ -980,8 +981,15 @@ struct IvfIndex : IndexBase {
         const bool ov = plan_overlap();
         cudaStream_t ps = ov ? side_stream : st;
         if (ov) {
+            if (side_pending) {
+                // a previous call left between fork and join (an error was thrown): drain its side-stream work before the
+                // scratch buffers are reused
+                KB2_CUDA_CHECK(cudaStreamSynchronize(side_stream));
+                side_pending = false;
+            }
             KB2_CUDA_CHECK(cudaEventRecord(ev_fork, st));
             KB2_CUDA_CHECK(cudaStreamWaitEvent(side_stream, ev_fork, 0));
+            side_pending = true;
         }
         // ---- phase A: exact scan of each query's nearest lists -> upper bound of its k_base-th best key.  A bound taken from ANY
         //      subset of the codes is valid on every rank, so with a communicator the query is handled by the rank that owns
@@ -1101,6 +1109,7 @@ struct IvfIndex : IndexBase {
             KB2_CUDA_CHECK(cudaGetLastError());
             KB2_CUDA_CHECK(cudaEventRecord(ev_join, side_stream));
             KB2_CUDA_CHECK(cudaStreamWaitEvent(st, ev_join, 0));
+            side_pending = false;
         }
         mark("plan");
         // ---- tensor-core filter + exact re-evaluation of the survivors
