@@ -10,9 +10,11 @@ A "step" = one Search() of the whole 10000-query batch.  `value` times the searc
 outputs resident in HBM; `e2e` times the same call with pinned HOST buffers (H2D of the queries and
 D2H of ids+distances inside the timed region).  Inputs (200 MB of codes, 5 GB of refine vectors) are
 larger than L2, so no explicit flush is needed between iterations.
-N>1: inverted lists are sharded (list l -> rank l % N), every rank scans its lists for the full batch,
-one NCCL all-gather of the per-shard top-k, merge kernel on every rank ("strong" scaling: fixed index
-and batch).  torch is plumbing here (device buffers, RNG, events, torch.distributed).
+N>1: inverted lists are packed onto the ranks by size; the SAME search call is a collective inside the library
+(NCCL communicator owned by libknowhere_b200.so): every rank ranks the centroids for 1/N of the batch (probe
+all-gather), bounds are min-reduced, every rank scans its own lists for the full batch, one all-gather of the
+per-shard top-k + merge kernel ("strong" scaling: fixed index and batch).  The N>1 line carries the proof that the
+merged result equals the unsharded one.  torch is plumbing here (device buffers, RNG, events, torch.distributed).
 """
 import argparse
 import json
